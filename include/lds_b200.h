@@ -1,0 +1,168 @@
+/* lds_b200.h — C ABI of the B200-native Unit2Mel diffusion-sampling library (liblds_b200.so).
+ *
+ * The reference (bfloat16/latent-diffusion-speech) is pure Python/PyTorch and has NO FFI or
+ * plugin interface for this path; the seam is two Python call sites.  Each entry point below
+ * names the reference code it replaces (file:line relative to the reference tree).  A host in
+ * any language binds these with plain pointers and sizes; the shipped Python host
+ * (latent_diffusion_speech_b200/capi.py) binds them with ctypes — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns LDS_OK (0) or a negative lds_status; the message of the last
+ *     failure on the calling thread is available from lds_last_error().
+ *   - all tensor pointers are DEVICE pointers unless a parameter says "host"; tensors are
+ *     contiguous; the caller keeps ownership and must keep them alive until the stream work
+ *     enqueued by the call has completed.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued asynchronously on it; no call synchronises the device except lds_plan,
+ *     lds_finalize_weights and lds_destroy.
+ *   - a handle is bound to one device and is not thread-safe.
+ *   - there is no random number generation inside the library: initial noise and per-step
+ *     DDPM noise are produced by the caller (reference: torch.randn at diffusion.py:207,170,118).
+ */
+#ifndef LDS_B200_H_
+#define LDS_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LDS_API __attribute__((visibility("default")))
+#else
+#define LDS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDS_VERSION 100 /* 0.1.0 */
+#define LDS_MAX_BLOCKS 8
+
+typedef enum {
+  LDS_OK = 0,
+  LDS_ERR_INVALID = -1,   /* bad argument / shape / state */
+  LDS_ERR_CUDA = -2,      /* CUDA runtime failure (sticky per handle) */
+  LDS_ERR_MISSING = -3,   /* a required weight was never loaded */
+  LDS_ERR_UNSUPPORTED = -4
+} lds_status;
+
+typedef enum { LDS_PREC_FP32 = 0, LDS_PREC_BF16 = 1 } lds_precision;
+typedef enum { LDS_DTYPE_F32 = 0, LDS_DTYPE_BF16 = 1, LDS_DTYPE_F16 = 2 } lds_dtype;
+
+/* Sampler kinds.  The per-step scalar coefficients are computed by the host (they are batch
+ * invariant) and handed to lds_plan as rows of LDS_COEF_STRIDE floats:
+ *  LDS_SAMPLER_DPMPP_2M   (diffusion/dpm_solver_pytorch.py:1171-1213,547-576,796-831)
+ *     n_rows = steps+1.  row k: [0]=sigma_k [1]=alpha_k  (x0 = (x - sigma*eps)/alpha at NFE k, k<steps)
+ *                               [2]=sigma_k/sigma_{k-1} [3]=alpha_k*phi1 [4]=0.5*alpha_k*phi1 [5]=1/r0 [6]=order (k>=1)
+ *  LDS_SAMPLER_UNIPC_BH2  (diffusion/uni_pc.py:471-588,606-658)
+ *     n_rows = steps+1.  row k: [0]=sigma_k [1]=alpha_k [2]=sigma_k/sigma_{k-1} [3]=alpha_k*h_phi_1
+ *                               [4]=alpha_k*B_h [5]=r_k [6]=order [7]=use_corrector [8]=rho_c[0] [9]=rho_c[-1] [10]=rho_p
+ *  LDS_SAMPLER_DDPM       (diffusion/diffusion.py:104-121,335-341)
+ *     n_rows = n_nfe.    row j: [0]=sqrt_recip_acp [1]=sqrt_recipm1_acp [2]=post_mean_coef1 [3]=post_mean_coef2
+ *                               [4]=[t>0]*exp(0.5*post_log_var)   (t = k_step-1-j)
+ */
+typedef enum { LDS_SAMPLER_DPMPP_2M = 0, LDS_SAMPLER_UNIPC_BH2 = 1, LDS_SAMPLER_DDPM = 2 } lds_sampler;
+#define LDS_COEF_STRIDE 12
+
+/* Mirrors Unit2Mel.__init__ (diffusion/unit2mel.py:52-71). */
+typedef struct {
+  int32_t input_channel;                 /* units feature dim (1280 for whisper_large_v3) */
+  int32_t n_spk;                         /* <=1: no speaker embedding */
+  int32_t out_dims;                      /* mel / latent bins (128) */
+  int32_t n_layers;                      /* resnets per down block (2) */
+  int32_t n_blocks;                      /* len(block_out_channels) (4) */
+  int32_t block_out_channels[LDS_MAX_BLOCKS];
+  int32_t n_heads;                       /* 8 */
+  int32_t n_hidden;                      /* conditioning width (256) */
+  int32_t norm_groups;                   /* 8 */
+  float acoustic_scale;                  /* data.acoustic_scale */
+  int32_t precision;                     /* lds_precision */
+} lds_config;
+
+typedef struct lds_handle lds_handle;
+
+LDS_API int lds_version(void);
+LDS_API const char* lds_last_error(void);
+
+/* Replaces Unit2Mel.__init__ / UNet1DConditionModel.__init__ (unit2mel.py:52, unet_1d_condition.py:151). */
+LDS_API int lds_create(const lds_config* cfg, int device, lds_handle** out);
+LDS_API void lds_destroy(lds_handle* h);
+
+/* Replaces model.load_state_dict(ckpt['model']) (unit2mel.py:31-33).  `key` is the reference
+ * state_dict key (e.g. "decoder.denoise_fn.conv_in.weight"); data may be a host or device
+ * pointer (copied; the caller keeps ownership).  Schedule buffers / spec_min/max are ignored. */
+LDS_API int lds_load_weight(lds_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype);
+/* Checks that every parameter arrived and repacks them (tap-major conv filters, fused QKV,
+ * value/gate-interleaved GEGLU projection, x/cond split of conv_in). */
+LDS_API int lds_finalize_weights(lds_handle* h);
+
+/* Allocates workspaces for a [B, T] batch and installs the sampler program.
+ *   t_sinusoid : host, [n_nfe, block_out_channels[0]] timestep sinusoids of the n_nfe denoiser
+ *                evaluations in execution order (embeddings.py:24-64; batch invariant)
+ *   coefs      : host, [n_rows, LDS_COEF_STRIDE]
+ * Replaces the per-call construction of NoiseScheduleVP / DPM_Solver / UniPC
+ * (diffusion.py:215-299) and evaluates the time-embedding MLP and all time_emb_proj layers
+ * for every step once (unet_1d_condition.py:841-848, resnet.py:614-617). */
+LDS_API int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t_sinusoid, int n_rows,
+             const float* coefs);
+
+/* cond[B,T,n_hidden] = unit_embed(units[B,T,input_channel]) + spk_embed[spk_id-1]
+ * (unit2mel.py:79-82).  spk_id: device int64 [B] (may be NULL when n_spk<=1). */
+LDS_API int lds_cond(lds_handle* h, const float* units, const int64_t* spk_id, float* cond, void* stream);
+
+/* One denoiser evaluation (UNet1DConditionModel.forward, unet_1d_condition.py:743-1036):
+ * eps[B,out_dims,T] = unet(cat(x[B,out_dims,T], cond^T), t).  t_sinusoid: host [block_out_channels[0]]. */
+LDS_API int lds_denoise(lds_handle* h, const float* x_BMT, const float* cond_BTH, const float* t_sinusoid, float* eps_BMT,
+                void* stream);
+
+/* The sampling loop (GaussianDiffusion.forward, infer branch, diffusion.py:203-343).
+ *   lds_sample_begin : x <- x_init[B,out_dims,T] (the reference's [B,1,M,T] state), binds cond
+ *   lds_sample_steps : runs program steps [k0, k1) ; step_noise[(k1-k0), B, out_dims, T] for DDPM, else NULL
+ *   lds_sample_end   : mel[B,T,out_dims] = x^T / acoustic_scale   (diffusion.py:342-343)
+ *   lds_sample       : begin + all steps + end
+ * Step indices: DPM/UniPC k in [0, steps] (k=0 is the first evaluation), DDPM j in [0, n_nfe). */
+LDS_API int lds_sample_begin(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, void* stream);
+LDS_API int lds_sample_steps(lds_handle* h, int k0, int k1, const float* step_noise, void* stream);
+LDS_API int lds_sample_end(lds_handle* h, float* mel_BTM, void* stream);
+LDS_API int lds_sample(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, const float* step_noise,
+               float* mel_BTM, void* stream);
+LDS_API int lds_num_steps(const lds_handle* h);
+
+/* Introspection used by bench.py / tests. */
+LDS_API int64_t lds_workspace_bytes(const lds_handle* h);
+LDS_API int64_t lds_kernel_launches(const lds_handle* h);   /* kernels launched by this handle so far */
+/* Per-kernel-class device time (CUDA events on the launch stream) of the LAST lds_sample /
+ * lds_denoise when profiling is enabled with lds_set_profiling(h, 1); classes are listed by
+ * lds_profile_class_name.  Returns milliseconds; n launches via lds_profile_class_launches. */
+LDS_API int lds_set_profiling(lds_handle* h, int enabled);
+LDS_API int lds_profile_num_classes(void);
+LDS_API const char* lds_profile_class_name(int cls);
+LDS_API double lds_profile_class_ms(lds_handle* h, int cls);
+LDS_API int64_t lds_profile_class_launches(lds_handle* h, int cls);
+LDS_API double lds_profile_class_flops(lds_handle* h, int cls);   /* algorithmic FLOPs issued in that class */
+LDS_API double lds_profile_class_bytes(lds_handle* h, int cls);   /* algorithmic bytes moved in that class */
+
+
+/* Stateless operator entry points (no handle): the individual kernels behind the sampler, exposed
+ * so that each one can be parity-tested against the PyTorch op it replaces.  Activations are
+ * channels-last [B*T, C] fp32; `w` is [N, taps*cin] with K index = tap*cin + c.
+ *   lds_op_gemm      : F.conv1d k=1/k=3 (stride 1/2, optional fused nearest upsample) and nn.Linear
+ *                      (lora.py:102, resnet.py:157-169,200-221); epilogue 0 none, 1 SiLU, 2 GEGLU
+ *                      (attention.py:299-301; rows of `w`/`bias` interleaved [64 value|64 gate] per 128)
+ *   lds_op_attention : F.scaled_dot_product_attention on fused qkv [B*T,3C] (attention_processor.py:1032)
+ *   lds_op_groupnorm : nn.GroupNorm over the virtual concat [x1|x2] (+ (1+scale)/shift, + SiLU)
+ *                      (resnet.py:597-631); part: scratch of B*ceil(T/32)*groups*3 floats
+ *   lds_op_layernorm : nn.LayerNorm(C) (attention.py:83) */
+LDS_API int lds_op_gemm(const float* A, int a_ld, const float* w, const float* bias, const float* R, int r_ld, int r_div,
+                float* C, int c_ld, int M, int N, int K, int taps, int cin, int t_out, int t_in, int t_conv,
+                int stride, int upsample, float up_scale, int epilogue, void* stream);
+LDS_API int lds_op_attention(const float* qkv, float* out, int B, int T, int C, int heads, void* stream);
+LDS_API int lds_op_groupnorm(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
+                     const float* gamma, const float* beta, const float* scale_shift, int silu, float* part,
+                     float* y, void* stream);
+LDS_API int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDS_B200_H_ */

@@ -1,0 +1,958 @@
+// lds_api.cu — C ABI (include/lds_b200.h), weight repacking, workspace planning and the host-side
+// executor that walks the U-Net / sampler and enqueues the hand-written kernels.
+//
+// Wiring follows the reference's live code path for the configured network (file:line relative
+// to the reference tree):
+//   unet_1d_condition.py:743-1036   conv_in -> down blocks -> mid -> up blocks -> GN/SiLU/conv_out
+//   unet_1d_blocks.py:949-1015,1070-1096,602-623,2069-2130,2181-2206   block order, skip push/pop, concat [hidden, skip]
+//   resnet.py:591-641               GN,SiLU,conv1,(scale,shift)=time_emb_proj(SiLU(emb)),GN,*(1+s)+sh,SiLU,conv2,+shortcut
+//   transformer_1d.py:256-295       GN(1e-6),proj_in,block,proj_out,+residual
+//   attention.py:130-203            LN,attn1,+ ; LN,attn2,+ ; LN,GEGLU-FF,+
+//   diffusion.py:203-343            sampler dispatch (DPM-Solver++ / UniPC / DDPM), final transpose and /acoustic_scale
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lds_b200.h"
+#include "lds_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+enum ProfClass { PC_CONV3 = 0, PC_LINEAR, PC_ATTENTION, PC_GN_STATS, PC_GN_APPLY, PC_LAYERNORM, PC_SOLVER, PC_LAYOUT, PC_COUNT };
+const char* kProfNames[PC_COUNT] = {"conv_k3_gemm", "linear_gemm", "attention", "groupnorm_stats", "groupnorm_apply",
+                                    "layernorm", "solver_update", "layout"};
+
+struct HostTensor {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+};
+
+struct ConvW { const float* w = nullptr; const float* b = nullptr; int cin = 0, cout = 0, taps = 1; };
+struct NormW { const float* g = nullptr; const float* b = nullptr; };
+struct ResnetW {
+  std::string key;
+  int c1 = 0, c2 = 0, cout = 0;      // input = [x1(c1) | x2(c2)]
+  int level = 0;                     // resolution level (frames = T_level)
+  NormW n1, n2;
+  ConvW conv1, conv2;
+  const float* sc_w1 = nullptr; const float* sc_w2 = nullptr; const float* sc_b = nullptr;
+  const float* temb_w = nullptr; const float* temb_b = nullptr;   // [2*cout, temb_dim]
+  int temb_off = 0;                                                // offset into a temb table row
+};
+struct AttnW { const float* qkv = nullptr; const float* out_w = nullptr; const float* out_b = nullptr; };
+struct XfW {
+  std::string key;
+  int C = 0;
+  NormW gn, ln1, ln2, ln3;
+  ConvW proj_in, proj_out;
+  AttnW a1, a2;
+  const float* ff1_w = nullptr; const float* ff1_b = nullptr;      // GEGLU-interleaved [8C, C]
+  const float* ff2_w = nullptr; const float* ff2_b = nullptr;      // [C, 4C]
+};
+
+struct Prof {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> cls;             // class of launch i (time = ev[i+1]-ev[i])
+  size_t used = 0;
+  double ms[PC_COUNT] = {0}, flops[PC_COUNT] = {0}, bytes[PC_COUNT] = {0};
+  int64_t launches[PC_COUNT] = {0};
+  bool resolved = true;
+};
+
+}  // namespace
+
+struct lds_handle {
+  lds_config cfg{};
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, HostTensor> raw;
+  // packed weights (one device arena)
+  float* warena = nullptr;
+  size_t warena_floats = 0;
+  int temb_dim = 0, temb_total = 0;
+  const float *unit_w = nullptr, *unit_b = nullptr, *spk_table = nullptr;
+  const float *time_w1 = nullptr, *time_b1 = nullptr, *time_w2 = nullptr, *time_b2 = nullptr;
+  const float *conv_in_wx = nullptr, *conv_in_wc = nullptr, *conv_in_b = nullptr;
+  std::vector<ResnetW> resnets;     // execution order
+  std::vector<XfW> xfs;             // execution order
+  std::vector<ConvW> downs, ups;
+  NormW norm_out;
+  ConvW conv_out;
+  // plan
+  bool planned = false;
+  int B = 0, T = 0, sampler = 0, n_nfe = 0, n_rows = 0;
+  std::vector<int> Tl;
+  std::vector<float> coefs;
+  float* arena = nullptr;
+  size_t arena_floats = 0;
+  float *temb = nullptr, *temb_single = nullptr, *sin_dev = nullptr, *e1 = nullptr, *e2 = nullptr;
+  float *cond_part = nullptr, *gn_part = nullptr, *spk_rows = nullptr;
+  std::vector<float*> skips;
+  float* hid[3] = {nullptr, nullptr, nullptr};
+  float *norm = nullptr, *tmp = nullptr, *tmp2 = nullptr, *xn = nullptr, *th = nullptr, *qkv = nullptr, *att = nullptr, *ffh = nullptr;
+  float *x = nullptr, *xb = nullptr, *xp = nullptr, *eps = nullptr, *mbuf[3] = {nullptr, nullptr, nullptr};
+  float *io_a = nullptr, *io_b = nullptr;   // channels-last staging for lds_denoise
+  const float* cond_bound = nullptr;
+  int m_cur = 0;                            // index of m0 in mbuf; m1 = (m_cur+2)%3, free = (m_cur+1)%3
+  // bookkeeping
+  int64_t launches = 0;
+  cudaError_t sticky = cudaSuccess;
+  Prof prof;
+};
+
+namespace {
+
+using namespace lds;
+
+#define LDS_CK(h, expr)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess) {                                                                             \
+      (h)->sticky = e__;                                                                                  \
+      return fail(LDS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    }                                                                                                     \
+  } while (0)
+
+#define LDS_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != LDS_OK) return rc__; \
+  } while (0)
+
+// ---- profiling helpers: one event between consecutive launches on the stream ----
+int prof_mark(lds_handle* h, cudaStream_t s) {
+  Prof& p = h->prof;
+  if (p.used == p.pool.size()) {
+    cudaEvent_t e;
+    LDS_CK(h, cudaEventCreate(&e));
+    p.pool.push_back(e);
+  }
+  LDS_CK(h, cudaEventRecord(p.pool[p.used++], s));
+  return LDS_OK;
+}
+
+int launched(lds_handle* h, cudaStream_t s, int cls, double flops, double bytes, cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    h->sticky = e;
+    return fail(LDS_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  }
+  h->launches++;
+  Prof& p = h->prof;
+  if (p.enabled && p.used == p.cls.size() + 1) {   // a start mark exists (set by *_begin / lds_denoise)
+    p.cls.push_back(cls);
+    p.flops[cls] += flops;
+    p.bytes[cls] += bytes;
+    p.launches[cls]++;
+    p.resolved = false;
+    return prof_mark(h, s);
+  }
+  return LDS_OK;
+}
+
+void prof_reset(lds_handle* h) {
+  Prof& p = h->prof;
+  p.used = 0;
+  p.cls.clear();
+  p.resolved = true;
+  for (int i = 0; i < PC_COUNT; ++i) p.ms[i] = p.flops[i] = p.bytes[i] = 0, p.launches[i] = 0;
+}
+
+int prof_resolve(lds_handle* h) {
+  Prof& p = h->prof;
+  if (p.resolved) return LDS_OK;
+  if (p.used) LDS_CK(h, cudaEventSynchronize(p.pool[p.used - 1]));
+  for (size_t i = 0; i + 1 < p.used && i < p.cls.size(); ++i) {
+    float ms = 0.f;
+    LDS_CK(h, cudaEventElapsedTime(&ms, p.pool[i], p.pool[i + 1]));
+    p.ms[p.cls[i]] += ms;
+  }
+  p.resolved = true;
+  return LDS_OK;
+}
+
+// ---- kernel launch wrappers with accounting ----
+int run_gemm(lds_handle* h, cudaStream_t s, const GemmArgs& a) {
+  const double flops = 2.0 * a.M * (double)a.N * a.K;
+  const double nout = (a.epilogue == EPI_GEGLU) ? a.N / 2 : a.N;
+  const double bytes = 4.0 * ((double)a.M * a.cin + (double)a.N * a.K + (double)a.M * nout * (a.R ? 2 : 1));
+  return launched(h, s, a.taps == 3 ? PC_CONV3 : PC_LINEAR, flops, bytes, launch_gemm_f32(a, s), "gemm_f32");
+}
+
+GemmArgs linear_args(const float* A, int M, int K, const float* W, const float* bias, int N, float* C) {
+  GemmArgs g;
+  g.A = A; g.a_ld = K; g.W = W; g.C = C; g.c_ld = N; g.bias = bias;
+  g.M = M; g.N = N; g.K = K; g.taps = 1; g.cin = K;
+  g.t_out = g.t_in = g.t_conv = M > 0 ? M : 1; g.stride = 1;
+  return g;
+}
+
+GemmArgs conv3_args(const float* A, int B, int t_in, int cin, const ConvW& w, float* C, int t_out, int stride) {
+  GemmArgs g;
+  g.A = A; g.a_ld = cin; g.W = w.w; g.C = C; g.c_ld = w.cout; g.bias = w.b;
+  g.M = B * t_out; g.N = w.cout; g.K = 3 * cin; g.taps = 3; g.cin = cin;
+  g.t_out = t_out; g.t_in = t_in; g.t_conv = t_in; g.stride = stride;
+  return g;
+}
+
+int run_gn(lds_handle* h, cudaStream_t s, const float* x1, int c1, const float* x2, int c2, int T, const NormW& n,
+           float eps, const float* ss, int silu, float* y) {
+  const double elems = (double)h->B * T * (c1 + c2);
+  LDS_TRY(launched(h, s, PC_GN_STATS, 0, 4.0 * elems, launch_gn_stats(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, s),
+                   "gn_stats"));
+  return launched(h, s, PC_GN_APPLY, 0, 8.0 * elems,
+                  launch_gn_apply(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, eps, n.g, n.b, ss, silu, y, s),
+                  "gn_apply");
+}
+
+int run_ln(lds_handle* h, cudaStream_t s, const float* x, const NormW& n, int rows, int C, float* y) {
+  return launched(h, s, PC_LAYERNORM, 0, 8.0 * rows * C, launch_layernorm(x, n.g, n.b, 1e-5f, rows, C, y, s), "layernorm");
+}
+
+// resnet.py:591-641
+int run_resnet(lds_handle* h, cudaStream_t s, const ResnetW& r, const float* x1, const float* x2, int T,
+               const float* temb_row, float* out) {
+  const int M = h->B * T, cin = r.c1 + r.c2;
+  LDS_TRY(run_gn(h, s, x1, r.c1, x2, r.c2, T, r.n1, 1e-5f, nullptr, 1, h->norm));
+  LDS_TRY(run_gemm(h, s, conv3_args(h->norm, h->B, T, cin, r.conv1, h->tmp, T, 1)));
+  LDS_TRY(run_gn(h, s, h->tmp, r.cout, nullptr, 0, T, r.n2, 1e-5f, temb_row + r.temb_off, 1, h->tmp2));
+  GemmArgs c2 = conv3_args(h->tmp2, h->B, T, r.cout, r.conv2, out, T, 1);
+  if (r.sc_w1) {
+    LDS_TRY(run_gemm(h, s, linear_args(x1, M, r.c1, r.sc_w1, r.sc_b, r.cout, out)));
+    if (r.c2) {
+      GemmArgs g = linear_args(x2, M, r.c2, r.sc_w2, nullptr, r.cout, out);
+      g.R = out; g.r_ld = r.cout;
+      LDS_TRY(run_gemm(h, s, g));
+    }
+    c2.R = out;
+  } else {
+    c2.R = x1;
+  }
+  c2.r_ld = r.cout;
+  return run_gemm(h, s, c2);
+}
+
+int run_attention(lds_handle* h, cudaStream_t s, const AttnW& a, const NormW& ln, int T, int C) {
+  const int M = h->B * T;
+  LDS_TRY(run_ln(h, s, h->th, ln, M, C, h->xn));
+  LDS_TRY(run_gemm(h, s, linear_args(h->xn, M, C, a.qkv, nullptr, 3 * C, h->qkv)));
+  LDS_TRY(launched(h, s, PC_ATTENTION, 4.0 * h->B * (double)T * T * C, 4.0 * 4.0 * M * C,
+                   launch_attention_f32(h->qkv, h->att, h->B, T, C, h->cfg.n_heads, s), "attention_f32"));
+  GemmArgs o = linear_args(h->att, M, C, a.out_w, a.out_b, C, h->th);
+  o.R = h->th; o.r_ld = C;
+  return run_gemm(h, s, o);
+}
+
+// transformer_1d.py:256-295 + attention.py:130-203
+int run_transformer(lds_handle* h, cudaStream_t s, const XfW& w, const float* x, int T, float* out) {
+  const int M = h->B * T, C = w.C;
+  LDS_TRY(run_gn(h, s, x, C, nullptr, 0, T, w.gn, 1e-6f, nullptr, 0, h->xn));
+  LDS_TRY(run_gemm(h, s, linear_args(h->xn, M, C, w.proj_in.w, w.proj_in.b, C, h->th)));
+  LDS_TRY(run_attention(h, s, w.a1, w.ln1, T, C));
+  LDS_TRY(run_attention(h, s, w.a2, w.ln2, T, C));
+  LDS_TRY(run_ln(h, s, h->th, w.ln3, M, C, h->xn));
+  GemmArgs f1 = linear_args(h->xn, M, C, w.ff1_w, w.ff1_b, 8 * C, h->ffh);
+  f1.epilogue = EPI_GEGLU; f1.c_ld = 4 * C;
+  LDS_TRY(run_gemm(h, s, f1));
+  GemmArgs f2 = linear_args(h->ffh, M, 4 * C, w.ff2_w, w.ff2_b, C, h->th);
+  f2.R = h->th; f2.r_ld = C;
+  LDS_TRY(run_gemm(h, s, f2));
+  GemmArgs po = linear_args(h->th, M, C, w.proj_out.w, w.proj_out.b, C, out);
+  po.R = x; po.r_ld = C;
+  return run_gemm(h, s, po);
+}
+
+float* other_hid(lds_handle* h, const float* a, const float* b) {
+  for (int i = 0; i < 3; ++i)
+    if (h->hid[i] != a && h->hid[i] != b) return h->hid[i];
+  return nullptr;
+}
+
+// One denoiser evaluation on channels-last state x [B*T, out_dims]; eps out [B*T, out_dims].
+int run_unet(lds_handle* h, cudaStream_t s, const float* x, const float* temb_row, float* eps) {
+  const lds_config& c = h->cfg;
+  const int nb = c.n_blocks, L = c.n_layers, B = h->B;
+  const int* ch = c.block_out_channels;
+  size_t ri = 0, xi = 0, si = 0;
+
+  {  // conv_in = conv(x part) + [conv(cond part) + bias] (precomputed per sample call)
+    ConvW w; w.w = h->conv_in_wx; w.b = nullptr; w.cin = c.out_dims; w.cout = ch[0]; w.taps = 3;
+    GemmArgs g = conv3_args(x, B, h->Tl[0], c.out_dims, w, h->skips[0], h->Tl[0], 1);
+    g.R = h->cond_part; g.r_ld = ch[0];
+    LDS_TRY(run_gemm(h, s, g));
+  }
+  const float* cur = h->skips[si++];
+  for (int i = 0; i < nb; ++i) {
+    const bool last = i == nb - 1;
+    const int T = h->Tl[i];
+    for (int j = 0; j < L; ++j) {
+      float* sk = h->skips[si++];
+      if (!last) {
+        float* r_out = other_hid(h, cur, nullptr);
+        LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, nullptr, T, temb_row, r_out));
+        LDS_TRY(run_transformer(h, s, h->xfs[xi++], r_out, T, sk));
+      } else {
+        LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, nullptr, T, temb_row, sk));
+      }
+      cur = sk;
+    }
+    if (!last) {
+      float* sk = h->skips[si++];
+      LDS_TRY(run_gemm(h, s, conv3_args(cur, B, T, ch[i], h->downs[i], sk, h->Tl[i + 1], 2)));
+      cur = sk;
+    }
+  }
+  {  // mid block
+    const int T = h->Tl[nb - 1];
+    float* a = h->hid[0];
+    float* b = h->hid[1];
+    LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, nullptr, T, temb_row, a));
+    LDS_TRY(run_transformer(h, s, h->xfs[xi++], a, T, b));
+    LDS_TRY(run_resnet(h, s, h->resnets[ri++], b, nullptr, T, temb_row, a));
+    cur = a;
+  }
+  for (int i = 0; i < nb; ++i) {
+    const int lvl = nb - 1 - i;
+    const int T = h->Tl[lvl];
+    const bool last = i == nb - 1;
+    for (int j = 0; j < L + 1; ++j) {
+      const float* skip = h->skips[--si];
+      float* r_out = other_hid(h, cur, nullptr);
+      LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, skip, T, temb_row, r_out));
+      cur = r_out;
+      if (i > 0) {
+        float* x_out = other_hid(h, cur, nullptr);
+        LDS_TRY(run_transformer(h, s, h->xfs[xi++], cur, T, x_out));
+        cur = x_out;
+      }
+    }
+    if (!last) {
+      const int t_up = h->Tl[lvl - 1];
+      float* u_out = other_hid(h, cur, nullptr);
+      GemmArgs g = conv3_args(cur, B, T, h->ups[i].cin, h->ups[i], u_out, t_up, 1);
+      g.upsample = 1; g.t_conv = t_up;
+      g.up_scale = (h->T % (1 << (nb - 1)) == 0) ? 0.5f : (float)T / (float)t_up;   // scale_factor=2 vs size= path
+      LDS_TRY(run_gemm(h, s, g));
+      cur = u_out;
+    }
+  }
+  LDS_TRY(run_gn(h, s, cur, ch[0], nullptr, 0, h->Tl[0], h->norm_out, 1e-5f, nullptr, 1, h->norm));
+  return run_gemm(h, s, conv3_args(h->norm, B, h->Tl[0], ch[0], h->conv_out, eps, h->Tl[0], 1));
+}
+
+// time-embedding MLP + every resnet's time_emb_proj for `rows` sinusoid rows (host) -> table [rows, temb_total]
+int run_temb(lds_handle* h, cudaStream_t s, const float* sin_host, int rows, float* table) {
+  const int c0 = h->cfg.block_out_channels[0], D = h->temb_dim;
+  LDS_CK(h, cudaMemcpyAsync(h->sin_dev, sin_host, sizeof(float) * rows * c0, cudaMemcpyHostToDevice, s));
+  GemmArgs g1 = linear_args(h->sin_dev, rows, c0, h->time_w1, h->time_b1, D, h->e1);
+  g1.epilogue = EPI_SILU;
+  LDS_TRY(run_gemm(h, s, g1));
+  GemmArgs g2 = linear_args(h->e1, rows, D, h->time_w2, h->time_b2, D, h->e2);
+  g2.epilogue = EPI_SILU;   // every consumer applies SiLU(emb) first (resnet.py:615-616)
+  LDS_TRY(run_gemm(h, s, g2));
+  for (const ResnetW& r : h->resnets) {
+    GemmArgs g = linear_args(h->e2, rows, D, r.temb_w, r.temb_b, 2 * r.cout, table + r.temb_off);
+    g.c_ld = h->temb_total;
+    LDS_TRY(run_gemm(h, s, g));
+  }
+  return LDS_OK;
+}
+
+const float* need(lds_handle* h, const std::string& key, std::vector<int64_t> shape, int* rc) {
+  auto it = h->raw.find(key);
+  if (it == h->raw.end()) {
+    *rc = fail(LDS_ERR_MISSING, "weight '%s' was not loaded", key.c_str());
+    return nullptr;
+  }
+  if (it->second.shape != shape) {
+    std::string got, want;
+    for (auto d : it->second.shape) got += std::to_string(d) + ",";
+    for (auto d : shape) want += std::to_string(d) + ",";
+    *rc = fail(LDS_ERR_INVALID, "weight '%s' has shape [%s], expected [%s]", key.c_str(), got.c_str(), want.c_str());
+    return nullptr;
+  }
+  return it->second.v.data();
+}
+
+struct Packer {
+  std::vector<float> host;
+  size_t add(const float* src, size_t n) {
+    size_t off = host.size();
+    off = (off + 63) / 64 * 64;       // 256-byte alignment of every tensor
+    host.resize(off + n);
+    if (src) memcpy(host.data() + off, src, n * sizeof(float));
+    return off;
+  }
+};
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int lds_version(void) { return LDS_VERSION; }
+const char* lds_last_error(void) { return g_last_error.c_str(); }
+
+int lds_create(const lds_config* cfg, int device, lds_handle** out) {
+  if (!cfg || !out) return fail(LDS_ERR_INVALID, "null argument");
+  if (cfg->n_blocks < 2 || cfg->n_blocks > LDS_MAX_BLOCKS) return fail(LDS_ERR_INVALID, "n_blocks must be in [2,%d]", LDS_MAX_BLOCKS);
+  if (cfg->precision != LDS_PREC_FP32 && cfg->precision != LDS_PREC_BF16) return fail(LDS_ERR_INVALID, "unknown precision");
+  if (cfg->norm_groups < 1 || cfg->norm_groups > 32) return fail(LDS_ERR_INVALID, "norm_groups must be in [1,32]");
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const int c = cfg->block_out_channels[i];
+    if (c % 64 || c % cfg->norm_groups || c % cfg->n_heads) return fail(LDS_ERR_INVALID, "block_out_channels[%d]=%d must be a multiple of 64, norm_groups and n_heads", i, c);
+    if (i < cfg->n_blocks - 1 || true) {
+      const int d = c / cfg->n_heads;
+      if (d != 32 && d != 48 && d != 64) return fail(LDS_ERR_UNSUPPORTED, "head dim %d (channels %d / heads %d) not in {32,48,64}", d, c, cfg->n_heads);
+    }
+  }
+  if (cfg->out_dims % 16 || cfg->n_hidden % 16 || cfg->input_channel % 16)
+    return fail(LDS_ERR_INVALID, "out_dims, n_hidden and input_channel must be multiples of 16");
+  if (cfg->precision == LDS_PREC_BF16) return fail(LDS_ERR_UNSUPPORTED, "bf16 tensor-core mode is not built in this version");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev)
+    return fail(LDS_ERR_CUDA, "CUDA device %d not available (%s); this library has no CPU fallback", device,
+                e == cudaSuccess ? "index out of range" : cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(LDS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(LDS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  lds_handle* h = new lds_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->temb_dim = 4 * cfg->block_out_channels[0];
+  *out = h;
+  return LDS_OK;
+}
+
+void lds_destroy(lds_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->arena) cudaFree(h->arena);
+  if (h->warena) cudaFree(h->warena);
+  for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
+  delete h;
+}
+
+int lds_load_weight(lds_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype) {
+  if (!h || !key || !data || !shape || ndim < 0 || ndim > 4) return fail(LDS_ERR_INVALID, "bad argument to lds_load_weight");
+  if (h->finalized) return fail(LDS_ERR_INVALID, "weights already finalized");
+  LDS_CK(h, cudaSetDevice(h->device));
+  size_t n = 1;
+  HostTensor t;
+  for (int i = 0; i < ndim; ++i) { n *= (size_t)shape[i]; t.shape.push_back(shape[i]); }
+  t.v.resize(n);
+  if (dtype == LDS_DTYPE_F32) {
+    LDS_CK(h, cudaMemcpy(t.v.data(), data, n * sizeof(float), cudaMemcpyDefault));
+  } else if (dtype == LDS_DTYPE_BF16 || dtype == LDS_DTYPE_F16) {
+    std::vector<uint16_t> tmp(n);
+    LDS_CK(h, cudaMemcpy(tmp.data(), data, n * 2, cudaMemcpyDefault));
+    for (size_t i = 0; i < n; ++i) {
+      if (dtype == LDS_DTYPE_BF16) {
+        uint32_t u = (uint32_t)tmp[i] << 16;
+        memcpy(&t.v[i], &u, 4);
+      } else {
+        __half hv;
+        memcpy(&hv, &tmp[i], 2);
+        t.v[i] = __half2float(hv);
+      }
+    }
+  } else {
+    return fail(LDS_ERR_INVALID, "unknown dtype %d", dtype);
+  }
+  h->raw[key] = std::move(t);
+  return LDS_OK;
+}
+
+int lds_finalize_weights(lds_handle* h) {
+  if (!h) return fail(LDS_ERR_INVALID, "null handle");
+  if (h->finalized) return LDS_OK;
+  LDS_CK(h, cudaSetDevice(h->device));
+  const lds_config& c = h->cfg;
+  const int nb = c.n_blocks, L = c.n_layers, D = h->temb_dim;
+  const int* ch = c.block_out_channels;
+  const std::string P = "decoder.denoise_fn.";
+  Packer pk;
+  int rc = LDS_OK;
+  std::vector<std::pair<const float**, size_t>> fix;   // pointer slots to patch once the arena exists
+  auto put = [&](const float** slot, const float* src, size_t n) { fix.emplace_back(slot, pk.add(src, n)); };
+  auto vec = [&](const float** slot, const std::string& key, int64_t n) {
+    const float* p = need(h, key, {n}, &rc);
+    if (p) put(slot, p, (size_t)n);
+    return p != nullptr;
+  };
+  auto norm = [&](NormW& nw, const std::string& key, int C) { return vec(&nw.g, key + ".weight", C) && vec(&nw.b, key + ".bias", C); };
+  // conv k=3: [cout, cin, 3] -> [cout][tap][cin]
+  auto conv3 = [&](ConvW& w, const std::string& key, int cin, int cout) {
+    const float* src = need(h, key + ".weight", {cout, cin, 3}, &rc);
+    if (!src) return false;
+    std::vector<float> t((size_t)cout * cin * 3);
+    for (int o = 0; o < cout; ++o)
+      for (int i = 0; i < cin; ++i)
+        for (int k = 0; k < 3; ++k) t[((size_t)o * 3 + k) * cin + i] = src[((size_t)o * cin + i) * 3 + k];
+    put(&w.w, t.data(), t.size());
+    w.cin = cin; w.cout = cout; w.taps = 3;
+    return vec(&w.b, key + ".bias", cout);
+  };
+  auto conv1 = [&](ConvW& w, const std::string& key, int cin, int cout) {
+    const float* src = need(h, key + ".weight", {cout, cin, 1}, &rc);
+    if (!src) return false;
+    put(&w.w, src, (size_t)cout * cin);
+    w.cin = cin; w.cout = cout; w.taps = 1;
+    return vec(&w.b, key + ".bias", cout);
+  };
+  auto lin = [&](const float** w, const float** b, const std::string& key, int in, int out) {
+    const float* src = need(h, key + ".weight", {out, in}, &rc);
+    if (!src) return false;
+    put(w, src, (size_t)out * in);
+    return b ? vec(b, key + ".bias", out) : true;
+  };
+  // The descriptor vectors must not reallocate after slots are taken: reserve exact sizes first.
+  const int n_res = nb * L + 2 + nb * (L + 1);
+  const int n_xf = (nb - 1) * L + 1 + (nb - 1) * (L + 1);
+  h->resnets.clear(); h->xfs.clear(); h->downs.clear(); h->ups.clear();
+  h->resnets.reserve(n_res); h->xfs.reserve(n_xf); h->downs.resize(nb); h->ups.resize(nb);
+  int temb_off = 0;
+
+  auto add_resnet = [&](const std::string& key, int c1, int c2, int cout, int level) -> bool {
+    h->resnets.emplace_back();
+    ResnetW& r = h->resnets.back();
+    r.key = key; r.c1 = c1; r.c2 = c2; r.cout = cout; r.level = level;
+    const int cin = c1 + c2;
+    if (!norm(r.n1, key + ".norm1", cin) || !conv3(r.conv1, key + ".conv1", cin, cout) ||
+        !lin(&r.temb_w, &r.temb_b, key + ".time_emb_proj", D, 2 * cout) || !norm(r.n2, key + ".norm2", cout) ||
+        !conv3(r.conv2, key + ".conv2", cout, cout))
+      return false;
+    r.temb_off = temb_off;
+    temb_off += 2 * cout;
+    if (cin != cout) {
+      const float* src = need(h, key + ".conv_shortcut.weight", {cout, cin, 1}, &rc);
+      if (!src) return false;
+      std::vector<float> w1((size_t)cout * c1), w2((size_t)cout * c2);
+      for (int o = 0; o < cout; ++o) {
+        memcpy(&w1[(size_t)o * c1], src + (size_t)o * cin, sizeof(float) * c1);
+        if (c2) memcpy(&w2[(size_t)o * c2], src + (size_t)o * cin + c1, sizeof(float) * c2);
+      }
+      put(&r.sc_w1, w1.data(), w1.size());
+      if (c2) put(&r.sc_w2, w2.data(), w2.size());
+      if (!vec(&r.sc_b, key + ".conv_shortcut.bias", cout)) return false;
+    }
+    return true;
+  };
+  auto add_attn = [&](AttnW& a, const std::string& key, int C) -> bool {
+    const float* q = need(h, key + ".to_q.weight", {C, C}, &rc);
+    const float* k = q ? need(h, key + ".to_k.weight", {C, C}, &rc) : nullptr;
+    const float* v = k ? need(h, key + ".to_v.weight", {C, C}, &rc) : nullptr;
+    if (!v) return false;
+    std::vector<float> t((size_t)3 * C * C);
+    memcpy(t.data(), q, sizeof(float) * C * C);
+    memcpy(t.data() + (size_t)C * C, k, sizeof(float) * C * C);
+    memcpy(t.data() + (size_t)2 * C * C, v, sizeof(float) * C * C);
+    put(&a.qkv, t.data(), t.size());
+    return lin(&a.out_w, &a.out_b, key + ".to_out.0", C, C);
+  };
+  auto add_xf = [&](const std::string& key, int C) -> bool {
+    h->xfs.emplace_back();
+    XfW& w = h->xfs.back();
+    w.key = key; w.C = C;
+    const std::string b = key + ".transformer_blocks.0";
+    if (!norm(w.gn, key + ".norm", C) || !conv1(w.proj_in, key + ".proj_in", C, C) || !norm(w.ln1, b + ".norm1", C) ||
+        !add_attn(w.a1, b + ".attn1", C) || !norm(w.ln2, b + ".norm2", C) || !add_attn(w.a2, b + ".attn2", C) ||
+        !norm(w.ln3, b + ".norm3", C))
+      return false;
+    // GEGLU projection [8C, C]: rows [0,4C) value, [4C,8C) gate -> per 128-row tile [64 value | 64 gate]
+    const float* pw = need(h, b + ".ff.net.0.proj.weight", {8 * C, C}, &rc);
+    const float* pb = pw ? need(h, b + ".ff.net.0.proj.bias", {8 * C}, &rc) : nullptr;
+    if (!pb) return false;
+    std::vector<float> tw((size_t)8 * C * C), tb((size_t)8 * C);
+    for (int t = 0; t < 4 * C / 64; ++t)
+      for (int i = 0; i < 64; ++i) {
+        const int v_src = t * 64 + i, g_src = 4 * C + t * 64 + i;
+        const int v_dst = t * 128 + i, g_dst = t * 128 + 64 + i;
+        memcpy(&tw[(size_t)v_dst * C], pw + (size_t)v_src * C, sizeof(float) * C);
+        memcpy(&tw[(size_t)g_dst * C], pw + (size_t)g_src * C, sizeof(float) * C);
+        tb[v_dst] = pb[v_src];
+        tb[g_dst] = pb[g_src];
+      }
+    put(&w.ff1_w, tw.data(), tw.size());
+    put(&w.ff1_b, tb.data(), tb.size());
+    return lin(&w.ff2_w, &w.ff2_b, b + ".ff.net.2", 4 * C, C) && conv1(w.proj_out, key + ".proj_out", C, C);
+  };
+
+  bool ok = true;
+  // front end (unit2mel.py:54-59)
+  ok = ok && lin(&h->unit_w, &h->unit_b, "unit_embed", c.input_channel, c.n_hidden);
+  if (ok && c.n_spk > 1) {
+    const float* src = need(h, "spk_embed.weight", {c.n_spk, c.n_hidden}, &rc);
+    ok = src != nullptr;
+    if (ok) put(&h->spk_table, src, (size_t)c.n_spk * c.n_hidden);
+  }
+  // conv_in split into the x part and the cond part
+  if (ok) {
+    const int cin = c.out_dims + c.n_hidden;
+    const float* src = need(h, P + "conv_in.weight", {ch[0], cin, 3}, &rc);
+    ok = src != nullptr;
+    if (ok) {
+      std::vector<float> wx((size_t)ch[0] * 3 * c.out_dims), wc((size_t)ch[0] * 3 * c.n_hidden);
+      for (int o = 0; o < ch[0]; ++o)
+        for (int k = 0; k < 3; ++k) {
+          for (int i = 0; i < c.out_dims; ++i) wx[((size_t)o * 3 + k) * c.out_dims + i] = src[((size_t)o * cin + i) * 3 + k];
+          for (int i = 0; i < c.n_hidden; ++i)
+            wc[((size_t)o * 3 + k) * c.n_hidden + i] = src[((size_t)o * cin + c.out_dims + i) * 3 + k];
+        }
+      put(&h->conv_in_wx, wx.data(), wx.size());
+      put(&h->conv_in_wc, wc.data(), wc.size());
+      ok = vec(&h->conv_in_b, P + "conv_in.bias", ch[0]);
+    }
+  }
+  ok = ok && lin(&h->time_w1, &h->time_b1, P + "time_embedding.linear_1", ch[0], D) &&
+       lin(&h->time_w2, &h->time_b2, P + "time_embedding.linear_2", D, D);
+  // down blocks
+  int c_out = ch[0];
+  for (int i = 0; ok && i < nb; ++i) {
+    const int c_in = c_out;
+    c_out = ch[i];
+    const bool last = i == nb - 1;
+    const std::string bk = P + "down_blocks." + std::to_string(i);
+    for (int j = 0; ok && j < L; ++j) {
+      ok = add_resnet(bk + ".resnets." + std::to_string(j), j == 0 ? c_in : c_out, 0, c_out, i);
+      if (ok && !last) ok = add_xf(bk + ".attentions." + std::to_string(j), c_out);
+    }
+    if (ok && !last) ok = conv3(h->downs[i], bk + ".downsamplers.0.conv", c_out, c_out);
+  }
+  // mid block
+  ok = ok && add_resnet(P + "mid_block.resnets.0", ch[nb - 1], 0, ch[nb - 1], nb - 1) && add_xf(P + "mid_block.attentions.0", ch[nb - 1]) &&
+       add_resnet(P + "mid_block.resnets.1", ch[nb - 1], 0, ch[nb - 1], nb - 1);
+  // up blocks (skip channels follow the push order of the down path)
+  if (ok) {
+    std::vector<int> skip_ch;
+    skip_ch.push_back(ch[0]);
+    for (int i = 0; i < nb; ++i) {
+      for (int j = 0; j < L; ++j) skip_ch.push_back(ch[i]);
+      if (i < nb - 1) skip_ch.push_back(ch[i]);
+    }
+    int prev = ch[nb - 1];
+    for (int i = 0; ok && i < nb; ++i) {
+      const int co = ch[nb - 1 - i];
+      const bool last = i == nb - 1;
+      const std::string bk = P + "up_blocks." + std::to_string(i);
+      for (int j = 0; ok && j < L + 1; ++j) {
+        const int sc = skip_ch.back();
+        skip_ch.pop_back();
+        ok = add_resnet(bk + ".resnets." + std::to_string(j), j == 0 ? prev : co, sc, co, nb - 1 - i);
+        if (ok && i > 0) ok = add_xf(bk + ".attentions." + std::to_string(j), co);
+      }
+      if (ok && !last) ok = conv3(h->ups[i], bk + ".upsamplers.0.conv", co, co);
+      prev = co;
+    }
+  }
+  ok = ok && norm(h->norm_out, P + "conv_norm_out", ch[0]) && conv3(h->conv_out, P + "conv_out", ch[0], c.out_dims);
+  if (!ok) {
+    h->resnets.clear(); h->xfs.clear();
+    return rc != LDS_OK ? rc : fail(LDS_ERR_MISSING, "weights incomplete");
+  }
+  h->temb_total = temb_off;
+
+  h->warena_floats = pk.host.size();
+  LDS_CK(h, cudaMalloc(&h->warena, h->warena_floats * sizeof(float)));
+  LDS_CK(h, cudaMemcpy(h->warena, pk.host.data(), h->warena_floats * sizeof(float), cudaMemcpyHostToDevice));
+  for (auto& f : fix) *f.first = h->warena + f.second;
+  h->raw.clear();
+  h->finalized = true;
+  return LDS_OK;
+}
+
+int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t_sinusoid, int n_rows, const float* coefs) {
+  if (!h || !h->finalized) return fail(LDS_ERR_INVALID, "lds_plan: weights not finalized");
+  if (B < 1 || T < 1) return fail(LDS_ERR_INVALID, "lds_plan: B and T must be positive");
+  if (sampler < LDS_SAMPLER_DPMPP_2M || sampler > LDS_SAMPLER_DDPM) return fail(LDS_ERR_INVALID, "unknown sampler %d", sampler);
+  if (n_nfe < 0 || n_rows < 0 || (n_nfe > 0 && !t_sinusoid) || (n_rows > 0 && !coefs)) return fail(LDS_ERR_INVALID, "lds_plan: bad program");
+  if (n_nfe > 0) {
+    if (sampler == LDS_SAMPLER_DDPM ? n_rows != n_nfe : n_rows != n_nfe + 1)
+      return fail(LDS_ERR_INVALID, "lds_plan: n_rows=%d inconsistent with n_nfe=%d for sampler %d", n_rows, n_nfe, sampler);
+  }
+  if ((int64_t)B * T > (1ll << 30)) return fail(LDS_ERR_INVALID, "B*T too large");
+  LDS_CK(h, cudaSetDevice(h->device));
+  LDS_CK(h, cudaDeviceSynchronize());
+  if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
+  h->planned = false;
+  const lds_config& c = h->cfg;
+  const int nb = c.n_blocks, L = c.n_layers;
+  const int* ch = c.block_out_channels;
+  h->B = B; h->T = T; h->sampler = sampler; h->n_nfe = n_nfe; h->n_rows = n_rows;
+  h->coefs.assign(coefs, coefs + (size_t)n_rows * LDS_COEF_STRIDE);
+  h->Tl.assign(nb, T);
+  for (int i = 1; i < nb; ++i) h->Tl[i] = (h->Tl[i - 1] - 1) / 2 + 1;
+
+  // ---- workspace layout ----
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };
+  std::vector<std::pair<float**, size_t>> slots;
+  auto want = [&](float** p, size_t n) { slots.emplace_back(p, take(n)); };
+  const size_t M0 = (size_t)B * T;
+  size_t max_mc = 0, max_cat = 0, max_c = 0;
+  for (int i = 0; i < nb; ++i) {
+    max_mc = std::max(max_mc, (size_t)B * h->Tl[i] * ch[i]);
+    max_c = std::max(max_c, (size_t)ch[i]);
+  }
+  for (int i = 0; i + 1 < nb; ++i) max_mc = std::max(max_mc, (size_t)B * h->Tl[i] * ch[i + 1]);   // upsampler output
+  max_cat = M0 * ch[0];   // conv_norm_out
+  for (const ResnetW& r : h->resnets) {
+    const size_t rows = (size_t)B * h->Tl[r.level];
+    max_cat = std::max(max_cat, rows * (size_t)(r.c1 + r.c2));
+    max_mc = std::max(max_mc, rows * (size_t)r.cout);
+  }
+  (void)max_c;
+  const int rows_t = std::max(1, n_nfe);
+  want(&h->temb, (size_t)rows_t * h->temb_total);
+  want(&h->temb_single, (size_t)h->temb_total);
+  want(&h->sin_dev, (size_t)rows_t * ch[0]);
+  want(&h->e1, (size_t)rows_t * h->temb_dim);
+  want(&h->e2, (size_t)rows_t * h->temb_dim);
+  want(&h->cond_part, M0 * ch[0]);
+  want(&h->spk_rows, (size_t)B * c.n_hidden);
+  want(&h->gn_part, (size_t)B * ((T + GN_ROWS - 1) / GN_ROWS) * c.norm_groups * 3);
+  h->skips.assign(1 + nb * L + (nb - 1), nullptr);
+  {
+    size_t si = 0;
+    want(&h->skips[si++], M0 * ch[0]);
+    for (int i = 0; i < nb; ++i) {
+      for (int j = 0; j < L; ++j) want(&h->skips[si++], (size_t)B * h->Tl[i] * ch[i]);
+      if (i < nb - 1) want(&h->skips[si++], (size_t)B * h->Tl[i + 1] * ch[i]);
+    }
+  }
+  for (int i = 0; i < 3; ++i) want(&h->hid[i], max_mc);
+  want(&h->norm, max_cat);
+  want(&h->tmp, max_mc);
+  want(&h->tmp2, max_mc);
+  want(&h->xn, max_mc);
+  want(&h->th, max_mc);
+  want(&h->qkv, 3 * max_mc);
+  want(&h->att, max_mc);
+  want(&h->ffh, 4 * max_mc);
+  const size_t nx = M0 * c.out_dims;
+  want(&h->x, nx); want(&h->xb, nx); want(&h->xp, nx); want(&h->eps, nx);
+  for (int i = 0; i < 3; ++i) want(&h->mbuf[i], nx);
+  want(&h->io_a, nx); want(&h->io_b, nx);
+  h->arena_floats = off;
+  LDS_CK(h, cudaMalloc(&h->arena, off * sizeof(float)));
+  for (auto& s : slots) *s.first = h->arena + s.second;
+
+  // ---- per-step time conditioning (batch invariant) ----
+  if (n_nfe > 0) {
+    LDS_TRY(run_temb(h, 0, t_sinusoid, n_nfe, h->temb));
+    LDS_CK(h, cudaStreamSynchronize(0));
+  }
+  h->planned = true;
+  return LDS_OK;
+}
+
+int lds_cond(lds_handle* h, const float* units, const int64_t* spk_id, float* cond, void* stream) {
+  if (!h || !h->planned) return fail(LDS_ERR_INVALID, "lds_cond: call lds_plan first");
+  if (!units || !cond) return fail(LDS_ERR_INVALID, "lds_cond: null tensor");
+  if (h->sticky != cudaSuccess) return fail(LDS_ERR_CUDA, "handle is in a failed state: %s", cudaGetErrorString(h->sticky));
+  cudaStream_t s = (cudaStream_t)stream;
+  LDS_CK(h, cudaSetDevice(h->device));
+  const lds_config& c = h->cfg;
+  GemmArgs g = linear_args(units, h->B * h->T, c.input_channel, h->unit_w, h->unit_b, c.n_hidden, cond);
+  if (c.n_spk > 1) {
+    if (!spk_id) return fail(LDS_ERR_INVALID, "lds_cond: spk_id required when n_spk > 1");
+    LDS_TRY(launched(h, s, PC_LAYOUT, 0, 4.0 * h->B * c.n_hidden,
+                     launch_spk_gather(h->spk_table, spk_id, c.n_spk, h->B, c.n_hidden, h->spk_rows, s), "spk_gather"));
+    g.R = h->spk_rows; g.r_ld = c.n_hidden; g.r_div = h->T;
+  }
+  return run_gemm(h, s, g);
+}
+
+static int bind_cond(lds_handle* h, cudaStream_t s, const float* cond) {
+  // cond half of conv_in (+ bias), constant across all denoiser evaluations of a call (diffusion.py:225)
+  const lds_config& c = h->cfg;
+  ConvW w; w.w = h->conv_in_wc; w.b = h->conv_in_b; w.cin = c.n_hidden; w.cout = c.block_out_channels[0]; w.taps = 3;
+  h->cond_bound = cond;
+  return run_gemm(h, s, conv3_args(cond, h->B, h->T, c.n_hidden, w, h->cond_part, h->T, 1));
+}
+
+int lds_denoise(lds_handle* h, const float* x_BMT, const float* cond_BTH, const float* t_sinusoid, float* eps_BMT, void* stream) {
+  if (!h || !h->planned) return fail(LDS_ERR_INVALID, "lds_denoise: call lds_plan first");
+  if (!x_BMT || !cond_BTH || !t_sinusoid || !eps_BMT) return fail(LDS_ERR_INVALID, "lds_denoise: null tensor");
+  if (h->sticky != cudaSuccess) return fail(LDS_ERR_CUDA, "handle is in a failed state: %s", cudaGetErrorString(h->sticky));
+  cudaStream_t s = (cudaStream_t)stream;
+  LDS_CK(h, cudaSetDevice(h->device));
+  const lds_config& c = h->cfg;
+  if (h->prof.enabled) { prof_reset(h); LDS_TRY(prof_mark(h, s)); }
+  // one-row time conditioning; reuse the plan-time scratch (rows >= 1)
+  LDS_TRY(run_temb(h, s, t_sinusoid, 1, h->temb_single));
+  LDS_TRY(bind_cond(h, s, cond_BTH));
+  LDS_TRY(launched(h, s, PC_LAYOUT, 0, 8.0 * h->B * h->T * c.out_dims,
+                   launch_transpose_bct_to_btc(x_BMT, h->io_a, h->B, c.out_dims, h->T, 1.f, s), "transpose"));
+  LDS_TRY(run_unet(h, s, h->io_a, h->temb_single, h->io_b));
+  return launched(h, s, PC_LAYOUT, 0, 8.0 * h->B * h->T * c.out_dims,
+                  launch_transpose_btc_to_bct(h->io_b, eps_BMT, h->B, c.out_dims, h->T, 1.f, s), "transpose");
+}
+
+int lds_num_steps(const lds_handle* h) {
+  if (!h || !h->planned) return 0;
+  return h->n_rows;
+}
+
+int lds_sample_begin(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, void* stream) {
+  if (!h || !h->planned || h->n_nfe <= 0) return fail(LDS_ERR_INVALID, "lds_sample_begin: no sampler program planned");
+  if (!cond_BTH || !x_init_BMT) return fail(LDS_ERR_INVALID, "lds_sample_begin: null tensor");
+  if (h->sticky != cudaSuccess) return fail(LDS_ERR_CUDA, "handle is in a failed state: %s", cudaGetErrorString(h->sticky));
+  cudaStream_t s = (cudaStream_t)stream;
+  LDS_CK(h, cudaSetDevice(h->device));
+  if (h->prof.enabled) { prof_reset(h); LDS_TRY(prof_mark(h, s)); }
+  LDS_TRY(bind_cond(h, s, cond_BTH));
+  h->m_cur = 0;
+  return launched(h, s, PC_LAYOUT, 0, 8.0 * h->B * h->T * h->cfg.out_dims,
+                  launch_transpose_bct_to_btc(x_init_BMT, h->x, h->B, h->cfg.out_dims, h->T, 1.f, s), "transpose");
+}
+
+int lds_sample_steps(lds_handle* h, int k0, int k1, const float* step_noise, void* stream) {
+  if (!h || !h->planned || h->n_nfe <= 0) return fail(LDS_ERR_INVALID, "lds_sample_steps: no sampler program planned");
+  if (k0 < 0 || k1 > h->n_rows || k0 > k1) return fail(LDS_ERR_INVALID, "lds_sample_steps: step range [%d,%d) outside [0,%d)", k0, k1, h->n_rows);
+  if (h->sticky != cudaSuccess) return fail(LDS_ERR_CUDA, "handle is in a failed state: %s", cudaGetErrorString(h->sticky));
+  if (h->sampler == LDS_SAMPLER_DDPM && !step_noise && k1 > k0) return fail(LDS_ERR_INVALID, "lds_sample_steps: DDPM needs step_noise");
+  cudaStream_t s = (cudaStream_t)stream;
+  LDS_CK(h, cudaSetDevice(h->device));
+  const int64_t n = (int64_t)h->B * h->T * h->cfg.out_dims;
+  const double sb = 4.0 * n;
+  const int S = h->n_nfe;   // DPM / UniPC: number of solver steps == number of evaluations
+  for (int k = k0; k < k1; ++k) {
+    const float* c = &h->coefs[(size_t)k * LDS_COEF_STRIDE];
+    float* m0 = h->mbuf[h->m_cur];
+    float* m1 = h->mbuf[(h->m_cur + 2) % 3];
+    float* mfree = h->mbuf[(h->m_cur + 1) % 3];
+    if (h->sampler == LDS_SAMPLER_DDPM) {
+      LDS_TRY(run_unet(h, s, h->x, h->temb + (size_t)k * h->temb_total, h->eps));
+      LDS_TRY(launched(h, s, PC_SOLVER, 0, 4 * sb,
+                       launch_ddpm_step(h->x, h->eps, step_noise + (size_t)(k - k0) * n, c[0], c[1], c[2], c[3], c[4], h->B,
+                                        h->T, h->cfg.out_dims, s), "ddpm_step"));
+      continue;
+    }
+    if (k == 0) {
+      LDS_TRY(run_unet(h, s, h->x, h->temb, h->eps));
+      LDS_TRY(launched(h, s, PC_SOLVER, 0, 3 * sb, launch_x0_pred(h->x, h->eps, c[0], c[1], m0, n, s), "x0_pred"));
+      continue;
+    }
+    if (h->sampler == LDS_SAMPLER_DPMPP_2M) {
+      LDS_TRY(launched(h, s, PC_SOLVER, 0, 4 * sb,
+                       launch_dpm_update(h->x, m0, m1, c[2], c[3], c[4], c[5], (int)c[6], n, s), "dpm_update"));
+      if (k < S) {
+        LDS_TRY(run_unet(h, s, h->x, h->temb + (size_t)k * h->temb_total, h->eps));
+        LDS_TRY(launched(h, s, PC_SOLVER, 0, 3 * sb, launch_x0_pred(h->x, h->eps, c[0], c[1], mfree, n, s), "x0_pred"));
+        h->m_cur = (h->m_cur + 1) % 3;
+      }
+    } else {  // UniPC-bh2
+      const int order = (int)c[6], corrector = (int)c[7];
+      LDS_TRY(launched(h, s, PC_SOLVER, 0, 5 * sb,
+                       launch_unipc_predict(h->x, m0, m1, c[2], c[3], c[4], c[5], c[10], order, h->xb, h->xp, n, s),
+                       "unipc_predict"));
+      if (corrector) {
+        LDS_TRY(run_unet(h, s, h->xp, h->temb + (size_t)k * h->temb_total, h->eps));
+        LDS_TRY(launched(h, s, PC_SOLVER, 0, 3 * sb, launch_x0_pred(h->xp, h->eps, c[0], c[1], mfree, n, s), "x0_pred"));
+        LDS_TRY(launched(h, s, PC_SOLVER, 0, 5 * sb,
+                         launch_unipc_correct(h->xb, m0, m1, mfree, c[4], c[5], c[8], c[9], order, h->x, n, s),
+                         "unipc_correct"));
+        h->m_cur = (h->m_cur + 1) % 3;
+      } else {
+        std::swap(h->x, h->xp);
+      }
+    }
+  }
+  return LDS_OK;
+}
+
+int lds_sample_end(lds_handle* h, float* mel_BTM, void* stream) {
+  if (!h || !h->planned || !mel_BTM) return fail(LDS_ERR_INVALID, "lds_sample_end: bad argument");
+  if (h->sticky != cudaSuccess) return fail(LDS_ERR_CUDA, "handle is in a failed state: %s", cudaGetErrorString(h->sticky));
+  cudaStream_t s = (cudaStream_t)stream;
+  LDS_CK(h, cudaSetDevice(h->device));
+  const int64_t n = (int64_t)h->B * h->T * h->cfg.out_dims;
+  // state is already [B,T,M]; diffusion.py:342-343: transpose (free here) then / acoustic_scale
+  return launched(h, s, PC_LAYOUT, 0, 8.0 * n, launch_div_copy(h->x, mel_BTM, n, h->cfg.acoustic_scale, s), "div_copy");
+}
+
+int lds_sample(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, const float* step_noise, float* mel_BTM, void* stream) {
+  LDS_TRY(lds_sample_begin(h, cond_BTH, x_init_BMT, stream));
+  LDS_TRY(lds_sample_steps(h, 0, h->n_rows, step_noise, stream));
+  return lds_sample_end(h, mel_BTM, stream);
+}
+
+int64_t lds_workspace_bytes(const lds_handle* h) { return h ? (int64_t)((h->arena_floats + h->warena_floats) * sizeof(float)) : 0; }
+int64_t lds_kernel_launches(const lds_handle* h) { return h ? h->launches : 0; }
+
+int lds_set_profiling(lds_handle* h, int enabled) {
+  if (!h) return fail(LDS_ERR_INVALID, "null handle");
+  h->prof.enabled = enabled != 0;
+  prof_reset(h);
+  return LDS_OK;
+}
+int lds_profile_num_classes(void) { return PC_COUNT; }
+const char* lds_profile_class_name(int cls) { return (cls >= 0 && cls < PC_COUNT) ? kProfNames[cls] : ""; }
+double lds_profile_class_ms(lds_handle* h, int cls) {
+  if (!h || cls < 0 || cls >= PC_COUNT || prof_resolve(h) != LDS_OK) return -1.0;
+  return h->prof.ms[cls];
+}
+int64_t lds_profile_class_launches(lds_handle* h, int cls) { return (h && cls >= 0 && cls < PC_COUNT) ? h->prof.launches[cls] : 0; }
+double lds_profile_class_flops(lds_handle* h, int cls) { return (h && cls >= 0 && cls < PC_COUNT) ? h->prof.flops[cls] : 0; }
+double lds_profile_class_bytes(lds_handle* h, int cls) { return (h && cls >= 0 && cls < PC_COUNT) ? h->prof.bytes[cls] : 0; }
+
+
+// ---- stateless operator entry points ----
+static int op_status(cudaError_t e, const char* what) {
+  return e == cudaSuccess ? LDS_OK : fail(LDS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int lds_op_gemm(const float* A, int a_ld, const float* w, const float* bias, const float* R, int r_ld, int r_div, float* C,
+                int c_ld, int M, int N, int K, int taps, int cin, int t_out, int t_in, int t_conv, int stride, int upsample,
+                float up_scale, int epilogue, void* stream) {
+  if (!A || !w || !C || r_div < 1 || t_out < 1 || (taps != 1 && taps != 3)) return fail(LDS_ERR_INVALID, "lds_op_gemm: bad argument");
+  lds::GemmArgs g;
+  g.A = A; g.a_ld = a_ld; g.W = w; g.C = C; g.c_ld = c_ld; g.bias = bias; g.R = R; g.r_ld = r_ld; g.r_div = r_div;
+  g.M = M; g.N = N; g.K = K; g.taps = taps; g.cin = cin; g.t_out = t_out; g.t_in = t_in; g.t_conv = t_conv;
+  g.stride = stride; g.upsample = upsample; g.up_scale = up_scale; g.epilogue = epilogue;
+  return op_status(lds::launch_gemm_f32(g, (cudaStream_t)stream), "lds_op_gemm");
+}
+int lds_op_attention(const float* qkv, float* out, int B, int T, int C, int heads, void* stream) {
+  if (!qkv || !out) return fail(LDS_ERR_INVALID, "lds_op_attention: null tensor");
+  return op_status(lds::launch_attention_f32(qkv, out, B, T, C, heads, (cudaStream_t)stream), "lds_op_attention");
+}
+int lds_op_groupnorm(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps, const float* gamma,
+                     const float* beta, const float* scale_shift, int silu, float* part, float* y, void* stream) {
+  if (!x1 || !gamma || !beta || !part || !y || (c2 > 0 && !x2)) return fail(LDS_ERR_INVALID, "lds_op_groupnorm: null tensor");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = op_status(lds::launch_gn_stats(x1, c1, x2, c2, B, T, groups, part, s), "lds_op_groupnorm(stats)");
+  if (rc != LDS_OK) return rc;
+  return op_status(lds::launch_gn_apply(x1, c1, x2, c2, B, T, groups, part, eps, gamma, beta, scale_shift, silu, y, s),
+                   "lds_op_groupnorm(apply)");
+}
+int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y, void* stream) {
+  if (!x || !gamma || !beta || !y) return fail(LDS_ERR_INVALID, "lds_op_layernorm: null tensor");
+  return op_status(lds::launch_layernorm(x, gamma, beta, eps, rows, C, y, (cudaStream_t)stream), "lds_op_layernorm");
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// lds_kernels.h — launch wrappers of the hand-written sm_100a kernels (internal header).
+// Activations are channels-last: a tensor of a U-Net level is [B*T_l, C] row-major fp32
+// (bf16 for tensor-core operands in LDS_PREC_BF16 mode).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace lds {
+
+enum Epilogue : int { EPI_NONE = 0, EPI_SILU = 1, EPI_GEGLU = 2 };
+
+// C[M,N] = epi( A (*) W^T + bias ) + R.
+//  A: source rows [*, a_ld]; logical K = taps * cin.  taps==1: plain GEMM row m <- source row m.
+//  taps==3: 1-D convolution along time, output row (b,to) reads source frames
+//           u = to*stride - 1 + tap (zero outside [0, t_conv)), where the convolution input is the
+//           source itself (t_conv = t_in) or its nearest-neighbour upsampling to t_conv frames
+//           (src = min(floor(u*up_scale), t_in-1), F.interpolate semantics, resnet.py:157-160).
+//  W: [N, K] row-major, K index = tap*cin + c.
+//  bias: [N].
+//  R (optional): row (m / r_div) of [*, r_ld] is added after the activation (residual / shortcut /
+//                partial sums; r_div = frames per utterance broadcasts one row per utterance).
+//  EPI_GEGLU: W rows are interleaved per 128-column tile as [64 value | 64 gate]; output has N/2 columns.
+struct GemmArgs {
+  const float* A = nullptr; int a_ld = 0;
+  const float* W = nullptr;
+  float* C = nullptr; int c_ld = 0;
+  const float* bias = nullptr;
+  const float* R = nullptr; int r_ld = 0; int r_div = 1;
+  int M = 0, N = 0, K = 0;
+  int taps = 1, cin = 0;
+  int t_out = 1, t_in = 1, t_conv = 1, stride = 1, upsample = 0; float up_scale = 1.f;
+  int epilogue = EPI_NONE;
+};
+cudaError_t launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
+
+// Flash-style self-attention on a fused QKV buffer [B*T, 3C]: head h uses columns
+// [h*d,(h+1)*d) of each C-wide third.  out [B*T, C].  softmax(q k^T / sqrt(d)) v, no mask.
+cudaError_t launch_attention_f32(const float* qkv, float* out, int B, int T, int C, int heads, cudaStream_t s);
+
+// GroupNorm over a (virtually concatenated) channels-last tensor [x1 | x2].
+//  stats : partial (count, mean, M2) per (b, chunk of GN_ROWS frames, group) -> part[B][nchunk][G][3]
+//  apply : y = GN(x)*gamma+beta ; optional y = y*(1+scale[c])+shift[c] (ss = [scale(C) | shift(C)]); optional SiLU
+constexpr int GN_ROWS = 32;
+cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float* part,
+                            cudaStream_t s);
+cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups,
+                            const float* part, float eps, const float* gamma, const float* beta, const float* ss,
+                            int silu, float* y, cudaStream_t s);
+
+// LayerNorm over the last dim of [rows, C].
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
+                             cudaStream_t s);
+
+// [B, C, T] <-> [B, T, C] tiled transposes; `scale` multiplies on the way.
+cudaError_t launch_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, float scale, cudaStream_t s);
+cudaError_t launch_transpose_btc_to_bct(const float* in, float* out, int B, int C, int T, float scale, cudaStream_t s);
+cudaError_t launch_div_copy(const float* in, float* out, int64_t n, float divisor, cudaStream_t s);
+cudaError_t launch_silu(const float* in, float* out, int64_t n, cudaStream_t s);
+// out[b][:] = table[idx[b]-1][:]   (nn.Embedding gather of spk_embed(spk_id - 1), unit2mel.py:82)
+cudaError_t launch_spk_gather(const float* table, const int64_t* idx, int n_rows, int B, int H, float* out,
+                              cudaStream_t s);
+
+// Solver updates on channels-last state tensors of n = B*T*M elements (coefficient rows: lds_b200.h).
+// x0 prediction: m = (x - sigma*eps)/alpha.
+cudaError_t launch_x0_pred(const float* x, const float* eps, float sigma, float alpha, float* m, int64_t n, cudaStream_t s);
+// DPM-Solver++: order 1: x = cx*x - cm*m0 ; order 2: x = cx*x - cm*m0 - hcm*(ir0*(m0-m1))
+cudaError_t launch_dpm_update(float* x, const float* m0, const float* m1, float cx, float cm, float hcm, float ir0,
+                              int order, int64_t n, cudaStream_t s);
+// UniPC predictor: xb = cx*x - cmE*m0 ; xp = xb - aB*(rho_p*((m1-m0)/rk)) (order 2) | xb (order 1)
+cudaError_t launch_unipc_predict(const float* x, const float* m0, const float* m1, float cx, float cmE, float aB,
+                                 float rk, float rho_p, int order, float* xb, float* xp, int64_t n, cudaStream_t s);
+// UniPC corrector: x = xb - aB*(rho_c0*((m1-m0)/rk) + rho_c1*(mt-m0))  (order 1: the first term is absent)
+cudaError_t launch_unipc_correct(const float* xb, const float* m0, const float* m1, const float* mt, float aB, float rk,
+                                 float rho_c0, float rho_c1, int order, float* x, int64_t n, cudaStream_t s);
+// DDPM ancestral step; noise is in the reference layout [B, M, T] and is transposed on the fly.
+cudaError_t launch_ddpm_step(float* x, const float* eps, const float* noise_BMT, float c_recip, float c_recipm1,
+                             float pm1, float pm2, float sig, int B, int T, int M, cudaStream_t s);
+
+}  // namespace lds

@@ -1,0 +1,195 @@
+// norm.cu — GroupNorm (statistics + fused affine / scale-shift / SiLU apply) and LayerNorm on
+// channels-last activations.  HBM-bound kernels: float4 accesses, warp-shuffle / shared-memory
+// reductions, Chan/Welford merging of (count, mean, M2) so that variance never suffers the
+// E[x^2]-E[x]^2 cancellation (activations reach |x| ~ 1e2 with random-init weights).
+//
+// Reference ops replaced:
+//   nn.GroupNorm(8, C, eps)                resnet.py:536,557 ; transformer_1d.py:134 ; unet_1d_condition.py:546
+//   h*(1+scale)+shift, SiLU                resnet.py:597-631
+//   torch.cat([hidden, skip], dim=1)       unet_1d_blocks.py:2084,2186  (virtual: two source pointers)
+//   nn.LayerNorm(C)                        attention.py:83,102,118
+#include "lds_kernels.h"
+
+namespace lds {
+namespace {
+
+struct Wf { float n, mean, m2; };
+
+__device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
+  if (b.n == 0.f) return a;
+  if (a.n == 0.f) return b;
+  const float n = a.n + b.n;
+  const float d = b.mean - a.mean;
+  const float f = b.n / n;
+  Wf r;
+  r.n = n;
+  r.mean = a.mean + d * f;
+  r.m2 = a.m2 + b.m2 + d * d * a.n * f;
+  return r;
+}
+
+__device__ __forceinline__ Wf wf_of4(float4 v) {
+  const float mean = (v.x + v.y + v.z + v.w) * 0.25f;
+  const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+  Wf r;
+  r.n = 4.f; r.mean = mean; r.m2 = a * a + b * b + c * c + d * d;
+  return r;
+}
+
+__device__ __forceinline__ float4 load_cat(const float* x1, int c1, const float* x2, int c2, size_t row, int c) {
+  // channel c of the virtual concat [x1 | x2]; c and c1 are multiples of 4
+  return (c < c1) ? __ldg(reinterpret_cast<const float4*>(x1 + row * c1 + c))
+                  : __ldg(reinterpret_cast<const float4*>(x2 + row * c2 + (c - c1)));
+}
+
+// grid (nchunk, B); block = (C/4) * rpar threads, thread (v, r) owns channel quad v and frames r, r+rpar, ...
+__global__ void gn_stats_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2, int T,
+                                int groups, int rpar, float* __restrict__ part) {
+  extern __shared__ float sh[];  // [nthreads][3]
+  const int C = c1 + c2, V = C >> 2, cg = C / groups;
+  const int v = threadIdx.x % V, r0 = threadIdx.x / V;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int t0 = chunk * GN_ROWS, t1 = min(t0 + GN_ROWS, T);
+  Wf acc{0.f, 0.f, 0.f};
+  if (r0 < rpar) {
+    for (int t = t0 + r0; t < t1; t += rpar) acc = wf_merge(acc, wf_of4(load_cat(x1, c1, x2, c2, (size_t)b * T + t, v * 4)));
+  }
+  sh[threadIdx.x * 3 + 0] = acc.n; sh[threadIdx.x * 3 + 1] = acc.mean; sh[threadIdx.x * 3 + 2] = acc.m2;
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x, vq = cg >> 2;  // quads per group
+    Wf tot{0.f, 0.f, 0.f};
+    for (int r = 0; r < rpar; ++r)
+      for (int q = 0; q < vq; ++q) {
+        const int th = r * V + g * vq + q;
+        tot = wf_merge(tot, Wf{sh[th * 3], sh[th * 3 + 1], sh[th * 3 + 2]});
+      }
+    float* dst = part + (((size_t)b * gridDim.x + chunk) * groups + g) * 3;
+    dst[0] = tot.n; dst[1] = tot.mean; dst[2] = tot.m2;
+  }
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+
+// grid (nchunk, B), 256 threads; each thread handles float4s of the [GN_ROWS, C] slab.
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2,
+                                                       int c2, int T, int groups, const float* __restrict__ part,
+                                                       float eps, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ ss,
+                                                       int silu, float* __restrict__ y) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int C = c1 + c2, V = C >> 2, cg = C / groups;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  if (threadIdx.x < groups) {
+    Wf tot{0.f, 0.f, 0.f};
+    const float* src = part + ((size_t)b * nchunk * groups + threadIdx.x) * 3;
+    for (int c = 0; c < nchunk; ++c, src += groups * 3) tot = wf_merge(tot, Wf{src[0], src[1], src[2]});
+    s_mean[threadIdx.x] = tot.mean;
+    s_rstd[threadIdx.x] = rsqrtf(tot.m2 / tot.n + eps);
+  }
+  __syncthreads();
+  const int t0 = chunk * GN_ROWS, rows = min(GN_ROWS, T - t0);
+  for (int e = threadIdx.x; e < rows * V; e += blockDim.x) {
+    const int r = e / V, c = (e - r * V) * 4;
+    const size_t row = (size_t)b * T + t0 + r;
+    const float4 xv = load_cat(x1, c1, x2, c2, row, c);
+    const int g = c / cg;
+    const float mean = s_mean[g], rstd = s_rstd[g];
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float o[4] = {(xv.x - mean) * rstd * ga.x + be.x, (xv.y - mean) * rstd * ga.y + be.y,
+                  (xv.z - mean) * rstd * ga.z + be.z, (xv.w - mean) * rstd * ga.w + be.w};
+    if (ss) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
+      const float4 sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+      o[0] = o[0] * (1.f + sc.x) + sf.x; o[1] = o[1] * (1.f + sc.y) + sf.y;
+      o[2] = o[2] * (1.f + sc.z) + sf.z; o[3] = o[3] * (1.f + sc.w) + sf.w;
+    }
+    if (silu) { o[0] = silu_f(o[0]); o[1] = silu_f(o[1]); o[2] = silu_f(o[2]); o[3] = silu_f(o[3]); }
+    *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// one warp per row; C <= 32*4*MAXV
+constexpr int LN_MAXV = 8;
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int rows, int C,
+                                                        float* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int V = C >> 2;
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)warp * C);
+  float4 v[LN_MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < V) {
+      v[i] = __ldg(src + q);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < V) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  float4* dst = reinterpret_cast<float4*>(y + (size_t)warp * C);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < V) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + q);
+      dst[q] = make_float4((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y,
+                           (v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float* part,
+                            cudaStream_t s) {
+  const int C = c1 + c2;
+  if (C % (4 * groups) || c1 % 4 || groups > 32 || C / 4 > 1024) return cudaErrorInvalidValue;
+  const int V = C / 4;
+  int rpar = 256 / V;
+  if (rpar < 1) rpar = 1;
+  if (rpar > GN_ROWS) rpar = GN_ROWS;
+  const int threads = ((V * rpar + 31) / 32) * 32;
+  dim3 grid((T + GN_ROWS - 1) / GN_ROWS, B);
+  gn_stats_kernel<<<grid, threads, threads * 3 * sizeof(float), s>>>(x1, c1, x2, c2, T, groups, rpar, part);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups,
+                            const float* part, float eps, const float* gamma, const float* beta, const float* ss,
+                            int silu, float* y, cudaStream_t s) {
+  const int C = c1 + c2;
+  if (C % (4 * groups) || c1 % 4 || groups > 32) return cudaErrorInvalidValue;
+  dim3 grid((T + GN_ROWS - 1) / GN_ROWS, B);
+  gn_apply_kernel<<<grid, 256, 0, s>>>(x1, c1, x2, c2, T, groups, part, eps, gamma, beta, ss, silu, y);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
+                             cudaStream_t s) {
+  if (C % 4 || C > 128 * LN_MAXV) return cudaErrorInvalidValue;
+  const int warps_per_block = 8;
+  const int grid = (rows + warps_per_block - 1) / warps_per_block;
+  layernorm_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y);
+  return cudaGetLastError();
+}
+
+}  // namespace lds

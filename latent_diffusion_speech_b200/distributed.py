@@ -1,0 +1,56 @@
+"""Batch sharding across the GPUs of one box.
+
+Utterances are independent — GroupNorm/LayerNorm/attention are per sample and every solver
+coefficient is batch invariant — so the batch is split contiguously across ranks, weights are
+replicated, and there is NO collective inside the step loop.  The only exchange is one final
+``all_gather`` of the ``[B/G, T, out_dims]`` mel shards (NCCL over NVLink 5 / NVSwitch on the GPU
+box; the same code runs over ``gloo`` in the CPU tests).  The reference has no inference-time
+parallelism at all (tools/infer_tools.py:14 is single-device).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) of rank's utterances; the first n_items % world_size ranks get one extra."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_mels(mel_shard: torch.Tensor, n_items: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gathers ragged [b_r, T, M] shards into [n_items, T, M] on every rank (rank order = batch order)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mel_shard
+    world = dist.get_world_size(group)
+    sizes = [shard_bounds(n_items, world, r) for r in range(world)]
+    max_b = max(hi - lo for lo, hi in sizes)
+    pad = mel_shard
+    if mel_shard.shape[0] < max_b:
+        pad = torch.zeros((max_b,) + tuple(mel_shard.shape[1:]), dtype=mel_shard.dtype, device=mel_shard.device)
+        pad[: mel_shard.shape[0]] = mel_shard
+    out = torch.empty((world * max_b,) + tuple(mel_shard.shape[1:]), dtype=mel_shard.dtype, device=mel_shard.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    out = out.view(world, max_b, *mel_shard.shape[1:])
+    return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+def sharded_infer(model, units: torch.Tensor, spk_id: Optional[torch.Tensor], *, noise: Optional[torch.Tensor] = None,
+                  gather: bool = True, group: Optional[dist.ProcessGroup] = None, **forward_kwargs) -> torch.Tensor:
+    """Runs ``model(units[lo:hi], ...)`` for this rank's slice of the GLOBAL batch and gathers the mels.
+
+    ``units`` / ``spk_id`` / ``noise`` are the global tensors (each rank slices its own part, nothing is
+    scattered); per-utterance noise makes the result independent of the number of ranks."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = units.shape[0]
+    lo, hi = shard_bounds(n, world, rank)
+    mel = model(units[lo:hi], None, spk_id=None if spk_id is None else spk_id[lo:hi], infer=True,
+                noise=None if noise is None else noise[lo:hi], **forward_kwargs)
+    return gather_mels(mel, n, group) if gather else mel

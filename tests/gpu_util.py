@@ -1,0 +1,90 @@
+"""Helpers for the GPU parity tests: ctypes calls into the stateless operator entry points and a
+JSON-lines report (gpurun_out/parity_report.jsonl) of every measured error."""
+import ctypes as C
+import json
+import os
+import time
+
+import torch
+
+from conftest import ROOT
+
+REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
+
+
+def report(**kw):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    kw["ts"] = time.time()
+    with open(REPORT, "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+def lib():
+    from latent_diffusion_speech_b200 import capi
+    return capi.load_library()
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed: %s" % (what, lib().lds_last_error().decode()))
+
+
+def pack_conv3(w):
+    """[Cout, Cin, 3] -> [Cout, 3*Cin] tap-major."""
+    return w.permute(0, 2, 1).contiguous().reshape(w.shape[0], -1)
+
+
+def op_gemm(A, w, bias=None, R=None, r_div=1, M=None, N=None, K=None, taps=1, cin=None, t_out=None, t_in=None,
+            t_conv=None, stride=1, upsample=0, up_scale=1.0, epilogue=0, out_cols=None):
+    N = N or w.shape[0]
+    K = K or w.shape[1]
+    cin = cin or K // taps
+    M = M if M is not None else A.shape[0]
+    t_out = t_out or M
+    t_in = t_in or t_out
+    t_conv = t_conv or t_in
+    oc = out_cols or (N // 2 if epilogue == 2 else N)
+    out = torch.empty(M, oc, device=A.device, dtype=torch.float32)
+    rc = lib().lds_op_gemm(ptr(A), A.shape[-1], ptr(w), ptr(bias), ptr(R), 0 if R is None else R.shape[-1], r_div,
+                           ptr(out), oc, M, N, K, taps, cin, t_out, t_in, t_conv, stride, upsample, float(up_scale),
+                           epilogue, stream())
+    check(rc, "lds_op_gemm")
+    return out
+
+
+def op_attention(qkv, B, T, Cc, heads):
+    out = torch.empty(B * T, Cc, device=qkv.device, dtype=torch.float32)
+    check(lib().lds_op_attention(ptr(qkv), ptr(out), B, T, Cc, heads, stream()), "lds_op_attention")
+    return out
+
+
+def op_groupnorm(x1, x2, B, T, groups, eps, gamma, beta, ss=None, silu=0):
+    c1 = x1.shape[-1]
+    c2 = 0 if x2 is None else x2.shape[-1]
+    part = torch.empty(B * ((T + 31) // 32) * groups * 3, device=x1.device, dtype=torch.float32)
+    y = torch.empty(B * T, c1 + c2, device=x1.device, dtype=torch.float32)
+    check(lib().lds_op_groupnorm(ptr(x1), c1, ptr(x2), c2, B, T, groups, float(eps), ptr(gamma), ptr(beta), ptr(ss), silu,
+                                 ptr(part), ptr(y), stream()), "lds_op_groupnorm")
+    return y
+
+
+def op_layernorm(x, gamma, beta, eps=1e-5):
+    y = torch.empty_like(x)
+    check(lib().lds_op_layernorm(ptr(x), ptr(gamma), ptr(beta), float(eps), x.shape[0], x.shape[1], ptr(y), stream()),
+          "lds_op_layernorm")
+    return y
+
+
+def errs(got, want):
+    got, want = got.double(), want.double()
+    d = (got - want).abs()
+    return dict(max_abs=float(d.max()), rel_l2=float((got - want).norm() / want.norm().clamp_min(1e-30)),
+                scale=float(want.abs().max()))

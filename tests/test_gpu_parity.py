@@ -1,0 +1,109 @@
+"""GPU: the CUDA path (through Unit2Mel -> C ABI) against
+  (1) the golden fixtures produced by the executed reference (CPU fp32),
+  (2) the oracle restatement run in fp64 (the accuracy yardstick), and
+  (3) size-independent properties at BASELINE.json's full shapes (batch-composition invariance).
+
+Tolerance (BASELINE.json north_star): fp32 mode max-abs mel error <= 1e-3.  With random-init weights
+the DPM/UniPC output has |x|max ~ 7e2, so 1e-3 is ~1.5e-6 relative — the fp32 round-off floor of the
+reference itself (reference fp32 vs fp64: 5.8e-4; 8 threads vs 1 thread: 7.9e-4).
+We therefore assert the stated 1e-3 against the fp64 ground truth, and 2e-3 (both round-off floors
+added) against the reference's own fp32 output."""
+import pytest
+import torch
+
+import gpu_util as G
+from conftest import golden_names, load_golden
+from oracle import unit2mel_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL_VS_FP64 = 1e-3
+TOL_VS_REF_FP32 = 2e-3
+
+
+def _inputs(g):
+    B, T = int(g["B"]), int(g["T"])
+    k_step = None if int(g["k_step"]) < 0 else int(g["k_step"])
+    method = str(g["method"]) or None
+    units, spk, noise, steps, gt = O.synthetic_inputs(B, T, n_step_noises=int(g["n_step_noises"]), gt=k_step is not None)
+    return B, T, k_step, method, int(g["infer_speedup"]), units, spk, noise, steps, gt
+
+
+def _run_cuda(model, units, spk, noise, steps, gt, method, speedup, k_step):
+    sn = None
+    if steps:
+        st = torch.stack(steps).cuda()
+        sn = lambda j0, j1: st[j0:j1]
+    with torch.no_grad():
+        mel = model(units.cuda(), None, spk_id=spk.cuda(), gt_spec=None if gt is None else gt.cuda(), infer=True,
+                    infer_speedup=speedup, method=method, k_step=k_step, noise=noise.cuda(), step_noise=sn)
+    torch.cuda.synchronize()
+    return mel.cpu()
+
+
+@pytest.mark.parametrize("name", golden_names("nfe_"))
+def test_denoiser_eval_vs_reference_golden(name, gpu_model, state_dict):
+    g = load_golden(name)
+    B, T = int(g["B"]), int(g["T"])
+    _, _, noise, _, _ = O.synthetic_inputs(B, T)
+    cond = torch.from_numpy(g["cond"])                        # [B, H, T] as the reference builds it
+    eps = gpu_model.denoise(noise[:, 0].cuda(), cond.transpose(1, 2).contiguous().cuda(), float(g["t"])).cpu()
+    e = G.errs(eps, torch.from_numpy(g["eps"]))
+    with torch.no_grad():
+        e64 = G.errs(eps, O.unet_forward({k: v.double() for k, v in state_dict.items()}, O.DEFAULT_CFG,
+                                         torch.cat([noise[:, 0], cond], dim=-2).double(), torch.full((B,), float(g["t"])).double()))
+    G.report(test="denoise_golden", name=name, vs_ref=e, vs_fp64=e64)
+    assert e["max_abs"] <= 5e-5 and e64["max_abs"] <= 5e-5, (e, e64)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("nfe_")])
+def test_sampler_vs_reference_golden(name, gpu_model, state_dict):
+    g = load_golden(name)
+    B, T, k_step, method, speedup, units, spk, noise, steps, gt = _inputs(g)
+    mel = _run_cuda(gpu_model, units, spk, noise, steps, gt, method, speedup, k_step)
+    want = torch.from_numpy(g["mel"])
+    e = G.errs(mel, want)
+    with torch.no_grad():
+        ref64 = O.unit2mel_infer(state_dict, O.DEFAULT_CFG, units, spk, noise, method, speedup, gt_spec=gt, k_step=k_step,
+                                 step_noises=steps, dtype=torch.float64)
+    e64 = G.errs(mel, ref64)
+    floor = G.errs(want, ref64)                                # the reference's own fp32 round-off on this case
+    G.report(test="sampler_golden", name=name, vs_ref=e, vs_fp64=e64, ref_fp32_vs_fp64=floor)
+    assert mel.shape == want.shape
+    assert e64["max_abs"] <= TOL_VS_FP64, (e64, floor)
+    assert e["max_abs"] <= TOL_VS_REF_FP32, (e, floor)
+
+
+def test_cond_matches_reference_expression(gpu_model, state_dict):
+    units, spk, _, _, _ = O.synthetic_inputs(3, 50)
+    eng = gpu_model._get_engine(torch.device("cuda", torch.cuda.current_device()))
+    eng.plan(3, 50, 0, None, None, key=None)
+    got = eng.cond(units.cuda(), spk.cuda()).cpu()
+    want = O.unit2mel_cond({k: v.double() for k, v in state_dict.items() if not k.startswith("decoder")}, units.double(), spk, 323)
+    e = G.errs(got, want)
+    G.report(test="cond", **e)
+    assert e["max_abs"] <= 2e-5, e
+
+
+def test_batch_composition_invariance_full_width(gpu_model):
+    """Utterances are independent: utterance b of a B=8 run equals the same utterance run
+    alone, bit for bit — the property the multi-GPU shard relies on.  T=864 is BASELINE's 10 s length."""
+    B, T = 8, 864
+    units, spk, noise, _, _ = O.synthetic_inputs(B, T)
+    full = _run_cuda(gpu_model, units, spk, noise, [], None, "unipc", 500, None)         # 2 steps keep it short
+    part = _run_cuda(gpu_model, units[5:7], spk[5:7], noise[5:7], [], None, "unipc", 500, None)
+    assert torch.equal(full[5:7], part)
+    assert torch.isfinite(full).all()
+
+
+def test_oracle_on_gpu_agrees_at_10s_length(gpu_model, state_dict):
+    """B=2 x T=861 (8 does not divide T -> forced upsample sizes, ragged tiles), DPM-Solver++ 20 steps,
+    against the oracle executed in fp64 on the same GPU (checker only)."""
+    B, T = 2, 861
+    units, spk, noise, _, _ = O.synthetic_inputs(B, T)
+    mel = _run_cuda(gpu_model, units, spk, noise, [], None, "dpm-solver", 50, None)
+    sd64 = {k: v.double().cuda() for k, v in state_dict.items()}
+    with torch.no_grad():
+        ref64 = O.unit2mel_infer(sd64, O.DEFAULT_CFG, units.cuda().double(), spk.cuda(), noise.cuda().double(), "dpm-solver", 50).cpu()
+    e = G.errs(mel, ref64)
+    G.report(test="dpm20_T861_vs_fp64_gpu_oracle", **e)
+    assert e["max_abs"] <= TOL_VS_FP64, e

@@ -1,0 +1,39 @@
+"""CPU: the oracle restatement against the fixtures produced by the executed reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import unit2mel_oracle as O
+
+CASES = [n for n in golden_names() if not n.startswith("nfe_")]
+FAST = ["dpm8_b1_t24", "unipc10_b2_t37", "ddpm12_b2_t24", "shallow_dpm20_b2_t32"]
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_oracle_reproduces_reference_mel(name, state_dict):
+    g = load_golden(name)
+    B, T = int(g["B"]), int(g["T"])
+    k_step = None if int(g["k_step"]) < 0 else int(g["k_step"])
+    method = str(g["method"]) or None
+    units, spk, noise, steps, gt = O.synthetic_inputs(B, T, n_step_noises=int(g["n_step_noises"]), gt=k_step is not None)
+    with torch.no_grad():
+        mel = O.unit2mel_infer(state_dict, O.DEFAULT_CFG, units, spk, noise, method, int(g["infer_speedup"]), gt_spec=gt,
+                               k_step=k_step, step_noises=steps)
+    want = torch.from_numpy(g["mel"])
+    err = float((mel - want).abs().max())
+    scale = float(want.abs().max())
+    # bit-exact on the authoring container (same torch build and thread count); a different host
+    # thread count reorders fp32 sums, which the reference itself shows as ~1e-6 of the output scale
+    assert err <= 4e-6 * max(scale, 1.0), (err, scale)
+
+
+@pytest.mark.parametrize("name", golden_names("nfe_"))
+def test_oracle_reproduces_reference_eps(name, state_dict):
+    g = load_golden(name)
+    B, T = int(g["B"]), int(g["T"])
+    _, _, noise, _, _ = O.synthetic_inputs(B, T)
+    cond = torch.from_numpy(g["cond"])
+    with torch.no_grad():
+        eps = O.unet_forward(state_dict, O.DEFAULT_CFG, torch.cat([noise[:, 0], cond], dim=-2), torch.full((B,), float(g["t"])))
+    assert float((eps - torch.from_numpy(g["eps"])).abs().max()) <= 2e-5
