@@ -222,7 +222,7 @@ class VPSchedule:
         if clip:
             log_sig = 0.5 * torch.log(1.0 - torch.exp(2.0 * log_alphas))
             lambs = log_alphas - log_sig
-            n_drop = int(torch.searchsorted(torch.flip(lambs, [0]), torch.tensor(-5.1, dtype=lambs.dtype)))
+            n_drop = int(torch.searchsorted(torch.flip(lambs, [0]), torch.tensor(-5.1, dtype=lambs.dtype, device=lambs.device)))
             if n_drop > 0:
                 log_alphas = log_alphas[:-n_drop]
         self.log_alpha = log_alphas.to(dtype)

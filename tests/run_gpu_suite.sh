@@ -1,0 +1,14 @@
+#!/bin/bash
+# GPU-box driver script: kernel tests, parity tests, smoke, short bench. Logs under gpurun_out/.
+mkdir -p gpurun_out
+rm -f gpurun_out/parity_report.jsonl
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/kernels.log 2>&1
+echo "kernels rc=$?" >> gpurun_out/kernels.log
+timeout 1500 python -m pytest tests/test_gpu_parity.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/parity.log 2>&1
+echo "parity rc=$?" >> gpurun_out/parity.log
+timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+echo "smoke rc=$?" >> gpurun_out/smoke.log
+timeout 900 python bench.py --steps ${BENCH_STEPS:-2} --warmup 3 > gpurun_out/bench.log 2>&1
+echo "bench rc=$?" >> gpurun_out/bench.log
+tail -5 gpurun_out/kernels.log; tail -5 gpurun_out/parity.log; tail -3 gpurun_out/smoke.log; tail -2 gpurun_out/bench.log
