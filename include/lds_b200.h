@@ -161,6 +161,15 @@ LDS_API int lds_op_groupnorm(const float* x1, int c1, const float* x2, int c2, i
                      float* y, void* stream);
 LDS_API int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
                      void* stream);
+/* Tensor-core (tcgen05/TMEM/TMA) form of lds_op_gemm on bf16 operands.
+ *   lds_op_split_cast : fp32 [rows, C] -> bf16 [rows, parts*C]; parts=1 rounds, parts=3 writes hi/mid/lo planes
+ *   lds_op_gemm_tc    : A bf16 [batches][rows][parts*cin], w bf16 [N][taps*parts*cin] (tap-major, then plane, then
+ *                       channel); parts=1: plain bf16 product; parts=3: six-term split product (fp32-accurate).
+ *                       taps=3: k=3/stride-1/pad-1 conv along rows.  out_kind 0 fp32, 1 bf16, 2 split planes. */
+LDS_API int lds_op_split_cast(const float* in, void* out_bf16, int64_t rows, int C, int parts, void* stream);
+LDS_API int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, int parts, const void* w_bf16, int N, int taps,
+                   const float* bias, const float* R, int r_ld, int r_div, void* C, int c_ld, int out_kind,
+                   int epilogue, void* stream);
 
 #ifdef __cplusplus
 }

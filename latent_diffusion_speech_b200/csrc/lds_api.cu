@@ -955,4 +955,20 @@ int lds_op_layernorm(const float* x, const float* gamma, const float* beta, floa
   return op_status(lds::launch_layernorm(x, gamma, beta, eps, rows, C, y, (cudaStream_t)stream), "lds_op_layernorm");
 }
 
+int lds_op_split_cast(const float* in, void* out_bf16, int64_t rows, int C, int parts, void* stream) {
+  if (!in || !out_bf16) return fail(LDS_ERR_INVALID, "lds_op_split_cast: null tensor");
+  return op_status(lds::launch_split_cast(in, (__nv_bfloat16*)out_bf16, rows, C, parts, (cudaStream_t)stream), "lds_op_split_cast");
+}
+int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, int parts, const void* w_bf16, int N, int taps,
+                   const float* bias, const float* R, int r_ld, int r_div, void* C, int c_ld, int out_kind, int epilogue,
+                   void* stream) {
+  if (!A_bf16 || !w_bf16 || !C || (parts != 1 && parts != 3)) return fail(LDS_ERR_INVALID, "lds_op_gemm_tc: bad argument");
+  lds::TcGemmArgs g;
+  g.A = (const __nv_bfloat16*)A_bf16; g.batches = batches; g.rows = rows; g.cin = cin;
+  g.W = (const __nv_bfloat16*)w_bf16; g.N = N; g.taps = taps;
+  if (parts == 3) lds::tc_set_split_pairs(g);
+  g.bias = bias; g.R = R; g.r_ld = r_ld; g.r_div = r_div; g.C = C; g.c_ld = c_ld; g.out_kind = out_kind; g.epilogue = epilogue;
+  return op_status(lds::launch_gemm_tc(g, (cudaStream_t)stream), "lds_op_gemm_tc");
+}
+
 }  // extern "C"

@@ -34,6 +34,29 @@ struct GemmArgs {
 };
 cudaError_t launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
 
+// tcgen05/TMEM/TMA implicit GEMM on bf16 operands (gemm_tc.cu).
+//  A: bf16 [batches][rows][a_parts*cin]; W: bf16 [N][taps*w_parts*cin]; logical product = sum over the listed
+//  (pair_a, pair_w) plane pairs of A_plane (*) W_plane^T.  Plain bf16: parts = 1, one pair (0,0).  Split-bf16
+//  (fp32-accurate): parts = 3 (hi, mid, lo planes) and the six significant pairs, smallest first.
+//  taps==3: k=3, stride-1, pad-1 convolution along `rows` (TMA out-of-bounds fill = zero padding).
+//  out_kind: 0 fp32 [*, c_ld], 1 bf16 [*, c_ld], 2 three bf16 planes of c_ld/3 columns each.
+struct TcGemmArgs {
+  const __nv_bfloat16* A = nullptr; int batches = 1, rows = 0, cin = 0, a_parts = 1;
+  const __nv_bfloat16* W = nullptr; int N = 0, taps = 1, w_parts = 1;
+  int n_pairs = 1; int pair_a[6] = {0, 0, 0, 0, 0, 0}; int pair_w[6] = {0, 0, 0, 0, 0, 0};
+  const float* bias = nullptr;
+  const float* R = nullptr; int r_ld = 0, r_div = 1;
+  void* C = nullptr; int c_ld = 0, out_kind = 0, epilogue = EPI_NONE;
+};
+cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
+inline void tc_set_split_pairs(TcGemmArgs& a) {   // lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
+  static const int pa[6] = {2, 0, 1, 1, 0, 0}, pw[6] = {0, 2, 1, 0, 1, 0};
+  a.a_parts = a.w_parts = 3; a.n_pairs = 6;
+  for (int i = 0; i < 6; ++i) { a.pair_a[i] = pa[i]; a.pair_w[i] = pw[i]; }
+}
+// fp32 [rows, C] -> bf16 [rows, parts*C]: parts=1 plain rounding; parts=3 hi/mid/lo planes (x == hi+mid+lo to 24 bits)
+cudaError_t launch_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, cudaStream_t s);
+
 // Flash-style self-attention on a fused QKV buffer [B*T, 3C]: head h uses columns
 // [h*d,(h+1)*d) of each C-wide third.  out [B*T, C].  softmax(q k^T / sqrt(d)) v, no mask.
 cudaError_t launch_attention_f32(const float* qkv, float* out, int B, int T, int C, int heads, cudaStream_t s);

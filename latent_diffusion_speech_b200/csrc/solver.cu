@@ -162,6 +162,31 @@ __global__ void spk_gather_kernel(const float* __restrict__ table, const int64_t
     out[(size_t)b * H + c] = (row >= 0 && row < n_rows) ? table[row * H + c] : 0.f;
 }
 
+// fp32 -> bf16 planes; one thread per 4 consecutive channels
+__global__ void split_cast_kernel(const float4* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows, int C, int parts) {
+  const int V = C >> 2;
+  const int64_t n = rows * V;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / V;
+    const int c = (int)(i - row * V) * 4;
+    const float4 q = in[i];
+    float r[4] = {q.x, q.y, q.z, q.w};
+    __nv_bfloat16* dst = out + row * (int64_t)(parts * C) + c;
+    for (int p = 0; p < parts; ++p) {
+      __nv_bfloat16 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(r[j]);
+        r[j] -= __bfloat162float(h[j]);
+      }
+      uint2 w;
+      w.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+      w.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+      *reinterpret_cast<uint2*>(dst + (int64_t)p * C) = w;
+    }
+  }
+}
+
 inline int grid_for(int64_t nvec) {
   int64_t g = (nvec + 255) / 256;
   const int64_t cap = 148 * 16;
@@ -217,6 +242,11 @@ cudaError_t launch_transpose_btc_to_bct(const float* in, float* out, int B, int 
 cudaError_t launch_div_copy(const float* in, float* out, int64_t n, float divisor, cudaStream_t s) {
   if (n % 4) return cudaErrorInvalidValue;
   div_copy_kernel<<<grid_for(n / 4), 256, 0, s>>>(V4(in), V4W(out), n, divisor);
+  return cudaGetLastError();
+}
+cudaError_t launch_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, cudaStream_t s) {
+  if (C % 4 || parts < 1 || parts > 3) return cudaErrorInvalidValue;
+  split_cast_kernel<<<grid_for(rows * (C / 4)), 256, 0, s>>>(V4(in), out, rows, C, parts);
   return cudaGetLastError();
 }
 cudaError_t launch_silu(const float* in, float* out, int64_t n, cudaStream_t s) {

@@ -88,3 +88,35 @@ def errs(got, want):
     d = (got - want).abs()
     return dict(max_abs=float(d.max()), rel_l2=float((got - want).norm() / want.norm().clamp_min(1e-30)),
                 scale=float(want.abs().max()))
+
+
+def op_split_cast(x, parts):
+    rows, Cc = x.shape
+    out = torch.empty(rows, parts * Cc, device=x.device, dtype=torch.bfloat16)
+    check(lib().lds_op_split_cast(ptr(x), ptr(out), rows, Cc, parts, stream()), "lds_op_split_cast")
+    return out
+
+
+def pack_w_parts(w, taps, parts):
+    """fp32 [N, taps*cin] (tap-major) -> bf16 [N, taps*parts*cin] (tap, plane, channel)."""
+    N, K = w.shape
+    cin = K // taps
+    sp = op_split_cast(w.reshape(N * taps, cin).contiguous(), parts)       # [N*taps, parts*cin]
+    return sp.reshape(N, taps * parts * cin).contiguous()
+
+
+def op_gemm_tc(a_bf16, batches, rows, cin, parts, w_bf16, N, taps=1, bias=None, R=None, r_div=1, out_kind=0, epilogue=0):
+    n_out = N // 2 if epilogue == 2 else N
+    if out_kind == 0:
+        out = torch.empty(batches * rows, n_out, device=a_bf16.device, dtype=torch.float32)
+        c_ld = n_out
+    elif out_kind == 1:
+        out = torch.empty(batches * rows, n_out, device=a_bf16.device, dtype=torch.bfloat16)
+        c_ld = n_out
+    else:
+        out = torch.empty(batches * rows, 3 * n_out, device=a_bf16.device, dtype=torch.bfloat16)
+        c_ld = 3 * n_out
+    check(lib().lds_op_gemm_tc(ptr(a_bf16), batches, rows, cin, parts, ptr(w_bf16), N, taps, ptr(bias), ptr(R),
+                               0 if R is None else R.shape[-1], r_div, ptr(out), c_ld, out_kind, epilogue, stream()),
+          "lds_op_gemm_tc")
+    return out

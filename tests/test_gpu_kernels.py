@@ -131,3 +131,74 @@ def test_layernorm(rows, C):
     e = G.errs(got, F.layer_norm(x.double(), (C,), gamma.double(), beta.double(), 1e-5))
     G.report(test="layernorm", rows=rows, C=C, **e)
     assert e["max_abs"] <= 2e-5, e
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tcgen05 / TMEM / TMA GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 256), (1000, 384, 1536), (4096, 768, 256), (77, 128, 1280)])
+def test_tc_gemm_bf16_exact_products(M, N, K):
+    """Plain bf16 mode against the exact product of the bf16-rounded operands (isolates the kernel mechanics)."""
+    A, W, b, R = _rand(M, K, seed=31), _rand(N, K, seed=32, scale=K ** -0.5), _rand(N, seed=33), _rand(M, N, seed=34)
+    a16, w16 = G.op_split_cast(A, 1), G.op_split_cast(W, 1)
+    got = G.op_gemm_tc(a16, 1, M, K, 1, w16, N, bias=b, R=R)
+    want = a16.double() @ w16.double().t() + b.double() + R.double()
+    e = G.errs(got, want)
+    G.report(test="tc_gemm_bf16", M=M, N=N, K=K, **e)
+    assert e["max_abs"] <= 3e-5 * math.sqrt(K / 256) * max(1.0, e["scale"] / 4), e
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 256), (1000, 384, 1536), (555, 512, 3072)])
+def test_tc_gemm_split_fp32_accuracy(M, N, K):
+    """Split-bf16 (6 plane products) against fp64 of the fp32 operands: must be fp32-grade."""
+    A, W, b = _rand(M, K, seed=35), _rand(N, K, seed=36, scale=K ** -0.5), _rand(N, seed=37)
+    a3, w3 = G.op_split_cast(A, 3), G.pack_w_parts(W, 1, 3)
+    got = G.op_gemm_tc(a3, 1, M, K, 3, w3, N, bias=b)
+    want = A.double() @ W.double().t() + b.double()
+    e = G.errs(got, want)
+    ffma = G.errs(G.op_gemm(A, W, b), want)
+    G.report(test="tc_gemm_split", M=M, N=N, K=K, split=e, ffma=ffma)
+    assert e["max_abs"] <= 5e-5 * math.sqrt(K / 256), (e, ffma)
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,parts", [(2, 37, 256, 384, 1), (3, 100, 384, 128, 1), (2, 300, 640, 256, 3), (1, 864, 256, 256, 3)])
+def test_tc_conv3(B, T, Cin, Cout, parts):
+    x = _rand(B, T, Cin, seed=38)
+    w, b = _rand(Cout, Cin, 3, seed=39, scale=(3 * Cin) ** -0.5), _rand(Cout, seed=40)
+    R = _rand(B * T, Cout, seed=41)
+    a = G.op_split_cast(x.view(B * T, Cin), parts)
+    wp = G.pack_w_parts(G.pack_conv3(w), 3, parts)
+    got = G.op_gemm_tc(a, B, T, Cin, parts, wp, Cout, taps=3, bias=b, R=R)
+    if parts == 1:
+        xr, wr = a.view(B, T, Cin).double(), w.bfloat16().double()
+    else:
+        xr, wr = x.double(), w.double()
+    want = F.conv1d(xr.transpose(1, 2), wr, b.double(), padding=1).transpose(1, 2).reshape(B * T, Cout) + R.double()
+    e = G.errs(got, want)
+    G.report(test="tc_conv3", B=B, T=T, Cin=Cin, Cout=Cout, parts=parts, **e)
+    assert e["max_abs"] <= 6e-5, e
+
+
+@pytest.mark.parametrize("out_kind,parts", [(1, 1), (2, 3)])
+def test_tc_gemm_geglu_and_output_kinds(out_kind, parts):
+    M, C = 333, 256
+    A, W, b = _rand(M, C, seed=42), _rand(8 * C, C, seed=43, scale=C ** -0.5), _rand(8 * C, seed=44)
+    idx = []
+    for t in range(4 * C // 64):
+        idx += list(range(t * 64, t * 64 + 64)) + list(range(4 * C + t * 64, 4 * C + t * 64 + 64))
+    idx = torch.tensor(idx, device=DEV)
+    a = G.op_split_cast(A, parts)
+    wp = G.pack_w_parts(W[idx].contiguous(), 1, parts)
+    got = G.op_gemm_tc(a, 1, M, C, parts, wp, 8 * C, bias=b[idx].contiguous(), out_kind=out_kind, epilogue=2)
+    if parts == 1:
+        y = a.double() @ G.op_split_cast(W, 1).double().t() + b.double()
+        want = y[:, :4 * C] * F.gelu(y[:, 4 * C:])
+        e = G.errs(got.float(), want)
+        tol = 2e-2 * max(1.0, e["scale"])            # bf16 output rounding
+    else:
+        y = A.double() @ W.double().t() + b.double()
+        want = y[:, :4 * C] * F.gelu(y[:, 4 * C:])
+        planes = got.float().view(M, 3, 4 * C)
+        e = G.errs(planes.double().sum(1), want)
+        tol = 5e-5
+    G.report(test="tc_geglu", out_kind=out_kind, parts=parts, **e)
+    assert e["max_abs"] <= tol, e
