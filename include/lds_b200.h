@@ -45,7 +45,12 @@ typedef enum {
   LDS_ERR_UNSUPPORTED = -4
 } lds_status;
 
-typedef enum { LDS_PREC_FP32 = 0, LDS_PREC_BF16 = 1 } lds_precision;
+/* LDS_PREC_FP32      : fp32-accurate.  GEMM operands are split into three bf16 planes (hi+mid+lo == x to 24 bits) and the
+ *                      six significant plane products are accumulated in fp32 in TMEM by tcgen05.mma; norms, softmax,
+ *                      attention and the solver run in fp32.
+ * LDS_PREC_BF16      : bf16 GEMM operands (one tcgen05.mma per K slice), fp32 accumulation, fp32 norms / solver state.
+ * LDS_PREC_FP32_FFMA : IEEE fp32 FFMA kernels on the CUDA cores (the first, reference-grade implementation). */
+typedef enum { LDS_PREC_FP32 = 0, LDS_PREC_BF16 = 1, LDS_PREC_FP32_FFMA = 2 } lds_precision;
 typedef enum { LDS_DTYPE_F32 = 0, LDS_DTYPE_BF16 = 1, LDS_DTYPE_F16 = 2 } lds_dtype;
 
 /* Sampler kinds.  The per-step scalar coefficients are computed by the host (they are batch

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblds_b200.so")
 MAX_BLOCKS = 8
 COEF_STRIDE = 12
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP32_FFMA = 0, 1, 2
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 
 EXPORTS = [
@@ -127,7 +127,7 @@ class Engine:
             cfg.block_out_channels[i] = int(c)
         cfg.n_heads, cfg.n_hidden, cfg.norm_groups = int(n_heads), int(n_hidden), int(norm_groups)
         cfg.acoustic_scale = float(acoustic_scale)
-        cfg.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16}[precision]
+        cfg.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp32_ffma": PREC_FP32_FFMA}[precision]
         self.cfg, self.precision = cfg, precision
         self.handle = C.c_void_p()
         check(self.lib, self.lib.lds_create(C.byref(cfg), self.index, C.byref(self.handle)), "lds_create")

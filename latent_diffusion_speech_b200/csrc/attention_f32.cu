@@ -12,6 +12,7 @@
 // permutation (row = (key%4)*16 + key/4) that makes both the P stores and the V/P loads
 // bank-conflict free; V rows are stored with the same permutation so the product is unchanged.
 #include "lds_kernels.h"
+#include "planes.cuh"
 #include <math.h>
 
 namespace lds {
@@ -21,7 +22,7 @@ constexpr int BQ = 64, BKV = 64, ATT_THREADS = 256, TLD = 68;  // TLD: padded le
 
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                                     int T, int C) {
+                                                                     __nv_bfloat16* __restrict__ outb, int parts, int T, int C) {
   constexpr int DC = D / 16;  // output columns per thread
   extern __shared__ __align__(16) float smem[];
   float* Qs = smem;                 // [D][TLD]   Qs[k][i]
@@ -149,14 +150,27 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_f32_kernel(const float*
     const int q = q0 + ty * 4 + i;
     if (q >= T) continue;
     const float inv = 1.f / l_run[i];
-    float* dst = out + ((size_t)b * T + q) * C + h * D + tx * DC;
+    if (outb) {
+      __nv_bfloat16* rowb = outb + ((size_t)b * T + q) * (size_t)(parts * C);
 #pragma unroll
-    for (int c = 0; c < DC; ++c) dst[c] = o[i][c] * inv;
+      for (int c = 0; c < DC; ++c) {
+        float r = o[i][c] * inv;
+        for (int pl = 0; pl < parts; ++pl) {
+          const __nv_bfloat16 hv = __float2bfloat16_rn(r);
+          r -= __bfloat162float(hv);
+          rowb[(size_t)pl * C + h * D + tx * DC + c] = hv;
+        }
+      }
+    } else {
+      float* dst = out + ((size_t)b * T + q) * C + h * D + tx * DC;
+#pragma unroll
+      for (int c = 0; c < DC; ++c) dst[c] = o[i][c] * inv;
+    }
   }
 }
 
 template <int D>
-cudaError_t launch_d(const float* qkv, float* out, int B, int T, int C, int heads, cudaStream_t s) {
+cudaError_t launch_d(const float* qkv, float* out, __nv_bfloat16* outb, int parts, int B, int T, int C, int heads, cudaStream_t s) {
   const size_t smem = (size_t)(2 * D * TLD + BKV * D + BKV * TLD) * sizeof(float);
   static bool configured = false;
   if (!configured) {
@@ -165,18 +179,19 @@ cudaError_t launch_d(const float* qkv, float* out, int B, int T, int C, int head
     configured = true;
   }
   dim3 grid((T + BQ - 1) / BQ, heads, B);
-  attention_f32_kernel<D><<<grid, ATT_THREADS, smem, s>>>(qkv, out, T, C);
+  attention_f32_kernel<D><<<grid, ATT_THREADS, smem, s>>>(qkv, out, outb, parts, T, C);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_attention_f32(const float* qkv, float* out, int B, int T, int C, int heads, cudaStream_t s) {
+cudaError_t launch_attention_f32(const float* qkv, float* out, __nv_bfloat16* outb, int parts, int B, int T, int C, int heads,
+                                 cudaStream_t s) {
   if (heads <= 0 || C % heads) return cudaErrorInvalidValue;
   switch (C / heads) {
-    case 32: return launch_d<32>(qkv, out, B, T, C, heads, s);
-    case 48: return launch_d<48>(qkv, out, B, T, C, heads, s);
-    case 64: return launch_d<64>(qkv, out, B, T, C, heads, s);
+    case 32: return launch_d<32>(qkv, out, outb, parts, B, T, C, heads, s);
+    case 48: return launch_d<48>(qkv, out, outb, parts, B, T, C, heads, s);
+    case 64: return launch_d<64>(qkv, out, outb, parts, B, T, C, heads, s);
     default: return cudaErrorNotSupported;
   }
 }

@@ -48,7 +48,7 @@ struct HostTensor {
   std::vector<int64_t> shape;
 };
 
-struct ConvW { const float* w = nullptr; const float* b = nullptr; int cin = 0, cout = 0, taps = 1; };
+struct ConvW { const float* w = nullptr; const __nv_bfloat16* wh = nullptr; const float* b = nullptr; int cin = 0, cout = 0, taps = 1; };
 struct NormW { const float* g = nullptr; const float* b = nullptr; };
 struct ResnetW {
   std::string key;
@@ -57,10 +57,14 @@ struct ResnetW {
   NormW n1, n2;
   ConvW conv1, conv2;
   const float* sc_w1 = nullptr; const float* sc_w2 = nullptr; const float* sc_b = nullptr;
+  const __nv_bfloat16* sc_wh = nullptr;                            // [cout, parts*(c1+c2)] (tensor-core modes)
   const float* temb_w = nullptr; const float* temb_b = nullptr;   // [2*cout, temb_dim]
   int temb_off = 0;                                                // offset into a temb table row
 };
-struct AttnW { const float* qkv = nullptr; const float* out_w = nullptr; const float* out_b = nullptr; };
+struct AttnW {
+  const float* qkv = nullptr; const float* out_w = nullptr; const float* out_b = nullptr;
+  const __nv_bfloat16* qkv_h = nullptr; const __nv_bfloat16* out_h = nullptr;
+};
 struct XfW {
   std::string key;
   int C = 0;
@@ -69,6 +73,7 @@ struct XfW {
   AttnW a1, a2;
   const float* ff1_w = nullptr; const float* ff1_b = nullptr;      // GEGLU-interleaved [8C, C]
   const float* ff2_w = nullptr; const float* ff2_b = nullptr;      // [C, 4C]
+  const __nv_bfloat16* ff1_h = nullptr; const __nv_bfloat16* ff2_h = nullptr;
 };
 
 struct Prof {
@@ -91,8 +96,12 @@ struct lds_handle {
   // packed weights (one device arena)
   float* warena = nullptr;
   size_t warena_floats = 0;
+  __nv_bfloat16* wharena = nullptr;   // bf16 operand planes of the GEMM weights (tensor-core modes)
+  size_t wharena_elems = 0;
+  int parts = 0;                      // 0: FFMA fp32 kernels; 1: bf16 tcgen05; 3: split-bf16 tcgen05 (fp32-accurate)
   int temb_dim = 0, temb_total = 0;
   const float *unit_w = nullptr, *unit_b = nullptr, *spk_table = nullptr;
+  const __nv_bfloat16 *unit_wh = nullptr, *conv_in_wxh = nullptr, *conv_in_wch = nullptr;
   const float *time_w1 = nullptr, *time_b1 = nullptr, *time_w2 = nullptr, *time_b2 = nullptr;
   const float *conv_in_wx = nullptr, *conv_in_wc = nullptr, *conv_in_b = nullptr;
   std::vector<ResnetW> resnets;     // execution order
@@ -114,6 +123,10 @@ struct lds_handle {
   float *norm = nullptr, *tmp = nullptr, *tmp2 = nullptr, *xn = nullptr, *th = nullptr, *qkv = nullptr, *att = nullptr, *ffh = nullptr;
   float *x = nullptr, *xb = nullptr, *xp = nullptr, *eps = nullptr, *mbuf[3] = {nullptr, nullptr, nullptr};
   float *io_a = nullptr, *io_b = nullptr;   // channels-last staging for lds_denoise
+  __nv_bfloat16* barena = nullptr;          // bf16 operand buffers (tensor-core modes)
+  size_t barena_elems = 0;
+  __nv_bfloat16 *norm_b = nullptr, *raw_b = nullptr, *tmp2_b = nullptr, *xn_b = nullptr, *att_b = nullptr, *ffh_b = nullptr,
+                *th_b = nullptr, *cast_b = nullptr;
   const float* cond_bound = nullptr;
   int m_cur = 0;                            // index of m0 in mbuf; m1 = (m_cur+2)%3, free = (m_cur+1)%3
   // bookkeeping
@@ -222,17 +235,21 @@ int run_gn(lds_handle* h, cudaStream_t s, const float* x1, int c1, const float* 
   LDS_TRY(launched(h, s, PC_GN_STATS, 0, 4.0 * elems, launch_gn_stats(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, s),
                    "gn_stats"));
   return launched(h, s, PC_GN_APPLY, 0, 8.0 * elems,
-                  launch_gn_apply(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, eps, n.g, n.b, ss, silu, y, s),
+                  launch_gn_apply(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, eps, n.g, n.b, ss, silu, y, nullptr, 1, nullptr, s),
                   "gn_apply");
 }
 
 int run_ln(lds_handle* h, cudaStream_t s, const float* x, const NormW& n, int rows, int C, float* y) {
-  return launched(h, s, PC_LAYERNORM, 0, 8.0 * rows * C, launch_layernorm(x, n.g, n.b, 1e-5f, rows, C, y, s), "layernorm");
+  return launched(h, s, PC_LAYERNORM, 0, 8.0 * rows * C, launch_layernorm(x, n.g, n.b, 1e-5f, rows, C, y, nullptr, 1, s), "layernorm");
 }
 
 // resnet.py:591-641
 int run_resnet(lds_handle* h, cudaStream_t s, const ResnetW& r, const float* x1, const float* x2, int T,
-               const float* temb_row, float* out) {
+               const float* temb_row, float* out);
+int run_transformer(lds_handle* h, cudaStream_t s, const XfW& w, const float* x, int T, float* out);
+
+int run_resnet_ffma(lds_handle* h, cudaStream_t s, const ResnetW& r, const float* x1, const float* x2, int T,
+                    const float* temb_row, float* out) {
   const int M = h->B * T, cin = r.c1 + r.c2;
   LDS_TRY(run_gn(h, s, x1, r.c1, x2, r.c2, T, r.n1, 1e-5f, nullptr, 1, h->norm));
   LDS_TRY(run_gemm(h, s, conv3_args(h->norm, h->B, T, cin, r.conv1, h->tmp, T, 1)));
@@ -258,14 +275,14 @@ int run_attention(lds_handle* h, cudaStream_t s, const AttnW& a, const NormW& ln
   LDS_TRY(run_ln(h, s, h->th, ln, M, C, h->xn));
   LDS_TRY(run_gemm(h, s, linear_args(h->xn, M, C, a.qkv, nullptr, 3 * C, h->qkv)));
   LDS_TRY(launched(h, s, PC_ATTENTION, 4.0 * h->B * (double)T * T * C, 4.0 * 4.0 * M * C,
-                   launch_attention_f32(h->qkv, h->att, h->B, T, C, h->cfg.n_heads, s), "attention_f32"));
+                   launch_attention_f32(h->qkv, h->att, nullptr, 1, h->B, T, C, h->cfg.n_heads, s), "attention_f32"));
   GemmArgs o = linear_args(h->att, M, C, a.out_w, a.out_b, C, h->th);
   o.R = h->th; o.r_ld = C;
   return run_gemm(h, s, o);
 }
 
 // transformer_1d.py:256-295 + attention.py:130-203
-int run_transformer(lds_handle* h, cudaStream_t s, const XfW& w, const float* x, int T, float* out) {
+int run_transformer_ffma(lds_handle* h, cudaStream_t s, const XfW& w, const float* x, int T, float* out) {
   const int M = h->B * T, C = w.C;
   LDS_TRY(run_gn(h, s, x, C, nullptr, 0, T, w.gn, 1e-6f, nullptr, 0, h->xn));
   LDS_TRY(run_gemm(h, s, linear_args(h->xn, M, C, w.proj_in.w, w.proj_in.b, C, h->th)));
@@ -283,10 +300,131 @@ int run_transformer(lds_handle* h, cudaStream_t s, const XfW& w, const float* x,
   return run_gemm(h, s, po);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// tensor-core path (h->parts = 1: bf16 operands, 3: split-bf16 fp32-accurate).  GEMM A operands are bf16 planes
+// written directly by the producing kernel (GroupNorm/LayerNorm apply, attention, GEGLU / FF epilogues, casts).
+TcGemmArgs tc_base(lds_handle* h, const __nv_bfloat16* A, int batches, int rows, int cin, int taps, const __nv_bfloat16* W,
+                   const float* bias, int N) {
+  TcGemmArgs g;
+  g.A = A; g.batches = batches; g.rows = rows; g.cin = cin; g.taps = taps; g.W = W; g.N = N; g.bias = bias;
+  if (h->parts == 3) tc_set_split_pairs(g);
+  return g;
+}
+void tc_out_f32(TcGemmArgs& g, float* C, int ld) { g.C = C; g.c_ld = ld; g.out_kind = 0; }
+void tc_out_planes(lds_handle* h, TcGemmArgs& g, __nv_bfloat16* C, int n_out) {
+  g.C = C; g.c_ld = h->parts * n_out; g.out_kind = h->parts == 3 ? 2 : 1;
+}
+int run_gemm_tc(lds_handle* h, cudaStream_t s, const TcGemmArgs& g) {
+  const double M = (double)g.batches * g.rows, K = (double)g.taps * g.cin;
+  const double nout = g.epilogue == EPI_GEGLU ? g.N / 2 : g.N;
+  const double esz = 2.0 * g.a_parts;
+  const double bytes = M * g.cin * esz + (double)g.N * K * esz + M * nout * (g.out_kind == 0 ? 4.0 : esz) + (g.R ? M * nout * 4.0 : 0.0);
+  return launched(h, s, g.taps == 3 ? PC_CONV3 : PC_LINEAR, 2.0 * M * g.N * K, bytes, launch_gemm_tc(g, s), "gemm_tc");
+}
+int run_gn_planes(lds_handle* h, cudaStream_t s, const float* x1, int c1, const float* x2, int c2, int T, const NormW& n,
+                  float eps, const float* ss, int silu, __nv_bfloat16* yb, __nv_bfloat16* rawb) {
+  const double elems = (double)h->B * T * (c1 + c2);
+  LDS_TRY(launched(h, s, PC_GN_STATS, 0, 4.0 * elems, launch_gn_stats(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, s),
+                   "gn_stats"));
+  return launched(h, s, PC_GN_APPLY, 0, (4.0 + 2.0 * h->parts * (rawb ? 2 : 1)) * elems,
+                  launch_gn_apply(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, eps, n.g, n.b, ss, silu, nullptr, yb,
+                                  h->parts, rawb, s), "gn_apply");
+}
+int run_ln_planes(lds_handle* h, cudaStream_t s, const float* x, const NormW& n, int rows, int C, __nv_bfloat16* yb) {
+  return launched(h, s, PC_LAYERNORM, 0, (4.0 + 2.0 * h->parts) * rows * C,
+                  launch_layernorm(x, n.g, n.b, 1e-5f, rows, C, nullptr, yb, h->parts, s), "layernorm");
+}
+int run_cast(lds_handle* h, cudaStream_t s, const float* in, int64_t rows, int C, __nv_bfloat16* out) {
+  return launched(h, s, PC_LAYOUT, 0, (4.0 + 2.0 * h->parts) * rows * C, launch_split_cast(in, out, rows, C, h->parts, s), "split_cast");
+}
+
+int run_resnet_tc(lds_handle* h, cudaStream_t s, const ResnetW& r, const float* x1, const float* x2, int T,
+                  const float* temb_row, float* out) {
+  const int M = h->B * T, cin = r.c1 + r.c2;
+  LDS_TRY(run_gn_planes(h, s, x1, r.c1, x2, r.c2, T, r.n1, 1e-5f, nullptr, 1, h->norm_b, r.sc_wh ? h->raw_b : nullptr));
+  TcGemmArgs c1 = tc_base(h, h->norm_b, h->B, T, cin, 3, r.conv1.wh, r.conv1.b, r.cout);
+  tc_out_f32(c1, h->tmp, r.cout);
+  LDS_TRY(run_gemm_tc(h, s, c1));
+  LDS_TRY(run_gn_planes(h, s, h->tmp, r.cout, nullptr, 0, T, r.n2, 1e-5f, temb_row + r.temb_off, 1, h->tmp2_b, nullptr));
+  TcGemmArgs c2 = tc_base(h, h->tmp2_b, h->B, T, r.cout, 3, r.conv2.wh, r.conv2.b, r.cout);
+  tc_out_f32(c2, out, r.cout);
+  if (r.sc_wh) {
+    TcGemmArgs sc = tc_base(h, h->raw_b, 1, M, cin, 1, r.sc_wh, r.sc_b, r.cout);
+    tc_out_f32(sc, out, r.cout);
+    LDS_TRY(run_gemm_tc(h, s, sc));
+    c2.R = out;
+  } else {
+    c2.R = x1;
+  }
+  c2.r_ld = r.cout;
+  return run_gemm_tc(h, s, c2);
+}
+
+int run_attention_tc(lds_handle* h, cudaStream_t s, const AttnW& a, const NormW& ln, int T, int C) {
+  const int M = h->B * T;
+  LDS_TRY(run_ln_planes(h, s, h->th, ln, M, C, h->xn_b));
+  TcGemmArgs q = tc_base(h, h->xn_b, 1, M, C, 1, a.qkv_h, nullptr, 3 * C);
+  tc_out_f32(q, h->qkv, 3 * C);
+  LDS_TRY(run_gemm_tc(h, s, q));
+  LDS_TRY(launched(h, s, PC_ATTENTION, 4.0 * h->B * (double)T * T * C, (3.0 * 4.0 + 2.0 * h->parts) * M * C,
+                   launch_attention_f32(h->qkv, nullptr, h->att_b, h->parts, h->B, T, C, h->cfg.n_heads, s), "attention_f32"));
+  TcGemmArgs o = tc_base(h, h->att_b, 1, M, C, 1, a.out_h, a.out_b, C);
+  tc_out_f32(o, h->th, C);
+  o.R = h->th; o.r_ld = C;
+  return run_gemm_tc(h, s, o);
+}
+
+int run_transformer_tc(lds_handle* h, cudaStream_t s, const XfW& w, const float* x, int T, float* out) {
+  const int M = h->B * T, C = w.C;
+  LDS_TRY(run_gn_planes(h, s, x, C, nullptr, 0, T, w.gn, 1e-6f, nullptr, 0, h->xn_b, nullptr));
+  TcGemmArgs pi = tc_base(h, h->xn_b, 1, M, C, 1, w.proj_in.wh, w.proj_in.b, C);
+  tc_out_f32(pi, h->th, C);
+  LDS_TRY(run_gemm_tc(h, s, pi));
+  LDS_TRY(run_attention_tc(h, s, w.a1, w.ln1, T, C));
+  LDS_TRY(run_attention_tc(h, s, w.a2, w.ln2, T, C));
+  LDS_TRY(run_ln_planes(h, s, h->th, w.ln3, M, C, h->xn_b));
+  TcGemmArgs f1 = tc_base(h, h->xn_b, 1, M, C, 1, w.ff1_h, w.ff1_b, 8 * C);
+  f1.epilogue = EPI_GEGLU;
+  tc_out_planes(h, f1, h->ffh_b, 4 * C);
+  LDS_TRY(run_gemm_tc(h, s, f1));
+  TcGemmArgs f2 = tc_base(h, h->ffh_b, 1, M, 4 * C, 1, w.ff2_h, w.ff2_b, C);
+  f2.R = h->th; f2.r_ld = C;
+  tc_out_planes(h, f2, h->th_b, C);        // only proj_out consumes the block output
+  LDS_TRY(run_gemm_tc(h, s, f2));
+  TcGemmArgs po = tc_base(h, h->th_b, 1, M, C, 1, w.proj_out.wh, w.proj_out.b, C);
+  tc_out_f32(po, out, C);
+  po.R = x; po.r_ld = C;
+  return run_gemm_tc(h, s, po);
+}
+
+// k=3 stride-2 downsample (resnet.py:200) and nearest-upsample + k=3 conv (resnet.py:157-169) on the tensor-core path
+int run_downsample_tc(lds_handle* h, cudaStream_t s, const ConvW& w, const float* x, int t_in, int t_out, float* out) {
+  LDS_TRY(launched(h, s, PC_LAYOUT, 0, 4.0 * h->B * t_in * w.cin + 2.0 * h->parts * 3.0 * h->B * t_out * w.cin,
+                   launch_cast_gather(x, h->cast_b, h->B, t_in, t_out, w.cin, h->parts, 2, 0.f, s), "cast_im2col_s2"));
+  TcGemmArgs g = tc_base(h, h->cast_b, 1, h->B * t_out, 3 * w.cin, 1, w.wh, w.b, w.cout);
+  tc_out_f32(g, out, w.cout);
+  return run_gemm_tc(h, s, g);
+}
+int run_upsample_tc(lds_handle* h, cudaStream_t s, const ConvW& w, const float* x, int t_in, int t_up, float scale, float* out) {
+  LDS_TRY(launched(h, s, PC_LAYOUT, 0, (4.0 + 2.0 * h->parts) * h->B * t_up * w.cin,
+                   launch_cast_gather(x, h->cast_b, h->B, t_in, t_up, w.cin, h->parts, 1, scale, s), "cast_upsample"));
+  TcGemmArgs g = tc_base(h, h->cast_b, h->B, t_up, w.cin, 3, w.wh, w.b, w.cout);
+  tc_out_f32(g, out, w.cout);
+  return run_gemm_tc(h, s, g);
+}
+
 float* other_hid(lds_handle* h, const float* a, const float* b) {
   for (int i = 0; i < 3; ++i)
     if (h->hid[i] != a && h->hid[i] != b) return h->hid[i];
   return nullptr;
+}
+
+int run_resnet(lds_handle* h, cudaStream_t s, const ResnetW& r, const float* x1, const float* x2, int T,
+               const float* temb_row, float* out) {
+  return h->parts ? run_resnet_tc(h, s, r, x1, x2, T, temb_row, out) : run_resnet_ffma(h, s, r, x1, x2, T, temb_row, out);
+}
+int run_transformer(lds_handle* h, cudaStream_t s, const XfW& w, const float* x, int T, float* out) {
+  return h->parts ? run_transformer_tc(h, s, w, x, T, out) : run_transformer_ffma(h, s, w, x, T, out);
 }
 
 // One denoiser evaluation on channels-last state x [B*T, out_dims]; eps out [B*T, out_dims].
@@ -296,7 +434,13 @@ int run_unet(lds_handle* h, cudaStream_t s, const float* x, const float* temb_ro
   const int* ch = c.block_out_channels;
   size_t ri = 0, xi = 0, si = 0;
 
-  {  // conv_in = conv(x part) + [conv(cond part) + bias] (precomputed per sample call)
+  if (h->parts) {  // conv_in = conv(x part) + [conv(cond part) + bias] (precomputed per sample call)
+    LDS_TRY(run_cast(h, s, x, (int64_t)B * h->Tl[0], c.out_dims, h->cast_b));
+    TcGemmArgs g = tc_base(h, h->cast_b, B, h->Tl[0], c.out_dims, 3, h->conv_in_wxh, nullptr, ch[0]);
+    tc_out_f32(g, h->skips[0], ch[0]);
+    g.R = h->cond_part; g.r_ld = ch[0];
+    LDS_TRY(run_gemm_tc(h, s, g));
+  } else {
     ConvW w; w.w = h->conv_in_wx; w.b = nullptr; w.cin = c.out_dims; w.cout = ch[0]; w.taps = 3;
     GemmArgs g = conv3_args(x, B, h->Tl[0], c.out_dims, w, h->skips[0], h->Tl[0], 1);
     g.R = h->cond_part; g.r_ld = ch[0];
@@ -319,7 +463,8 @@ int run_unet(lds_handle* h, cudaStream_t s, const float* x, const float* temb_ro
     }
     if (!last) {
       float* sk = h->skips[si++];
-      LDS_TRY(run_gemm(h, s, conv3_args(cur, B, T, ch[i], h->downs[i], sk, h->Tl[i + 1], 2)));
+      if (h->parts) LDS_TRY(run_downsample_tc(h, s, h->downs[i], cur, T, h->Tl[i + 1], sk));
+      else LDS_TRY(run_gemm(h, s, conv3_args(cur, B, T, ch[i], h->downs[i], sk, h->Tl[i + 1], 2)));
       cur = sk;
     }
   }
@@ -350,12 +495,22 @@ int run_unet(lds_handle* h, cudaStream_t s, const float* x, const float* temb_ro
     if (!last) {
       const int t_up = h->Tl[lvl - 1];
       float* u_out = other_hid(h, cur, nullptr);
-      GemmArgs g = conv3_args(cur, B, T, h->ups[i].cin, h->ups[i], u_out, t_up, 1);
-      g.upsample = 1; g.t_conv = t_up;
-      g.up_scale = (h->T % (1 << (nb - 1)) == 0) ? 0.5f : (float)T / (float)t_up;   // scale_factor=2 vs size= path
-      LDS_TRY(run_gemm(h, s, g));
+      const float up_scale = (h->T % (1 << (nb - 1)) == 0) ? 0.5f : (float)T / (float)t_up;   // scale_factor=2 vs size= path
+      if (h->parts) {
+        LDS_TRY(run_upsample_tc(h, s, h->ups[i], cur, T, t_up, up_scale, u_out));
+      } else {
+        GemmArgs g = conv3_args(cur, B, T, h->ups[i].cin, h->ups[i], u_out, t_up, 1);
+        g.upsample = 1; g.t_conv = t_up; g.up_scale = up_scale;
+        LDS_TRY(run_gemm(h, s, g));
+      }
       cur = u_out;
     }
+  }
+  if (h->parts) {
+    LDS_TRY(run_gn_planes(h, s, cur, ch[0], nullptr, 0, h->Tl[0], h->norm_out, 1e-5f, nullptr, 1, h->norm_b, nullptr));
+    TcGemmArgs g = tc_base(h, h->norm_b, B, h->Tl[0], ch[0], 3, h->conv_out.wh, h->conv_out.b, c.out_dims);
+    tc_out_f32(g, eps, c.out_dims);
+    return run_gemm_tc(h, s, g);
   }
   LDS_TRY(run_gn(h, s, cur, ch[0], nullptr, 0, h->Tl[0], h->norm_out, 1e-5f, nullptr, 1, h->norm));
   return run_gemm(h, s, conv3_args(h->norm, B, h->Tl[0], ch[0], h->conv_out, eps, h->Tl[0], 1));
@@ -395,6 +550,38 @@ const float* need(lds_handle* h, const std::string& key, std::vector<int64_t> sh
   return it->second.v.data();
 }
 
+inline uint16_t host_f2bf(float f) {     // round-to-nearest-even, identical to __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float host_bf2f(uint16_t b) {
+  const uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// fp32 [rows][cin] -> bf16 planes [rows][parts][cin]
+struct PlanePacker {
+  std::vector<uint16_t> host;
+  size_t add(const float* src, size_t rows, int cin, int parts) {
+    size_t off = (host.size() + 127) / 128 * 128;   // 256-byte alignment
+    host.resize(off + rows * parts * cin);
+    for (size_t r = 0; r < rows; ++r)
+      for (int c = 0; c < cin; ++c) {
+        float v = src[r * cin + c];
+        for (int p = 0; p < parts; ++p) {
+          const uint16_t b = host_f2bf(v);
+          host[off + (r * parts + p) * cin + c] = b;
+          v -= host_bf2f(b);
+        }
+      }
+    return off;
+  }
+};
+
 struct Packer {
   std::vector<float> host;
   size_t add(const float* src, size_t n) {
@@ -417,7 +604,8 @@ const char* lds_last_error(void) { return g_last_error.c_str(); }
 int lds_create(const lds_config* cfg, int device, lds_handle** out) {
   if (!cfg || !out) return fail(LDS_ERR_INVALID, "null argument");
   if (cfg->n_blocks < 2 || cfg->n_blocks > LDS_MAX_BLOCKS) return fail(LDS_ERR_INVALID, "n_blocks must be in [2,%d]", LDS_MAX_BLOCKS);
-  if (cfg->precision != LDS_PREC_FP32 && cfg->precision != LDS_PREC_BF16) return fail(LDS_ERR_INVALID, "unknown precision");
+  if (cfg->precision != LDS_PREC_FP32 && cfg->precision != LDS_PREC_BF16 && cfg->precision != LDS_PREC_FP32_FFMA)
+    return fail(LDS_ERR_INVALID, "unknown precision");
   if (cfg->norm_groups < 1 || cfg->norm_groups > 32) return fail(LDS_ERR_INVALID, "norm_groups must be in [1,32]");
   for (int i = 0; i < cfg->n_blocks; ++i) {
     const int c = cfg->block_out_channels[i];
@@ -429,7 +617,12 @@ int lds_create(const lds_config* cfg, int device, lds_handle** out) {
   }
   if (cfg->out_dims % 16 || cfg->n_hidden % 16 || cfg->input_channel % 16)
     return fail(LDS_ERR_INVALID, "out_dims, n_hidden and input_channel must be multiples of 16");
-  if (cfg->precision == LDS_PREC_BF16) return fail(LDS_ERR_UNSUPPORTED, "bf16 tensor-core mode is not built in this version");
+  if (cfg->precision != LDS_PREC_FP32_FFMA) {   // tcgen05 tiles: N multiple of 128, K multiple of 64
+    for (int i = 0; i < cfg->n_blocks; ++i)
+      if (cfg->block_out_channels[i] % 128) return fail(LDS_ERR_UNSUPPORTED, "tensor-core modes need block_out_channels multiples of 128");
+    if (cfg->out_dims % 128 || cfg->n_hidden % 128 || cfg->input_channel % 64)
+      return fail(LDS_ERR_UNSUPPORTED, "tensor-core modes need out_dims, n_hidden multiples of 128 and input_channel multiple of 64");
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || device < 0 || device >= ndev)
@@ -442,6 +635,7 @@ int lds_create(const lds_config* cfg, int device, lds_handle** out) {
   lds_handle* h = new lds_handle();
   h->cfg = *cfg;
   h->device = device;
+  h->parts = cfg->precision == LDS_PREC_FP32 ? 3 : (cfg->precision == LDS_PREC_BF16 ? 1 : 0);
   h->temb_dim = 4 * cfg->block_out_channels[0];
   *out = h;
   return LDS_OK;
@@ -453,6 +647,8 @@ void lds_destroy(lds_handle* h) {
   cudaDeviceSynchronize();
   if (h->arena) cudaFree(h->arena);
   if (h->warena) cudaFree(h->warena);
+  if (h->wharena) cudaFree(h->wharena);
+  if (h->barena) cudaFree(h->barena);
   for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
   delete h;
 }
@@ -496,8 +692,16 @@ int lds_finalize_weights(lds_handle* h) {
   const int* ch = c.block_out_channels;
   const std::string P = "decoder.denoise_fn.";
   Packer pk;
+  PlanePacker pkh;
+  const int parts = h->parts;
   int rc = LDS_OK;
   std::vector<std::pair<const float**, size_t>> fix;   // pointer slots to patch once the arena exists
+  std::vector<std::pair<const __nv_bfloat16**, size_t>> fixh;
+  // GEMM weights: fp32 for the FFMA kernels, bf16 planes [rows][parts][cin] for the tcgen05 kernels
+  auto put_gemm = [&](const float** slot, const __nv_bfloat16** slot_h, const float* src, size_t rows, int cin) {
+    if (parts == 0) fix.emplace_back(slot, pk.add(src, rows * cin));
+    else fixh.emplace_back(slot_h, pkh.add(src, rows, cin, parts));
+  };
   auto put = [&](const float** slot, const float* src, size_t n) { fix.emplace_back(slot, pk.add(src, n)); };
   auto vec = [&](const float** slot, const std::string& key, int64_t n) {
     const float* p = need(h, key, {n}, &rc);
@@ -506,28 +710,35 @@ int lds_finalize_weights(lds_handle* h) {
   };
   auto norm = [&](NormW& nw, const std::string& key, int C) { return vec(&nw.g, key + ".weight", C) && vec(&nw.b, key + ".bias", C); };
   // conv k=3: [cout, cin, 3] -> [cout][tap][cin]
-  auto conv3 = [&](ConvW& w, const std::string& key, int cin, int cout) {
+  auto conv3 = [&](ConvW& w, const std::string& key, int cin, int cout, bool as_im2col = false) {
     const float* src = need(h, key + ".weight", {cout, cin, 3}, &rc);
     if (!src) return false;
     std::vector<float> t((size_t)cout * cin * 3);
     for (int o = 0; o < cout; ++o)
       for (int i = 0; i < cin; ++i)
         for (int k = 0; k < 3; ++k) t[((size_t)o * 3 + k) * cin + i] = src[((size_t)o * cin + i) * 3 + k];
-    put(&w.w, t.data(), t.size());
+    if (as_im2col) put_gemm(&w.w, &w.wh, t.data(), (size_t)cout, 3 * cin);   // K = 3*cin in one plane group
+    else put_gemm(&w.w, &w.wh, t.data(), (size_t)cout * 3, cin);
     w.cin = cin; w.cout = cout; w.taps = 3;
     return vec(&w.b, key + ".bias", cout);
   };
   auto conv1 = [&](ConvW& w, const std::string& key, int cin, int cout) {
     const float* src = need(h, key + ".weight", {cout, cin, 1}, &rc);
     if (!src) return false;
-    put(&w.w, src, (size_t)cout * cin);
+    put_gemm(&w.w, &w.wh, src, (size_t)cout, cin);
     w.cin = cin; w.cout = cout; w.taps = 1;
     return vec(&w.b, key + ".bias", cout);
   };
-  auto lin = [&](const float** w, const float** b, const std::string& key, int in, int out) {
+  auto lin = [&](const float** w, const float** b, const std::string& key, int in, int out) {   // stays fp32 (FFMA kernel)
     const float* src = need(h, key + ".weight", {out, in}, &rc);
     if (!src) return false;
     put(w, src, (size_t)out * in);
+    return b ? vec(b, key + ".bias", out) : true;
+  };
+  auto lin_gemm = [&](const float** w, const __nv_bfloat16** wh, const float** b, const std::string& key, int in, int out) {
+    const float* src = need(h, key + ".weight", {out, in}, &rc);
+    if (!src) return false;
+    put_gemm(w, wh, src, (size_t)out, in);
     return b ? vec(b, key + ".bias", out) : true;
   };
   // The descriptor vectors must not reallocate after slots are taken: reserve exact sizes first.
@@ -556,8 +767,12 @@ int lds_finalize_weights(lds_handle* h) {
         memcpy(&w1[(size_t)o * c1], src + (size_t)o * cin, sizeof(float) * c1);
         if (c2) memcpy(&w2[(size_t)o * c2], src + (size_t)o * cin + c1, sizeof(float) * c2);
       }
-      put(&r.sc_w1, w1.data(), w1.size());
-      if (c2) put(&r.sc_w2, w2.data(), w2.size());
+      if (parts == 0) {
+        put(&r.sc_w1, w1.data(), w1.size());
+        if (c2) put(&r.sc_w2, w2.data(), w2.size());
+      } else {
+        fixh.emplace_back(&r.sc_wh, pkh.add(src, (size_t)cout, cin, parts));
+      }
       if (!vec(&r.sc_b, key + ".conv_shortcut.bias", cout)) return false;
     }
     return true;
@@ -571,8 +786,8 @@ int lds_finalize_weights(lds_handle* h) {
     memcpy(t.data(), q, sizeof(float) * C * C);
     memcpy(t.data() + (size_t)C * C, k, sizeof(float) * C * C);
     memcpy(t.data() + (size_t)2 * C * C, v, sizeof(float) * C * C);
-    put(&a.qkv, t.data(), t.size());
-    return lin(&a.out_w, &a.out_b, key + ".to_out.0", C, C);
+    put_gemm(&a.qkv, &a.qkv_h, t.data(), (size_t)3 * C, C);
+    return lin_gemm(&a.out_w, &a.out_h, &a.out_b, key + ".to_out.0", C, C);
   };
   auto add_xf = [&](const std::string& key, int C) -> bool {
     h->xfs.emplace_back();
@@ -597,14 +812,14 @@ int lds_finalize_weights(lds_handle* h) {
         tb[v_dst] = pb[v_src];
         tb[g_dst] = pb[g_src];
       }
-    put(&w.ff1_w, tw.data(), tw.size());
+    put_gemm(&w.ff1_w, &w.ff1_h, tw.data(), (size_t)8 * C, C);
     put(&w.ff1_b, tb.data(), tb.size());
-    return lin(&w.ff2_w, &w.ff2_b, b + ".ff.net.2", 4 * C, C) && conv1(w.proj_out, key + ".proj_out", C, C);
+    return lin_gemm(&w.ff2_w, &w.ff2_h, &w.ff2_b, b + ".ff.net.2", 4 * C, C) && conv1(w.proj_out, key + ".proj_out", C, C);
   };
 
   bool ok = true;
   // front end (unit2mel.py:54-59)
-  ok = ok && lin(&h->unit_w, &h->unit_b, "unit_embed", c.input_channel, c.n_hidden);
+  ok = ok && lin_gemm(&h->unit_w, &h->unit_wh, &h->unit_b, "unit_embed", c.input_channel, c.n_hidden);
   if (ok && c.n_spk > 1) {
     const float* src = need(h, "spk_embed.weight", {c.n_spk, c.n_hidden}, &rc);
     ok = src != nullptr;
@@ -623,8 +838,8 @@ int lds_finalize_weights(lds_handle* h) {
           for (int i = 0; i < c.n_hidden; ++i)
             wc[((size_t)o * 3 + k) * c.n_hidden + i] = src[((size_t)o * cin + c.out_dims + i) * 3 + k];
         }
-      put(&h->conv_in_wx, wx.data(), wx.size());
-      put(&h->conv_in_wc, wc.data(), wc.size());
+      put_gemm(&h->conv_in_wx, &h->conv_in_wxh, wx.data(), (size_t)ch[0] * 3, c.out_dims);
+      put_gemm(&h->conv_in_wc, &h->conv_in_wch, wc.data(), (size_t)ch[0] * 3, c.n_hidden);
       ok = vec(&h->conv_in_b, P + "conv_in.bias", ch[0]);
     }
   }
@@ -641,7 +856,7 @@ int lds_finalize_weights(lds_handle* h) {
       ok = add_resnet(bk + ".resnets." + std::to_string(j), j == 0 ? c_in : c_out, 0, c_out, i);
       if (ok && !last) ok = add_xf(bk + ".attentions." + std::to_string(j), c_out);
     }
-    if (ok && !last) ok = conv3(h->downs[i], bk + ".downsamplers.0.conv", c_out, c_out);
+    if (ok && !last) ok = conv3(h->downs[i], bk + ".downsamplers.0.conv", c_out, c_out, /*as_im2col=*/parts != 0);
   }
   // mid block
   ok = ok && add_resnet(P + "mid_block.resnets.0", ch[nb - 1], 0, ch[nb - 1], nb - 1) && add_xf(P + "mid_block.attentions.0", ch[nb - 1]) &&
@@ -680,6 +895,12 @@ int lds_finalize_weights(lds_handle* h) {
   LDS_CK(h, cudaMalloc(&h->warena, h->warena_floats * sizeof(float)));
   LDS_CK(h, cudaMemcpy(h->warena, pk.host.data(), h->warena_floats * sizeof(float), cudaMemcpyHostToDevice));
   for (auto& f : fix) *f.first = h->warena + f.second;
+  if (!pkh.host.empty()) {
+    h->wharena_elems = pkh.host.size();
+    LDS_CK(h, cudaMalloc(&h->wharena, h->wharena_elems * sizeof(__nv_bfloat16)));
+    LDS_CK(h, cudaMemcpy(h->wharena, pkh.host.data(), h->wharena_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    for (auto& f : fixh) *f.first = h->wharena + f.second;
+  }
   h->raw.clear();
   h->finalized = true;
   return LDS_OK;
@@ -745,14 +966,16 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
     }
   }
   for (int i = 0; i < 3; ++i) want(&h->hid[i], max_mc);
-  want(&h->norm, max_cat);
   want(&h->tmp, max_mc);
-  want(&h->tmp2, max_mc);
-  want(&h->xn, max_mc);
   want(&h->th, max_mc);
   want(&h->qkv, 3 * max_mc);
-  want(&h->att, max_mc);
-  want(&h->ffh, 4 * max_mc);
+  if (!h->parts) {   // fp32 GEMM operands of the FFMA path (the tensor-core path keeps them as bf16 planes)
+    want(&h->norm, max_cat);
+    want(&h->tmp2, max_mc);
+    want(&h->xn, max_mc);
+    want(&h->att, max_mc);
+    want(&h->ffh, 4 * max_mc);
+  }
   const size_t nx = M0 * c.out_dims;
   want(&h->x, nx); want(&h->xb, nx); want(&h->xp, nx); want(&h->eps, nx);
   for (int i = 0; i < 3; ++i) want(&h->mbuf[i], nx);
@@ -760,6 +983,30 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
   h->arena_floats = off;
   LDS_CK(h, cudaMalloc(&h->arena, off * sizeof(float)));
   for (auto& s : slots) *s.first = h->arena + s.second;
+  if (h->barena) { cudaFree(h->barena); h->barena = nullptr; }
+  h->barena_elems = 0;
+  if (h->parts) {
+    const size_t P = (size_t)h->parts;
+    size_t boff = 0;
+    std::vector<std::pair<__nv_bfloat16**, size_t>> bslots;
+    auto wantb = [&](__nv_bfloat16** p, size_t n) { bslots.emplace_back(p, boff); boff += (n + 127) / 128 * 128; };
+    size_t cast_max = std::max(M0 * (size_t)c.input_channel, M0 * (size_t)std::max(c.n_hidden, c.out_dims));
+    for (int i = 0; i + 1 < nb; ++i) {
+      cast_max = std::max(cast_max, (size_t)B * h->Tl[i + 1] * 3 * ch[i]);      // stride-2 im2col of level i
+      cast_max = std::max(cast_max, (size_t)B * h->Tl[i] * ch[i + 1]);          // upsampled level i+1
+    }
+    wantb(&h->norm_b, max_cat * P);
+    wantb(&h->raw_b, max_cat * P);
+    wantb(&h->tmp2_b, max_mc * P);
+    wantb(&h->xn_b, max_mc * P);
+    wantb(&h->att_b, max_mc * P);
+    wantb(&h->ffh_b, 4 * max_mc * P);
+    wantb(&h->th_b, max_mc * P);
+    wantb(&h->cast_b, cast_max * P);
+    h->barena_elems = boff;
+    LDS_CK(h, cudaMalloc(&h->barena, boff * sizeof(__nv_bfloat16)));
+    for (auto& b : bslots) *b.first = h->barena + b.second;
+  }
 
   // ---- per-step time conditioning (batch invariant) ----
   if (n_nfe > 0) {
@@ -777,13 +1024,21 @@ int lds_cond(lds_handle* h, const float* units, const int64_t* spk_id, float* co
   cudaStream_t s = (cudaStream_t)stream;
   LDS_CK(h, cudaSetDevice(h->device));
   const lds_config& c = h->cfg;
-  GemmArgs g = linear_args(units, h->B * h->T, c.input_channel, h->unit_w, h->unit_b, c.n_hidden, cond);
   if (c.n_spk > 1) {
     if (!spk_id) return fail(LDS_ERR_INVALID, "lds_cond: spk_id required when n_spk > 1");
     LDS_TRY(launched(h, s, PC_LAYOUT, 0, 4.0 * h->B * c.n_hidden,
                      launch_spk_gather(h->spk_table, spk_id, c.n_spk, h->B, c.n_hidden, h->spk_rows, s), "spk_gather"));
-    g.R = h->spk_rows; g.r_ld = c.n_hidden; g.r_div = h->T;
   }
+  if (h->parts) {
+    const int M = h->B * h->T;
+    LDS_TRY(run_cast(h, s, units, M, c.input_channel, h->cast_b));
+    TcGemmArgs g = tc_base(h, h->cast_b, 1, M, c.input_channel, 1, h->unit_wh, h->unit_b, c.n_hidden);
+    tc_out_f32(g, cond, c.n_hidden);
+    if (c.n_spk > 1) { g.R = h->spk_rows; g.r_ld = c.n_hidden; g.r_div = h->T; }
+    return run_gemm_tc(h, s, g);
+  }
+  GemmArgs g = linear_args(units, h->B * h->T, c.input_channel, h->unit_w, h->unit_b, c.n_hidden, cond);
+  if (c.n_spk > 1) { g.R = h->spk_rows; g.r_ld = c.n_hidden; g.r_div = h->T; }
   return run_gemm(h, s, g);
 }
 
@@ -792,6 +1047,12 @@ static int bind_cond(lds_handle* h, cudaStream_t s, const float* cond) {
   const lds_config& c = h->cfg;
   ConvW w; w.w = h->conv_in_wc; w.b = h->conv_in_b; w.cin = c.n_hidden; w.cout = c.block_out_channels[0]; w.taps = 3;
   h->cond_bound = cond;
+  if (h->parts) {
+    LDS_TRY(run_cast(h, s, cond, (int64_t)h->B * h->T, c.n_hidden, h->cast_b));
+    TcGemmArgs g = tc_base(h, h->cast_b, h->B, h->T, c.n_hidden, 3, h->conv_in_wch, h->conv_in_b, w.cout);
+    tc_out_f32(g, h->cond_part, w.cout);
+    return run_gemm_tc(h, s, g);
+  }
   return run_gemm(h, s, conv3_args(cond, h->B, h->T, c.n_hidden, w, h->cond_part, h->T, 1));
 }
 
@@ -902,7 +1163,9 @@ int lds_sample(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, co
   return lds_sample_end(h, mel_BTM, stream);
 }
 
-int64_t lds_workspace_bytes(const lds_handle* h) { return h ? (int64_t)((h->arena_floats + h->warena_floats) * sizeof(float)) : 0; }
+int64_t lds_workspace_bytes(const lds_handle* h) {
+  return h ? (int64_t)((h->arena_floats + h->warena_floats) * sizeof(float) + (h->barena_elems + h->wharena_elems) * 2) : 0;
+}
 int64_t lds_kernel_launches(const lds_handle* h) { return h ? h->launches : 0; }
 
 int lds_set_profiling(lds_handle* h, int enabled) {
@@ -939,7 +1202,7 @@ int lds_op_gemm(const float* A, int a_ld, const float* w, const float* bias, con
 }
 int lds_op_attention(const float* qkv, float* out, int B, int T, int C, int heads, void* stream) {
   if (!qkv || !out) return fail(LDS_ERR_INVALID, "lds_op_attention: null tensor");
-  return op_status(lds::launch_attention_f32(qkv, out, B, T, C, heads, (cudaStream_t)stream), "lds_op_attention");
+  return op_status(lds::launch_attention_f32(qkv, out, nullptr, 1, B, T, C, heads, (cudaStream_t)stream), "lds_op_attention");
 }
 int lds_op_groupnorm(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps, const float* gamma,
                      const float* beta, const float* scale_shift, int silu, float* part, float* y, void* stream) {
@@ -947,12 +1210,12 @@ int lds_op_groupnorm(const float* x1, int c1, const float* x2, int c2, int B, in
   cudaStream_t s = (cudaStream_t)stream;
   int rc = op_status(lds::launch_gn_stats(x1, c1, x2, c2, B, T, groups, part, s), "lds_op_groupnorm(stats)");
   if (rc != LDS_OK) return rc;
-  return op_status(lds::launch_gn_apply(x1, c1, x2, c2, B, T, groups, part, eps, gamma, beta, scale_shift, silu, y, s),
+  return op_status(lds::launch_gn_apply(x1, c1, x2, c2, B, T, groups, part, eps, gamma, beta, scale_shift, silu, y, nullptr, 1, nullptr, s),
                    "lds_op_groupnorm(apply)");
 }
 int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y, void* stream) {
   if (!x || !gamma || !beta || !y) return fail(LDS_ERR_INVALID, "lds_op_layernorm: null tensor");
-  return op_status(lds::launch_layernorm(x, gamma, beta, eps, rows, C, y, (cudaStream_t)stream), "lds_op_layernorm");
+  return op_status(lds::launch_layernorm(x, gamma, beta, eps, rows, C, y, nullptr, 1, (cudaStream_t)stream), "lds_op_layernorm");
 }
 
 int lds_op_split_cast(const float* in, void* out_bf16, int64_t rows, int C, int parts, void* stream) {

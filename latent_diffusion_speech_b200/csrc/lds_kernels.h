@@ -56,10 +56,17 @@ inline void tc_set_split_pairs(TcGemmArgs& a) {   // lo*hi, hi*lo, mid*mid, mid*
 }
 // fp32 [rows, C] -> bf16 [rows, parts*C]: parts=1 plain rounding; parts=3 hi/mid/lo planes (x == hi+mid+lo to 24 bits)
 cudaError_t launch_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, cudaStream_t s);
+// Gathering casts for the two resampling convolutions (channels-last [B, t, C] fp32 -> bf16 planes):
+//  mode 1: nearest upsample to t_out frames, out [B, t_out, parts*C], src = min(floor(u*scale), t_in-1)   (resnet.py:157-160)
+//  mode 2: k=3 / stride-2 / pad-1 im2col, out [B, t_out, parts*3C] with element (p, tap, c) at p*3C + tap*C + c  (resnet.py:200)
+cudaError_t launch_cast_gather(const float* in, __nv_bfloat16* out, int B, int t_in, int t_out, int C, int parts, int mode,
+                               float scale, cudaStream_t s);
 
 // Flash-style self-attention on a fused QKV buffer [B*T, 3C]: head h uses columns
 // [h*d,(h+1)*d) of each C-wide third.  out [B*T, C].  softmax(q k^T / sqrt(d)) v, no mask.
-cudaError_t launch_attention_f32(const float* qkv, float* out, int B, int T, int C, int heads, cudaStream_t s);
+// Output: fp32 `out` [B*T, C], or (outb != nullptr) bf16 operand planes [B*T, parts*C] for the following tensor-core GEMM.
+cudaError_t launch_attention_f32(const float* qkv, float* out, __nv_bfloat16* outb, int parts, int B, int T, int C, int heads,
+                                 cudaStream_t s);
 
 // GroupNorm over a (virtually concatenated) channels-last tensor [x1 | x2].
 //  stats : partial (count, mean, M2) per (b, chunk of GN_ROWS frames, group) -> part[B][nchunk][G][3]
@@ -69,11 +76,13 @@ cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, in
                             cudaStream_t s);
 cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups,
                             const float* part, float eps, const float* gamma, const float* beta, const float* ss,
-                            int silu, float* y, cudaStream_t s);
+                            int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s);
+//  (yb != nullptr: write bf16 operand planes [B*T, parts*C] instead of fp32 y; rawb: also copy the un-normalised
+//   concat input as planes — the A operand of the 1x1 shortcut convolution)
 
 // LayerNorm over the last dim of [rows, C].
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
-                             cudaStream_t s);
+                             __nv_bfloat16* yb, int parts, cudaStream_t s);
 
 // [B, C, T] <-> [B, T, C] tiled transposes; `scale` multiplies on the way.
 cudaError_t launch_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, float scale, cudaStream_t s);

@@ -9,6 +9,7 @@
 //   torch.cat([hidden, skip], dim=1)       unet_1d_blocks.py:2084,2186  (virtual: two source pointers)
 //   nn.LayerNorm(C)                        attention.py:83,102,118
 #include "lds_kernels.h"
+#include "planes.cuh"
 
 namespace lds {
 namespace {
@@ -76,7 +77,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        int c2, int T, int groups, const float* __restrict__ part,
                                                        float eps, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ ss,
-                                                       int silu, float* __restrict__ y) {
+                                                       int silu, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+                                                       int parts, __nv_bfloat16* __restrict__ rawb) {
   __shared__ float s_mean[32], s_rstd[32];
   const int C = c1 + c2, V = C >> 2, cg = C / groups;
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
@@ -106,7 +108,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
       o[2] = o[2] * (1.f + sc.z) + sf.z; o[3] = o[3] * (1.f + sc.w) + sf.w;
     }
     if (silu) { o[0] = silu_f(o[0]); o[1] = silu_f(o[1]); o[2] = silu_f(o[2]); o[3] = silu_f(o[3]); }
-    *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (yb) store_planes4(yb + row * (size_t)(parts * C), c, C, parts, o[0], o[1], o[2], o[3]);
+    else *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (rawb) store_planes4(rawb + row * (size_t)(parts * C), c, C, parts, xv.x, xv.y, xv.z, xv.w);
   }
 }
 
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 constexpr int LN_MAXV = 8;
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int rows, int C,
-                                                        float* __restrict__ y) {
+                                                        float* __restrict__ y, __nv_bfloat16* __restrict__ yb, int parts) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int V = C >> 2;
@@ -144,15 +148,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
   const float rstd = rsqrtf(sq / (float)C + eps);
-  float4* dst = reinterpret_cast<float4*>(y + (size_t)warp * C);
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) {
     const int q = lane + 32 * i;
     if (q < V) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
       const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + q);
-      dst[q] = make_float4((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y,
-                           (v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
+      const float4 o = make_float4((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y,
+                                   (v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
+      if (yb) store_planes4(yb + (size_t)warp * (parts * C), q * 4, C, parts, o.x, o.y, o.z, o.w);
+      else reinterpret_cast<float4*>(y + (size_t)warp * C)[q] = o;
     }
   }
 }
@@ -175,20 +180,20 @@ cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, in
 
 cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups,
                             const float* part, float eps, const float* gamma, const float* beta, const float* ss,
-                            int silu, float* y, cudaStream_t s) {
+                            int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s) {
   const int C = c1 + c2;
   if (C % (4 * groups) || c1 % 4 || groups > 32) return cudaErrorInvalidValue;
   dim3 grid((T + GN_ROWS - 1) / GN_ROWS, B);
-  gn_apply_kernel<<<grid, 256, 0, s>>>(x1, c1, x2, c2, T, groups, part, eps, gamma, beta, ss, silu, y);
+  gn_apply_kernel<<<grid, 256, 0, s>>>(x1, c1, x2, c2, T, groups, part, eps, gamma, beta, ss, silu, y, yb, parts, rawb);
   return cudaGetLastError();
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
-                             cudaStream_t s) {
+                             __nv_bfloat16* yb, int parts, cudaStream_t s) {
   if (C % 4 || C > 128 * LN_MAXV) return cudaErrorInvalidValue;
   const int warps_per_block = 8;
   const int grid = (rows + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y);
+  layernorm_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y, yb, parts);
   return cudaGetLastError();
 }
 

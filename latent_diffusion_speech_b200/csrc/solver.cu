@@ -12,6 +12,7 @@
 //   DDPM ancestral step (x0 clamp, posterior mean, + sigma*z)    diffusion.py:95-121
 //   [B,1,M,T] <-> channels-last [B,T,M], /acoustic_scale         diffusion.py:225,342-343
 #include "lds_kernels.h"
+#include "planes.cuh"
 
 namespace lds {
 namespace {
@@ -187,6 +188,32 @@ __global__ void split_cast_kernel(const float4* __restrict__ in, __nv_bfloat16* 
   }
 }
 
+__global__ void cast_gather_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int t_in, int t_out, int C,
+                                   int parts, int mode, float scale, int64_t n) {
+  const int V = C >> 2;
+  const int taps = mode == 2 ? 3 : 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    int64_t r = i / V;
+    const int tap = (int)(r % taps);
+    r /= taps;
+    const int to = (int)(r % t_out);
+    const int b = (int)(r / t_out);
+    int src;
+    bool ok = true;
+    if (mode == 1) {
+      src = min((int)floorf((float)to * scale), t_in - 1);
+    } else {
+      src = 2 * to - 1 + tap;
+      ok = src >= 0 && src < t_in;
+    }
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) q = __ldg(reinterpret_cast<const float4*>(in + ((size_t)b * t_in + src) * C) + v);
+    const int Cw = taps * C;   // plane width of the output row
+    store_planes4(out + ((size_t)b * t_out + to) * (size_t)(parts * Cw), tap * C + v * 4, Cw, parts, q.x, q.y, q.z, q.w);
+  }
+}
+
 inline int grid_for(int64_t nvec) {
   int64_t g = (nvec + 255) / 256;
   const int64_t cap = 148 * 16;
@@ -247,6 +274,13 @@ cudaError_t launch_div_copy(const float* in, float* out, int64_t n, float diviso
 cudaError_t launch_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, cudaStream_t s) {
   if (C % 4 || parts < 1 || parts > 3) return cudaErrorInvalidValue;
   split_cast_kernel<<<grid_for(rows * (C / 4)), 256, 0, s>>>(V4(in), out, rows, C, parts);
+  return cudaGetLastError();
+}
+cudaError_t launch_cast_gather(const float* in, __nv_bfloat16* out, int B, int t_in, int t_out, int C, int parts, int mode,
+                               float scale, cudaStream_t s) {
+  if (C % 4 || parts < 1 || parts > 3 || (mode != 1 && mode != 2)) return cudaErrorInvalidValue;
+  const int64_t n = (int64_t)B * t_out * (mode == 2 ? 3 : 1) * (C / 4);
+  cast_gather_kernel<<<grid_for(n), 256, 0, s>>>(in, out, t_in, t_out, C, parts, mode, scale, n);
   return cudaGetLastError();
 }
 cudaError_t launch_silu(const float* in, float* out, int64_t n, cudaStream_t s) {

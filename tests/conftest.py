@@ -41,13 +41,22 @@ def state_dict(host_model):
     return {k: v.detach().clone() for k, v in host_model.state_dict().items()}
 
 
-@pytest.fixture(scope="session")
-def gpu_model(host_model):
+_GPU_MODELS = {}
+
+
+def gpu_model_for(host_model, precision):
+    """One GPU copy of the model per precision mode (fp32 = split-bf16 tcgen05, fp32_ffma, bf16)."""
     import copy
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    m = copy.deepcopy(host_model).cuda().eval()
-    return m
+    if precision not in _GPU_MODELS:
+        _GPU_MODELS[precision] = copy.deepcopy(host_model).cuda().eval().set_precision(precision)
+    return _GPU_MODELS[precision]
+
+
+@pytest.fixture(scope="session")
+def gpu_model(host_model):
+    return gpu_model_for(host_model, "fp32")
 
 
 def load_golden(name):

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 import gpu_util as G
-from conftest import golden_names, load_golden
+from conftest import golden_names, gpu_model_for, load_golden
 from oracle import unit2mel_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -40,8 +40,14 @@ def _run_cuda(model, units, spk, noise, steps, gt, method, speedup, k_step):
     return mel.cpu()
 
 
+FP32_MODES = ["fp32", "fp32_ffma"]     # split-bf16 tcgen05 (default) and the CUDA-core FFMA implementation
+TOL_BF16_REL_L2 = 1e-2                 # BASELINE.json north_star: relative L2 <= 1e-2 in bf16 mode
+
+
+@pytest.mark.parametrize("precision", FP32_MODES)
 @pytest.mark.parametrize("name", golden_names("nfe_"))
-def test_denoiser_eval_vs_reference_golden(name, gpu_model, state_dict):
+def test_denoiser_eval_vs_reference_golden(name, precision, host_model, state_dict):
+    gpu_model = gpu_model_for(host_model, precision)
     g = load_golden(name)
     B, T = int(g["B"]), int(g["T"])
     _, _, noise, _, _ = O.synthetic_inputs(B, T)
@@ -51,26 +57,50 @@ def test_denoiser_eval_vs_reference_golden(name, gpu_model, state_dict):
     with torch.no_grad():
         e64 = G.errs(eps, O.unet_forward({k: v.double() for k, v in state_dict.items()}, O.DEFAULT_CFG,
                                          torch.cat([noise[:, 0], cond], dim=-2).double(), torch.full((B,), float(g["t"])).double()))
-    G.report(test="denoise_golden", name=name, vs_ref=e, vs_fp64=e64)
+    G.report(test="denoise_golden", precision=precision, name=name, vs_ref=e, vs_fp64=e64)
     assert e["max_abs"] <= 5e-5 and e64["max_abs"] <= 5e-5, (e, e64)
 
 
+_FP64_CACHE = {}
+
+
+def _fp64_reference(name, state_dict, units, spk, noise, method, speedup, gt, k_step, steps):
+    if name not in _FP64_CACHE:
+        with torch.no_grad():
+            _FP64_CACHE[name] = O.unit2mel_infer(state_dict, O.DEFAULT_CFG, units, spk, noise, method, speedup, gt_spec=gt,
+                                                 k_step=k_step, step_noises=steps, dtype=torch.float64)
+    return _FP64_CACHE[name]
+
+
+@pytest.mark.parametrize("precision", FP32_MODES)
 @pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("nfe_")])
-def test_sampler_vs_reference_golden(name, gpu_model, state_dict):
+def test_sampler_vs_reference_golden(name, precision, host_model, state_dict):
+    gpu_model = gpu_model_for(host_model, precision)
     g = load_golden(name)
     B, T, k_step, method, speedup, units, spk, noise, steps, gt = _inputs(g)
     mel = _run_cuda(gpu_model, units, spk, noise, steps, gt, method, speedup, k_step)
     want = torch.from_numpy(g["mel"])
     e = G.errs(mel, want)
-    with torch.no_grad():
-        ref64 = O.unit2mel_infer(state_dict, O.DEFAULT_CFG, units, spk, noise, method, speedup, gt_spec=gt, k_step=k_step,
-                                 step_noises=steps, dtype=torch.float64)
+    ref64 = _fp64_reference(name, state_dict, units, spk, noise, method, speedup, gt, k_step, steps)
     e64 = G.errs(mel, ref64)
     floor = G.errs(want, ref64)                                # the reference's own fp32 round-off on this case
-    G.report(test="sampler_golden", name=name, vs_ref=e, vs_fp64=e64, ref_fp32_vs_fp64=floor)
+    G.report(test="sampler_golden", precision=precision, name=name, vs_ref=e, vs_fp64=e64, ref_fp32_vs_fp64=floor)
     assert mel.shape == want.shape
     assert e64["max_abs"] <= TOL_VS_FP64, (e64, floor)
     assert e["max_abs"] <= TOL_VS_REF_FP32, (e, floor)
+
+
+@pytest.mark.parametrize("name", ["dpm20_b2_t40", "unipc10_b2_t37", "shallow_dpm20_b2_t32", "ddpm12_b2_t24"])
+def test_sampler_bf16_mode(name, host_model, state_dict):
+    """bf16 GEMM operands (tcgen05), fp32 accumulation / norms / solver: relative L2 <= 1e-2 vs the fp64 oracle."""
+    gpu_model = gpu_model_for(host_model, "bf16")
+    g = load_golden(name)
+    B, T, k_step, method, speedup, units, spk, noise, steps, gt = _inputs(g)
+    mel = _run_cuda(gpu_model, units, spk, noise, steps, gt, method, speedup, k_step)
+    ref64 = _fp64_reference(name, state_dict, units, spk, noise, method, speedup, gt, k_step, steps)
+    e64 = G.errs(mel, ref64)
+    G.report(test="sampler_bf16", name=name, vs_fp64=e64)
+    assert e64["rel_l2"] <= TOL_BF16_REL_L2, e64
 
 
 def test_cond_matches_reference_expression(gpu_model, state_dict):
