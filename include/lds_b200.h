@@ -175,6 +175,12 @@ LDS_API int lds_op_split_cast(const float* in, void* out_bf16, int64_t rows, int
 LDS_API int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, int parts, const void* w_bf16, int N, int taps,
                    const float* bias, const float* R, int r_ld, int r_div, void* C, int c_ld, int out_kind,
                    int epilogue, void* stream);
+/* Fused QKV projection + tcgen05 flash attention (attention_processor.py:1012-1034) on bf16 planes:
+ *   x planes [B*T][parts*C] -> q/k/v^T scratch (layouts in lds_kernels.h) -> out planes [B*T][parts*C].
+ *   w_qkv: bf16 [3*H*dpad][parts*C], rows = [q | k | v] x heads x dpad (head dim zero-padded to dpad in {32,64}).
+ *   scratch sizes (bf16 elements): q, k: B*T*parts*H*dpad; vt: B*parts*H*dpad*T_pad, T_pad = round_up(T, 8). */
+LDS_API int lds_op_qkv_attention_tc(const void* x_planes, const void* w_qkv, int B, int T, int C, int H, int dpad, int parts,
+                            void* q_scratch, void* k_scratch, void* vt_scratch, void* out_planes, void* stream);
 
 #ifdef __cplusplus
 }

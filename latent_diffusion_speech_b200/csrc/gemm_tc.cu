@@ -24,6 +24,7 @@
 #include <unordered_map>
 
 #include "lds_kernels.h"
+#include "tc_ptx.cuh"
 
 namespace lds {
 namespace {
@@ -41,82 +42,14 @@ struct TcParams {
   int N;
   const float* bias;
   const float* R; int r_ld, r_div;
-  void* C; int c_ld; int out_kind;      // 0 fp32, 1 bf16, 2 split bf16 (3 planes of c_ld/3 columns)
+  void* C; int c_ld; int out_kind;      // 0 fp32, 1 bf16, 2 split bf16 (3 planes of c_ld/3 columns), 3 attention operands
   int epilogue;
+  __nv_bfloat16 *q_out, *k_out, *vt_out; int att_T, att_H, att_dpad, att_Tpad;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128-byte swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B).
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);   // start address
-  d |= (uint64_t)0 << 16;                   // leading byte offset (unused: one swizzle atom along K)
-  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row atoms
-  d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
+using namespace ptx;
+constexpr uint32_t kIdesc = umma_idesc_bf16(TBM, TBN);
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) { return umma_desc_kmajor(saddr, 128); }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
@@ -160,6 +93,43 @@ __device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int c
   }
 }
 
+// out_kind 3: 32 consecutive columns of the fused [q | k | v] projection (one head, one of q/k/v) as attention operands
+__device__ __forceinline__ void store_qkv32(const TcParams& p, size_t row, int col, const float* v) {
+  const int parts = p.w_parts, HD = p.att_H * p.att_dpad;
+  const int region = col / HD, rem = col - region * HD;
+  float r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = v[i];
+  if (region < 2) {
+    __nv_bfloat16* base = (region == 0 ? p.q_out : p.k_out) + row * (size_t)(parts * HD) + rem;
+    for (int pl = 0; pl < parts; ++pl) {
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const __nv_bfloat16 a = __float2bfloat16_rn(r[2 * i]), b = __float2bfloat16_rn(r[2 * i + 1]);
+        r[2 * i] -= __bfloat162float(a);
+        r[2 * i + 1] -= __bfloat162float(b);
+        w[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(base + (size_t)pl * HD);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+  } else {
+    const int bb = (int)(row / p.att_T), tt = (int)(row - (size_t)bb * p.att_T);
+    const int hh = rem / p.att_dpad, j0 = rem - hh * p.att_dpad;
+    for (int pl = 0; pl < parts; ++pl) {
+      __nv_bfloat16* dst = p.vt_out + ((size_t)((bb * parts + pl) * p.att_H + hh) * p.att_dpad + j0) * p.att_Tpad + tt;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {          // lanes hold consecutive frames: each store is a coalesced 64 B row segment
+        const __nv_bfloat16 a = __float2bfloat16_rn(r[i]);
+        r[i] -= __bfloat162float(a);
+        dst[(size_t)i * p.att_Tpad] = a;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -179,18 +149,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int t0 = (blockIdx.y - b * p.tiles_per_batch) * TBM;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapW)) : "memory");
+    prefetch_tensormap(&mapA);
+    prefetch_tensormap(&mapW);
     for (int s = 0; s < TSTAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   } else if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
@@ -228,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint64_t wd = umma_smem_desc(w_base + s * W_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < TBK / 16; ++k)   // +32 B (16 bf16) along K inside the swizzle atom per UMMA_K step
-          umma_bf16(tmem_acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), (it > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), kIdesc, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(empty_bar(s));
       }
       umma_commit(tmem_full_bar);
@@ -289,7 +257,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
             }
           }
-          store_row32(p, grow, col, p.N, v);
+          if (p.out_kind == 3) store_qkv32(p, grow, col, v);
+          else store_row32(p, grow, col, p.N, v);
         }
       }
     }
@@ -298,7 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TMEM_COLS) : "memory");
+    tmem_dealloc(tmem_acc, TMEM_COLS);
   }
 }
 
@@ -372,12 +341,27 @@ cudaError_t get_map(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint
 
 }  // namespace
 
-void tc_gemm_forget_maps() {}
+// generic bf16 tiled tensor map (rank 2 or 3) with a 32/64/128-byte swizzle and zero out-of-bounds fill
+cudaError_t tc_make_map_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                             int swizzle_bytes, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  if (rank < 2 || rank > 3) return cudaErrorInvalidValue;
+  cuuint64_t d[3], st[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
 
 cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (a.batches <= 0 || a.rows <= 0 || a.N <= 0) return cudaSuccess;
   if (a.cin % TBK || a.N % TBN || (a.taps != 1 && a.taps != 3) || a.n_pairs < 1 || a.n_pairs > 6 || a.a_parts < 1 ||
-      a.w_parts < 1 || a.c_ld % 8 || (a.R && a.r_ld % 4) || a.r_div < 1)
+      a.w_parts < 1 || (a.out_kind != 3 && a.c_ld % 8) || (a.R && a.r_ld % 4) || a.r_div < 1)
     return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
@@ -397,6 +381,11 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   for (int i = 0; i < 6; ++i) { p.pair_a[i] = a.pair_a[i]; p.pair_w[i] = a.pair_w[i]; }
   p.N = a.N; p.bias = a.bias; p.R = a.R; p.r_ld = a.r_ld; p.r_div = a.r_div;
   p.C = a.C; p.c_ld = a.c_ld; p.out_kind = a.out_kind; p.epilogue = a.epilogue;
+  p.q_out = a.q_out; p.k_out = a.k_out; p.vt_out = a.vt_out;
+  p.att_T = a.att_T; p.att_H = a.att_H; p.att_dpad = a.att_dpad; p.att_Tpad = a.att_Tpad;
+  if (a.out_kind == 3 && (!a.q_out || !a.k_out || !a.vt_out || a.att_T < 1 || a.att_dpad % 32 || a.N != 3 * a.att_H * a.att_dpad ||
+                          a.epilogue != EPI_NONE))
+    return cudaErrorInvalidValue;
   dim3 grid(a.N / TBN, p.tiles_per_batch * a.batches);
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(mA, mW, p);
   return cudaGetLastError();

@@ -126,7 +126,7 @@ struct lds_handle {
   __nv_bfloat16* barena = nullptr;          // bf16 operand buffers (tensor-core modes)
   size_t barena_elems = 0;
   __nv_bfloat16 *norm_b = nullptr, *raw_b = nullptr, *tmp2_b = nullptr, *xn_b = nullptr, *att_b = nullptr, *ffh_b = nullptr,
-                *th_b = nullptr, *cast_b = nullptr;
+                *th_b = nullptr, *cast_b = nullptr, *q_b = nullptr, *k_b = nullptr, *vt_b = nullptr;
   const float* cond_bound = nullptr;
   int m_cur = 0;                            // index of m0 in mbuf; m1 = (m_cur+2)%3, free = (m_cur+1)%3
   // bookkeeping
@@ -363,11 +363,16 @@ int run_resnet_tc(lds_handle* h, cudaStream_t s, const ResnetW& r, const float* 
 int run_attention_tc(lds_handle* h, cudaStream_t s, const AttnW& a, const NormW& ln, int T, int C) {
   const int M = h->B * T;
   LDS_TRY(run_ln_planes(h, s, h->th, ln, M, C, h->xn_b));
-  TcGemmArgs q = tc_base(h, h->xn_b, 1, M, C, 1, a.qkv_h, nullptr, 3 * C);
-  tc_out_f32(q, h->qkv, 3 * C);
+  const int H = h->cfg.n_heads, d = C / H, dpad = d <= 32 ? 32 : 64, t_pad = (T + 7) / 8 * 8;
+  TcGemmArgs q = tc_base(h, h->xn_b, 1, M, C, 1, a.qkv_h, nullptr, 3 * H * dpad);
+  q.out_kind = 3; q.q_out = h->q_b; q.k_out = h->k_b; q.vt_out = h->vt_b;
+  q.att_T = T; q.att_H = H; q.att_dpad = dpad; q.att_Tpad = t_pad;
   LDS_TRY(run_gemm_tc(h, s, q));
-  LDS_TRY(launched(h, s, PC_ATTENTION, 4.0 * h->B * (double)T * T * C, (3.0 * 4.0 + 2.0 * h->parts) * M * C,
-                   launch_attention_f32(h->qkv, nullptr, h->att_b, h->parts, h->B, T, C, h->cfg.n_heads, s), "attention_f32"));
+  AttnTcArgs at;
+  at.q = h->q_b; at.k = h->k_b; at.vt = h->vt_b; at.out = h->att_b;
+  at.B = h->B; at.T = T; at.T_pad = t_pad; at.H = H; at.d = d; at.dpad = dpad; at.parts = h->parts;
+  LDS_TRY(launched(h, s, PC_ATTENTION, 4.0 * h->B * (double)T * T * C, 2.0 * h->parts * (3.0 * M * H * dpad + (double)M * C),
+                   launch_attention_tc(at, s), "attention_tc"));
   TcGemmArgs o = tc_base(h, h->att_b, 1, M, C, 1, a.out_h, a.out_b, C);
   tc_out_f32(o, h->th, C);
   o.R = h->th; o.r_ld = C;
@@ -786,7 +791,16 @@ int lds_finalize_weights(lds_handle* h) {
     memcpy(t.data(), q, sizeof(float) * C * C);
     memcpy(t.data() + (size_t)C * C, k, sizeof(float) * C * C);
     memcpy(t.data() + (size_t)2 * C * C, v, sizeof(float) * C * C);
-    put_gemm(&a.qkv, &a.qkv_h, t.data(), (size_t)3 * C, C);
+    if (parts == 0) {
+      put(&a.qkv, t.data(), t.size());
+    } else {   // [q | k | v] x heads x dpad rows, head dim zero-padded to 32/64 (attention_tc.cu operand layout)
+      const int H = c.n_heads, d = C / H, dpad = d <= 32 ? 32 : 64;
+      std::vector<float> tp((size_t)3 * H * dpad * C, 0.f);
+      for (int r = 0; r < 3; ++r)
+        for (int hh = 0; hh < H; ++hh)
+          memcpy(&tp[((size_t)(r * H + hh) * dpad) * C], &t[((size_t)r * C + (size_t)hh * d) * C], sizeof(float) * d * C);
+      fixh.emplace_back(&a.qkv_h, pkh.add(tp.data(), (size_t)3 * H * dpad, C, parts));
+    }
     return lin_gemm(&a.out_w, &a.out_h, &a.out_b, key + ".to_out.0", C, C);
   };
   auto add_xf = [&](const std::string& key, int C) -> bool {
@@ -968,8 +982,8 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
   for (int i = 0; i < 3; ++i) want(&h->hid[i], max_mc);
   want(&h->tmp, max_mc);
   want(&h->th, max_mc);
-  want(&h->qkv, 3 * max_mc);
-  if (!h->parts) {   // fp32 GEMM operands of the FFMA path (the tensor-core path keeps them as bf16 planes)
+  if (!h->parts) {
+    want(&h->qkv, 3 * max_mc);   // fp32 GEMM operands of the FFMA path (the tensor-core path keeps them as bf16 planes)
     want(&h->norm, max_cat);
     want(&h->tmp2, max_mc);
     want(&h->xn, max_mc);
@@ -1003,6 +1017,15 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
     wantb(&h->ffh_b, 4 * max_mc * P);
     wantb(&h->th_b, max_mc * P);
     wantb(&h->cast_b, cast_max * P);
+    size_t att_max = 0, vt_max = 0;
+    for (int i = 0; i < nb; ++i) {
+      const int d = ch[i] / c.n_heads, dpad = d <= 32 ? 32 : 64;
+      att_max = std::max(att_max, (size_t)B * h->Tl[i] * c.n_heads * dpad);
+      vt_max = std::max(vt_max, (size_t)B * c.n_heads * dpad * ((h->Tl[i] + 7) / 8 * 8));
+    }
+    wantb(&h->q_b, att_max * P);
+    wantb(&h->k_b, att_max * P);
+    wantb(&h->vt_b, vt_max * P);
     h->barena_elems = boff;
     LDS_CK(h, cudaMalloc(&h->barena, boff * sizeof(__nv_bfloat16)));
     for (auto& b : bslots) *b.first = h->barena + b.second;
@@ -1232,6 +1255,26 @@ int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, int parts
   if (parts == 3) lds::tc_set_split_pairs(g);
   g.bias = bias; g.R = R; g.r_ld = r_ld; g.r_div = r_div; g.C = C; g.c_ld = c_ld; g.out_kind = out_kind; g.epilogue = epilogue;
   return op_status(lds::launch_gemm_tc(g, (cudaStream_t)stream), "lds_op_gemm_tc");
+}
+
+int lds_op_qkv_attention_tc(const void* x_planes, const void* w_qkv, int B, int T, int C, int H, int dpad, int parts,
+                            void* q_scratch, void* k_scratch, void* vt_scratch, void* out_planes, void* stream) {
+  if (!x_planes || !w_qkv || !q_scratch || !k_scratch || !vt_scratch || !out_planes || (parts != 1 && parts != 3) || H < 1 || C % H)
+    return fail(LDS_ERR_INVALID, "lds_op_qkv_attention_tc: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int t_pad = (T + 7) / 8 * 8;
+  lds::TcGemmArgs g;
+  g.A = (const __nv_bfloat16*)x_planes; g.batches = 1; g.rows = B * T; g.cin = C;
+  g.W = (const __nv_bfloat16*)w_qkv; g.N = 3 * H * dpad; g.taps = 1;
+  if (parts == 3) lds::tc_set_split_pairs(g);
+  g.out_kind = 3; g.q_out = (__nv_bfloat16*)q_scratch; g.k_out = (__nv_bfloat16*)k_scratch; g.vt_out = (__nv_bfloat16*)vt_scratch;
+  g.att_T = T; g.att_H = H; g.att_dpad = dpad; g.att_Tpad = t_pad;
+  int rc = op_status(lds::launch_gemm_tc(g, s), "lds_op_qkv_attention_tc(qkv gemm)");
+  if (rc != LDS_OK) return rc;
+  lds::AttnTcArgs a;
+  a.q = g.q_out; a.k = g.k_out; a.vt = g.vt_out; a.out = (__nv_bfloat16*)out_planes;
+  a.B = B; a.T = T; a.T_pad = t_pad; a.H = H; a.d = C / H; a.dpad = dpad; a.parts = parts;
+  return op_status(lds::launch_attention_tc(a, s), "lds_op_qkv_attention_tc(attention)");
 }
 
 }  // extern "C"

@@ -39,7 +39,10 @@ cudaError_t launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
 //  (pair_a, pair_w) plane pairs of A_plane (*) W_plane^T.  Plain bf16: parts = 1, one pair (0,0).  Split-bf16
 //  (fp32-accurate): parts = 3 (hi, mid, lo planes) and the six significant pairs, smallest first.
 //  taps==3: k=3, stride-1, pad-1 convolution along `rows` (TMA out-of-bounds fill = zero padding).
-//  out_kind: 0 fp32 [*, c_ld], 1 bf16 [*, c_ld], 2 three bf16 planes of c_ld/3 columns each.
+//  out_kind: 0 fp32 [*, c_ld], 1 bf16 [*, c_ld], 2 three bf16 planes of c_ld/3 columns each,
+//            3 attention operands of a fused QKV projection with N = 3*H*dpad columns ([q | k | v], head dim padded
+//              to dpad): q_out/k_out planes [rows][parts][H*dpad], vt_out planes [B][parts][H][dpad][T_pad] (V transposed,
+//              keys contiguous) — the layouts attention_tc.cu loads with TMA.
 struct TcGemmArgs {
   const __nv_bfloat16* A = nullptr; int batches = 1, rows = 0, cin = 0, a_parts = 1;
   const __nv_bfloat16* W = nullptr; int N = 0, taps = 1, w_parts = 1;
@@ -47,8 +50,18 @@ struct TcGemmArgs {
   const float* bias = nullptr;
   const float* R = nullptr; int r_ld = 0, r_div = 1;
   void* C = nullptr; int c_ld = 0, out_kind = 0, epilogue = EPI_NONE;
+  __nv_bfloat16 *q_out = nullptr, *k_out = nullptr, *vt_out = nullptr; int att_T = 0, att_H = 0, att_dpad = 0, att_Tpad = 0;
 };
 cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
+
+// tcgen05 flash attention (attention_tc.cu) on the operands written by a QKV projection with out_kind 3.
+// out: bf16 planes [B*T][parts*H*d].
+struct AttnTcArgs {
+  const __nv_bfloat16 *q = nullptr, *k = nullptr, *vt = nullptr;
+  __nv_bfloat16* out = nullptr;
+  int B = 0, T = 0, T_pad = 0, H = 0, d = 0, dpad = 0, parts = 1;
+};
+cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s);
 inline void tc_set_split_pairs(TcGemmArgs& a) {   // lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
   static const int pa[6] = {2, 0, 1, 1, 0, 0}, pw[6] = {0, 2, 1, 0, 1, 0};
   a.a_parts = a.w_parts = 3; a.n_pairs = 6;

@@ -120,3 +120,26 @@ def op_gemm_tc(a_bf16, batches, rows, cin, parts, w_bf16, N, taps=1, bias=None, 
                                0 if R is None else R.shape[-1], r_div, ptr(out), c_ld, out_kind, epilogue, stream()),
           "lds_op_gemm_tc")
     return out
+
+
+def op_qkv_attention_tc(x, wq, wk, wv, B, T, heads, parts):
+    """x fp32 [B*T, C]; returns attention output as fp32 (planes summed) [B*T, C]."""
+    Cc = x.shape[1]
+    d = Cc // heads
+    dpad = 32 if d <= 32 else 64
+    rows = []
+    for w in (wq, wk, wv):
+        for hh in range(heads):
+            rows.append(w[hh * d:(hh + 1) * d])
+            if dpad > d:
+                rows.append(torch.zeros(dpad - d, Cc, device=x.device))
+    wp = pack_w_parts(torch.cat(rows, 0).contiguous(), 1, parts)
+    xp = op_split_cast(x, parts)
+    t_pad = (T + 7) // 8 * 8
+    q = torch.zeros(B * T * parts * heads * dpad, device=x.device, dtype=torch.bfloat16)
+    k = torch.zeros_like(q)
+    vt = torch.zeros(B * parts * heads * dpad * t_pad, device=x.device, dtype=torch.bfloat16)
+    out = torch.zeros(B * T, parts * Cc, device=x.device, dtype=torch.bfloat16)
+    check(lib().lds_op_qkv_attention_tc(ptr(xp), ptr(wp), B, T, Cc, heads, dpad, parts, ptr(q), ptr(k), ptr(vt), ptr(out), stream()),
+          "lds_op_qkv_attention_tc")
+    return out.float().view(B * T, parts, Cc).double().sum(1)

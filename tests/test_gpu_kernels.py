@@ -202,3 +202,22 @@ def test_tc_gemm_geglu_and_output_kinds(out_kind, parts):
         tol = 5e-5
     G.report(test="tc_geglu", out_kind=out_kind, parts=parts, **e)
     assert e["max_abs"] <= tol, e
+
+
+@pytest.mark.parametrize("B,T,C,parts", [(2, 100, 256, 3), (1, 864, 256, 3), (2, 431, 384, 3), (3, 216, 512, 3), (2, 64, 512, 3),
+                                         (1, 1, 256, 3), (2, 300, 256, 1), (2, 216, 384, 1), (1, 129, 512, 1)])
+def test_tc_qkv_attention(B, T, C, parts):
+    """Fused QKV projection (attention-operand epilogue) + tcgen05 flash attention vs fp64 SDPA."""
+    heads = 8
+    x = _rand(B * T, C, seed=51)
+    wq, wk, wv = (_rand(C, C, seed=52 + i, scale=C ** -0.5) for i in range(3))
+    got = G.op_qkv_attention_tc(x, wq, wk, wv, B, T, heads, parts)
+    xr = x.double() if parts == 3 else x.bfloat16().double()
+    ws = [w.double() if parts == 3 else w.bfloat16().double() for w in (wq, wk, wv)]
+    q, k, v = ((xr @ w.t()).view(B, T, heads, C // heads).transpose(1, 2) for w in ws)
+    if parts == 1:      # the projection results are rounded to bf16 before the attention in bf16 mode
+        q, k, v = (z.float().bfloat16().double() for z in (q, k, v))
+    want = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, C)
+    e = G.errs(got, want)
+    G.report(test="tc_qkv_attention", B=B, T=T, C=C, parts=parts, **e)
+    assert e["max_abs"] <= (3e-5 if parts == 3 else 3e-2), e
