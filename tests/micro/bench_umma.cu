@@ -1,0 +1,122 @@
+// Micro-benchmark: cycles per tcgen05.mma (kind::f16, cta_group::1, M=128, K=16) as a function of N and swizzle width,
+// operands in shared memory (SS).  One CTA per SM, one issuing thread; operands are whatever is in smem (zeros).
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../latent_diffusion_speech_b200/csrc/tc_ptx.cuh"
+using namespace lds::ptx;
+
+template <int N, int SWZ, int NACC = 1>
+__global__ void __launch_bounds__(128) k(long long* out, int iters, int ksteps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw), base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar = base + 96 * 1024;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 96 * 1024 + 16);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(slot), 256);
+  fence_async_smem();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = *slot;
+  if (threadIdx.x == 0) {
+    const uint64_t ad = umma_desc_kmajor(base, SWZ), bd = umma_desc_kmajor(base + 32 * 1024, SWZ);
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i)
+      for (int ks = 0; ks < ksteps; ++ks) umma_bf16(tm, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 256); }
+}
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+
+// A operand from TMEM (TS): A tile lives in TMEM columns [256, 256+8*ksteps)
+template <int N, int SWZ>
+__global__ void __launch_bounds__(128) kts(long long* out, int iters, int ksteps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw), base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar = base + 96 * 1024;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 96 * 1024 + 16);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(slot), 512);
+  fence_async_smem();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = *slot;
+  if (threadIdx.x == 0) {
+    const uint64_t bd = umma_desc_kmajor(base + 32 * 1024, SWZ);
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i)
+      for (int ks = 0; ks < ksteps; ++ks) umma_bf16_ts(tm, tm + 256 + 8 * ks, bd + 2 * ks, idesc, 1u);
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+
+template <int N, int SWZ>
+void run_ts(const char* name, int grid) {
+  long long* d; cudaMalloc(&d, 8);
+  const int iters = 2000, ksteps = SWZ / 32;
+  cudaFuncSetAttribute(kts<N, SWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  kts<N, SWZ><<<grid, 128, 100 * 1024>>>(d, iters, ksteps);
+  kts<N, SWZ><<<grid, 128, 100 * 1024>>>(d, iters, ksteps);
+  long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaGetLastError();
+  printf("TS %-23s grid=%3d  %.1f cycles/MMA  (ideal math %d)  %s\n", name, grid, (double)h / (iters * ksteps), 128 * N / 256, cudaGetErrorString(e));
+  cudaFree(d);
+}
+
+template <int N, int SWZ, int NACC = 1>
+void run(const char* name, int grid) {
+  long long* d; cudaMalloc(&d, 8);
+  const int iters = 2000, ksteps = SWZ / 32;
+  cudaFuncSetAttribute(k<N, SWZ, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  k<N, SWZ, NACC><<<grid, 128, 100 * 1024>>>(d, iters, ksteps);
+  k<N, SWZ, NACC><<<grid, 128, 100 * 1024>>>(d, iters, ksteps);
+  long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaGetLastError();
+  printf("%-26s grid=%3d  %.1f cycles/MMA  (ideal math %d)  %s\n", name, grid, (double)h / (iters * ksteps), 128 * N / 256, cudaGetErrorString(e));
+  cudaFree(d);
+}
+
+int main() {
+  for (int grid : {148}) {
+    run<32, 128>("M128 N32  SW128", grid);
+    run<64, 128>("M128 N64  SW128", grid);
+    run<64, 64>("M128 N64  SW64", grid);
+    run<128, 128>("M128 N128 SW128", grid);
+    run<256, 128>("M128 N256 SW128", grid);
+    run<64, 128, 2>("M128 N64 SW128 2 accum", grid);
+    run<64, 128, 4>("M128 N64 SW128 4 accum", grid);
+    run<32, 128, 4>("M128 N32 SW128 4 accum", grid);
+    run<128, 128, 2>("M128 N128 SW128 2 accum", grid);
+    run<96, 128>("M128 N96  SW128", grid);
+    run<192, 128>("M128 N192 SW128", grid);
+    run_ts<32, 128>("M128 N32  B:SW128", grid);
+    run_ts<64, 128>("M128 N64  B:SW128", grid);
+    run_ts<64, 64>("M128 N64  B:SW64", grid);
+    run_ts<96, 128>("M128 N96  B:SW128", grid);
+    run_ts<128, 128>("M128 N128 B:SW128", grid);
+    run_ts<192, 128>("M128 N192 B:SW128", grid);
+    run_ts<256, 128>("M128 N256 B:SW128", grid);
+  }
+  return 0;
+}
