@@ -31,8 +31,7 @@ using namespace ptx;
 constexpr int AQ = 128, AKV = 64, ATT_TC_THREADS = 320, NSOFT = 256;
 
 struct AttnTcParams {
-  int T, H, d, C, parts, n_pairs;
-  int pair_a[6], pair_w[6];
+  int T, H, d, C, parts, nk, nv, nsb, npb;   // ring depths: K, V^T tiles (smem), S (TMEM) and P (smem) buffers
   float scale;
   __nv_bfloat16* out;   // planes [B*T][parts*C]
 };
@@ -71,36 +70,42 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int DPAD, int NK, int NV, int NP>
-__global__ void __launch_bounds__(ATT_TC_THREADS)
+// MMA work lists.  tcgen05.mma costs ~92 cycles for any N <= 128 (M = 128, K = 16; measured, tests/micro/bench_umma.cu),
+// 96 for N = 192 and 128 for N = 256, so the plane products of the split mode are batched along N: one instruction
+// multiplies an A plane with up to three B planes that sit in consecutive shared-memory rows and writes one
+// accumulator column block per B plane; the softmax / epilogue threads add the blocks.
+struct MmaItem { int a_plane, b_plane0, n_planes, blk; };
+
+template <int DPAD, int AKV, int PARTS>
+__global__ void __launch_bounds__(ATT_TC_THREADS, PARTS == 1 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapVT, const AttnTcParams p) {
   constexpr int SWZ = DPAD * 2;                    // swizzle width of the Q/K tiles (bytes per row)
-  constexpr int QB = AQ * DPAD * 2, KB = AKV * DPAD * 2, VB = DPAD * AKV * 2, PB = AQ * AKV * 2;
-  constexpr uint32_t IDESC_QK = umma_idesc_bf16(AQ, AKV), IDESC_PV = umma_idesc_bf16(AQ, DPAD);
-  constexpr int TMEM_COLS = 256;                   // S0: [0,64), S1: [64,128), O: [128, 128+DPAD)
+  constexpr int KBLK = AKV / 64;                   // 64-key (128-byte) K-blocks of the P and V^T operands
+  constexpr int QB = AQ * DPAD * 2, KB = AKV * DPAD * 2, VBK = DPAD * 128, PBK = AQ * 128;
   constexpr int OC = DPAD / 2;                     // output columns per softmax thread
+  constexpr int NCH = AKV / 64;                    // 32-column chunks per softmax thread and tile
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int parts = p.parts;
-  const uint32_t q_s = base, k_s = q_s + parts * QB, v_s = k_s + NK * parts * KB, p_s = v_s + NV * parts * VB;
-  const uint32_t bar0 = p_s + NP * parts * PB;
+  constexpr int parts = PARTS;
+  const int NK = p.nk, NV = p.nv;
+  const uint32_t q_s = base, k_s = q_s + parts * QB, v_s = k_s + NK * parts * KB, p_s = v_s + NV * parts * KBLK * VBK;
+  const int NSB = p.nsb, NPB = p.npb;
+  const uint32_t bar0 = p_s + NPB * parts * KBLK * PBK;
   uint8_t* p_ptr = smem + (p_s - base);
-  // barriers (8 B each)
   const uint32_t q_full = bar0;
-  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (1 + NK + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * NK + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 2 * NK + NV + s); };
-  const uint32_t bar1 = bar0 + 8u * (1 + 2 * NK + 2 * NV);
-  auto s_full = [&](int s) { return bar1 + 8u * s; };
-  auto s_free = [&](int s) { return bar1 + 8u * (2 + s); };
-  auto p_full = [&](int s) { return bar1 + 32 + 8u * s; };
-  auto pv_done = [&](int s) { return bar1 + 48 + 8u * s; };
-  uint8_t* misc = smem + (bar1 - base) + 64;
+  auto s_full = [&](int s) { return bar0 + 8 + 8u * s; };
+  auto s_free = [&](int s) { return bar0 + 24 + 8u * s; };
+  auto p_full = [&](int s) { return bar0 + 40 + 8u * s; };
+  auto pv_done = [&](int s) { return bar0 + 56 + 8u * s; };
+  auto k_full = [&](int s) { return bar0 + 72 + 8u * s; };
+  auto k_empty = [&](int s) { return bar0 + 72 + 8u * (4 + s); };
+  auto v_full = [&](int s) { return bar0 + 72 + 8u * (8 + s); };
+  auto v_empty = [&](int s) { return bar0 + 72 + 8u * (12 + s); };
+  uint8_t* misc = smem + (bar0 - base) + 72 + 8 * 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
   float* red = reinterpret_cast<float*>(misc + 16);          // [2][128] exchange of row max / row sum between the halves
 
@@ -108,25 +113,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
   const int nt = (p.T + AKV - 1) / AKV;
   const int HD = p.H * DPAD;
+  constexpr int tmem_cols = parts == 3 ? 512 : 256;
+  constexpr int o_col = parts == 3 ? 256 : 128;    // S buffers start at column 0, O blocks at o_col
+  constexpr int n_sblk = parts == 3 ? (AKV == 64 ? 3 : 2) : 1;
+  constexpr int s_stride = n_sblk * AKV;           // TMEM columns per S buffer
+  constexpr int n_oblk = parts == 3 ? 3 : 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&mapQ);
     prefetch_tensormap(&mapK);
     prefetch_tensormap(&mapVT);
     mbar_init(q_full, 1);
-    for (int s = 0; s < NK; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
-    for (int s = 0; s < NV; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(s_free(s), NSOFT); }
-    for (int s = 0; s < NP; ++s) { mbar_init(p_full(s), NSOFT); mbar_init(pv_done(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(s_free(s), NSOFT); mbar_init(p_full(s), NSOFT); mbar_init(pv_done(s), 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
     mbar_fence_init();
   } else if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem0 = *tmem_slot;
-  const uint32_t tmem_o = tmem0 + 128;
+  const uint32_t tmem_o = tmem0 + o_col;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -142,51 +150,76 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         if (it >= nt) {
           const int vs = jt % NV;
           mbar_wait(v_empty(vs), ((uint32_t)(jt / NV) & 1u) ^ 1u);
-          mbar_expect_tx(v_full(vs), parts * VB);
-          for (int pl = 0; pl < parts; ++pl)
-            tma_load_2d(v_s + (vs * parts + pl) * VB, &mapVT, v_full(vs), jt * AKV, ((b * parts + pl) * p.H + h) * DPAD);
+          mbar_expect_tx(v_full(vs), parts * KBLK * VBK);
+          for (int kb = 0; kb < KBLK; ++kb)
+            for (int pl = 0; pl < parts; ++pl)
+              tma_load_2d(v_s + ((vs * KBLK + kb) * parts + pl) * VBK, &mapVT, v_full(vs), jt * AKV + kb * 64,
+                          ((b * parts + pl) * p.H + h) * DPAD);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // work lists (widest instruction first: it initialises every accumulator block it covers)
+      MmaItem qk[4], pv[3];
+      int n_qk, n_pv;
+      if (parts == 3) {
+        if (AKV == 64) { qk[0] = {0, 0, 3, 0}; qk[1] = {1, 0, 2, 0}; qk[2] = {2, 0, 1, 0}; n_qk = 3; }
+        else { qk[0] = {0, 0, 2, 0}; qk[1] = {1, 0, 2, 0}; qk[2] = {0, 2, 1, 1}; qk[3] = {2, 0, 1, 0}; n_qk = 4; }
+        pv[0] = {0, 0, 3, 0}; pv[1] = {1, 0, 2, 0}; pv[2] = {2, 0, 1, 0}; n_pv = 3;
+      } else {
+        qk[0] = {0, 0, 1, 0}; n_qk = 1;
+        pv[0] = {0, 0, 1, 0}; n_pv = 1;
+      }
+      // descriptors are assembled once; the loops below only add address offsets (units of 16 bytes)
+      uint64_t qd0[4], kd0[4], pd0[3], vd0[3];
+      uint32_t qk_idesc[4], pv_idesc[3], qk_dst[4], pv_dst[3];
+      for (int e = 0; e < n_qk; ++e) {
+        qd0[e] = umma_desc_kmajor(q_s + qk[e].a_plane * QB, SWZ);
+        kd0[e] = umma_desc_kmajor(k_s + qk[e].b_plane0 * KB, SWZ);
+        qk_idesc[e] = umma_idesc_bf16(AQ, qk[e].n_planes * AKV);
+        qk_dst[e] = tmem0 + qk[e].blk * AKV;
+      }
+      for (int e = 0; e < n_pv; ++e) {
+        pd0[e] = umma_desc_kmajor(p_s + pv[e].a_plane * KBLK * PBK, 128);
+        vd0[e] = umma_desc_kmajor(v_s + pv[e].b_plane0 * VBK, 128);
+        pv_idesc[e] = umma_idesc_bf16(AQ, pv[e].n_planes * DPAD);
+        pv_dst[e] = tmem_o + pv[e].blk * DPAD;
+      }
+      const uint64_t k_stage_step = (uint64_t)((parts * KB) >> 4), v_stage_step = (uint64_t)((parts * KBLK * VBK) >> 4),
+                     v_kb_step = (uint64_t)((parts * VBK) >> 4), p_buf_step = (uint64_t)((parts * KBLK * PBK) >> 4),
+                     p_kb_step = (uint64_t)(PBK >> 4);
       mbar_wait(q_full, 0);
-      // S = Q K^T of global iteration `it` into S buffer it&1
       auto issue_qk = [&](int it) {
-        const int ks = it % NK, sb = it & 1, u = it >> 1;
+        const int ks = it % NK, sb = it % NSB;
         mbar_wait(k_full(ks), (uint32_t)(it / NK) & 1u);
-        mbar_wait(s_free(sb), ((uint32_t)u & 1u) ^ 1u);        // previous use of this S buffer has been read
+        mbar_wait(s_free(sb), ((uint32_t)(it / NSB) & 1u) ^ 1u);   // the softmax threads have read the previous use of this S buffer
         tc_fence_after();
-        bool first = true;
-        for (int pr = 0; pr < p.n_pairs; ++pr) {
-          const uint64_t qd = umma_desc_kmajor(q_s + p.pair_a[pr] * QB, SWZ);
-          const uint64_t kd = umma_desc_kmajor(k_s + (ks * parts + p.pair_w[pr]) * KB, SWZ);
+        const uint64_t koff = (uint64_t)ks * k_stage_step;
+        const uint32_t soff = (uint32_t)(sb * s_stride);
 #pragma unroll
-          for (int k = 0; k < DPAD / 16; ++k) {
-            umma_bf16(tmem0 + sb * 64, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), IDESC_QK, first ? 0u : 1u);
-            first = false;
-          }
-        }
+        for (int k = 0; k < DPAD / 16; ++k)
+          for (int e = 0; e < n_qk; ++e)
+            umma_bf16(qk_dst[e] + soff, qd0[e] + (uint64_t)(2 * k), kd0[e] + koff + (uint64_t)(2 * k), qk_idesc[e],
+                      (k == 0 && e == 0) ? 0u : 1u);
         umma_commit(k_empty(ks));
         umma_commit(s_full(sb));
       };
       for (int it = 0; it < nt; ++it) issue_qk(it);            // pass A
-      issue_qk(nt);                                            // pass B runs Q K^T one tile ahead of P V
+      issue_qk(nt);                                            // pass B: Q K^T runs one tile ahead of P V
       for (int jb = 0; jb < nt; ++jb) {
         if (jb + 1 < nt) issue_qk(nt + jb + 1);
-        const int vs = jb % NV, pb = jb % NP;
+        const int vs = jb % NV, pb = jb % NPB;
         mbar_wait(v_full(vs), (uint32_t)(jb / NV) & 1u);
-        mbar_wait(p_full(pb), (uint32_t)(jb / NP) & 1u);
+        mbar_wait(p_full(pb), (uint32_t)(jb / NPB) & 1u);
         tc_fence_after();
-        bool pfirst = jb == 0;
-        for (int pr = 0; pr < p.n_pairs; ++pr) {
-          const uint64_t pd = umma_desc_kmajor(p_s + (pb * parts + p.pair_a[pr]) * PB, 128);
-          const uint64_t vd = umma_desc_kmajor(v_s + (vs * parts + p.pair_w[pr]) * VB, 128);
+        const uint64_t poff = (uint64_t)pb * p_buf_step, voff = (uint64_t)vs * v_stage_step;
 #pragma unroll
-          for (int k = 0; k < AKV / 16; ++k) {
-            umma_bf16(tmem_o, pd + (uint64_t)(2 * k), vd + (uint64_t)(2 * k), IDESC_PV, pfirst ? 0u : 1u);
-            pfirst = false;
-          }
+        for (int k = 0; k < AKV / 16; ++k) {
+          const uint64_t pk = poff + (uint64_t)(k >> 2) * p_kb_step + (uint64_t)(2 * (k & 3));
+          const uint64_t vk = voff + (uint64_t)(k >> 2) * v_kb_step + (uint64_t)(2 * (k & 3));
+          for (int e = 0; e < n_pv; ++e)
+            umma_bf16(pv_dst[e], pd0[e] + pk, vd0[e] + vk, pv_idesc[e], (jb == 0 && k == 0 && e == 0) ? 0u : 1u);
         }
         umma_commit(v_empty(vs));
         umma_commit(pv_done(pb));
@@ -196,26 +229,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const int c0 = half * 32;                            // this thread's key columns inside a tile
+    const int c0 = half * (AKV / 2);                     // this thread's key columns inside a tile
     const float sl2 = p.scale * 1.4426950408889634f;    // softmax scale * log2(e): exp(x*scale - m) = 2^(x*sl2 - m*sl2)
+    // sum of the accumulator blocks of 32 columns starting at column c of the S tile
+    auto load_s32 = [&](int sb, int c, float* s) {
+      const uint32_t sbase = tmem0 + lane_off + sb * s_stride + c;
+      tmem_ld32(sbase + (n_sblk - 1) * AKV, s);
+      for (int blk = n_sblk - 2; blk >= 0; --blk) {
+        float t[32];
+        tmem_ld32(sbase + blk * AKV, t);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[i] += t[i];
+      }
+    };
     float m = -INFINITY;
     // ---- pass A: row maximum of the scaled, masked scores ----
     for (int it = 0; it < nt; ++it) {
-      const int sb = it & 1;
-      mbar_wait(s_full(sb), (uint32_t)(it >> 1) & 1u);
+      const int sb = it % NSB;
+      mbar_wait(s_full(sb), (uint32_t)(it / NSB) & 1u);
       tc_fence_after();
-      float s[32];
-      tmem_ld32(tmem0 + lane_off + sb * 64 + c0, s);
-      tc_fence_before();
-      mbar_arrive(s_free(sb));
-      const int k0 = it * AKV + c0;
-      if (k0 + 32 <= p.T) {
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ++ch) {
+        float s[32];
+        load_s32(sb, c0 + ch * 32, s);
+        if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
+        const int k0 = it * AKV + c0 + ch * 32;
+        if (k0 + 32 <= p.T) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, s[i]);
-      } else {
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, s[i]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (k0 + i < p.T) m = fmaxf(m, s[i]);
+          for (int i = 0; i < 32; ++i)
+            if (k0 + i < p.T) m = fmaxf(m, s[i]);
+        }
       }
     }
     m *= sl2;                                            // row maximum in the log2 domain (sl2 > 0)
@@ -227,45 +273,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     float l = 0.f;
     uint8_t* prow = p_ptr + (row >> 3) * 1024 + (row & 7) * 128;     // 8-row / 1024 B swizzle atoms, 128 B per row
     for (int jb = 0; jb < nt; ++jb) {
-      const int it = nt + jb, sb = it & 1;
-      mbar_wait(s_full(sb), (uint32_t)(it >> 1) & 1u);
+      const int it = nt + jb, sb = it % NSB, pb = jb % NPB;
+      mbar_wait(s_full(sb), (uint32_t)(it / NSB) & 1u);
       tc_fence_after();
-      float s[32];
-      tmem_ld32(tmem0 + lane_off + sb * 64 + c0, s);
-      tc_fence_before();
-      mbar_arrive(s_free(sb));
-      const int k0 = jb * AKV + c0;
+      uint32_t w[PARTS][16 * NCH];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) s[i] = ex2_approx(fmaf(s[i], sl2, -m));
-      if (k0 + 32 > p.T) {                                             // ragged last tile: keys beyond T contribute nothing
+      for (int ch = 0; ch < NCH; ++ch) {
+        float s[32];
+        load_s32(sb, c0 + ch * 32, s);
+        if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
+        const int k0 = jb * AKV + c0 + ch * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (k0 + i >= p.T) s[i] = 0.f;
-      }
-      float l0 = 0.f, l1 = 0.f;
+        for (int i = 0; i < 32; ++i) s[i] = ex2_approx(fmaf(s[i], sl2, -m));
+        if (k0 + 32 > p.T) {                                           // ragged last tile: keys beyond T contribute nothing
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) { l0 += s[i]; l1 += s[i + 1]; }
-      l += l0 + l1;
-      // split into bf16 planes in registers first, so that only the stores sit behind the P-buffer hand-off
-      uint32_t w[3][16];
+          for (int i = 0; i < 32; ++i)
+            if (k0 + i >= p.T) s[i] = 0.f;
+        }
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl) {
-        if (pl < parts) {
-          const bool last_plane = pl == parts - 1;
+        for (int i = 0; i < 32; i += 2) { l0 += s[i]; l1 += s[i + 1]; }
+        l += l0 + l1;
+        // split into bf16 planes in registers, so that only the stores sit behind the P-buffer hand-off
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w[pl][i] = last_plane ? pack_pair(s[2 * i], s[2 * i + 1]) : split_pair(s[2 * i], s[2 * i + 1]);
+        for (int pl = 0; pl < PARTS; ++pl) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            w[pl][ch * 16 + i] = (pl == PARTS - 1) ? pack_pair(s[2 * i], s[2 * i + 1]) : split_pair(s[2 * i], s[2 * i + 1]);
         }
       }
-      const int pb = jb % NP;
-      if (jb >= NP) mbar_wait(pv_done(pb), (uint32_t)(jb / NP - 1) & 1u);   // the P*V that last used this P buffer is done
+      if (jb >= NPB) mbar_wait(pv_done(pb), (uint32_t)(jb / NPB - 1) & 1u);   // the P*V that last used this P buffer is done
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl) {
-        if (pl < parts) {
-          uint8_t* dst = prow + (pb * parts + pl) * PB;
+      for (int pl = 0; pl < PARTS; ++pl) {
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch)                                // 16-byte chunk = 8 keys
-            *reinterpret_cast<uint4*>(dst + (((half * 4 + ch) ^ (row & 7)) << 4)) =
-                make_uint4(w[pl][4 * ch], w[pl][4 * ch + 1], w[pl][4 * ch + 2], w[pl][4 * ch + 3]);
+        for (int cc = 0; cc < 4 * NCH; ++cc) {                         // 16-byte chunk = 8 keys
+          const int key_chunk = (c0 >> 3) + cc;                        // chunk index inside the AKV-key row
+          uint8_t* dst = prow + ((pb * parts + pl) * KBLK + (key_chunk >> 3)) * PBK;
+          *reinterpret_cast<uint4*>(dst + (((key_chunk & 7) ^ (row & 7)) << 4)) =
+              make_uint4(w[pl][4 * cc], w[pl][4 * cc + 1], w[pl][4 * cc + 2], w[pl][4 * cc + 3]);
         }
       }
       fence_async_smem();
@@ -275,13 +320,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     softmax_bar();
     l += red[(half ^ 1) * 128 + row];
     // ---- epilogue: O / l -> bf16 planes; this thread writes output columns [half*OC, half*OC + OC) ----
-    mbar_wait(pv_done((nt - 1) % NP), (uint32_t)((nt - 1) / NP) & 1u);
+    mbar_wait(pv_done((nt - 1) % NPB), (uint32_t)((nt - 1) / NPB) & 1u);
     tc_fence_after();
     const int q = q0 + row;
     const float inv = 1.f / l;
     float o[OC];
-    if constexpr (OC == 32) tmem_ld32(tmem_o + lane_off + half * OC, o);
-    else tmem_ld16(tmem_o + lane_off + half * OC, o);
+    {
+      auto ld = [&](uint32_t addr, float* v) {
+        if constexpr (OC == 32) tmem_ld32(addr, v); else tmem_ld16(addr, v);
+      };
+      ld(tmem_o + lane_off + (n_oblk - 1) * DPAD + half * OC, o);
+      for (int blk = n_oblk - 2; blk >= 0; --blk) {
+        float t[OC];
+        ld(tmem_o + lane_off + blk * DPAD + half * OC, t);
+#pragma unroll
+        for (int i = 0; i < OC; ++i) o[i] += t[i];
+      }
+    }
     const int ncol = min(OC, p.d - half * OC);                        // d = 48: 16 valid columns in the upper half
     if (q < p.T && ncol > 0) {
       __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q) * (size_t)(parts * p.C) + h * p.d + half * OC;
@@ -302,16 +357,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem0, TMEM_COLS);
+    tmem_dealloc(tmem0, tmem_cols);
   }
 }
 
-template <int DPAD, int NK, int NV, int NP>
-cudaError_t launch_attn(const AttnTcArgs& a, cudaStream_t s) {
+template <int DPAD, int AKV, int PARTS>
+cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, cudaStream_t s) {
   const int parts = a.parts;
-  const size_t smem = (size_t)parts * (AQ * DPAD * 2 + NK * AKV * DPAD * 2 + NV * DPAD * AKV * 2 + NP * AQ * AKV * 2) + 1024 +
-                      8 * (1 + 2 * NK + 2 * NV) + 64 + 16 + 2 * 128 * 4 + 64;
-  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, NK, NV, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)parts * (AQ * DPAD * 2 + nk * AKV * DPAD * 2 + nv * DPAD * AKV * 2 + npb * AQ * AKV * 2) + 1024 +
+                      72 + 8 * 16 + 16 + 2 * 128 * 4 + 64;
+  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, AKV, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint64_t HD = (uint64_t)a.H * DPAD;
   CUtensorMap mQ, mK, mV;
@@ -325,23 +380,15 @@ cudaError_t launch_attn(const AttnTcArgs& a, cudaStream_t s) {
   {
     const uint64_t dims[2] = {(uint64_t)a.T, (uint64_t)a.B * parts * HD};
     const uint64_t str[1] = {(uint64_t)a.T_pad * 2};
-    const uint32_t box[2] = {(uint32_t)AKV, (uint32_t)DPAD};
+    const uint32_t box[2] = {64u, (uint32_t)DPAD};
     if ((e = tc_make_map_bf16(a.vt, 2, dims, str, box, 128, &mV)) != cudaSuccess) return e;
   }
   AttnTcParams p;
-  p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts;
+  p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts; p.nk = nk; p.nv = nv; p.nsb = nsb; p.npb = npb;
   p.scale = 1.0f / sqrtf((float)a.d);
   p.out = a.out;
-  if (parts == 3) {
-    static const int pa[6] = {2, 0, 1, 1, 0, 0}, pw[6] = {0, 2, 1, 0, 1, 0};
-    p.n_pairs = 6;
-    for (int i = 0; i < 6; ++i) { p.pair_a[i] = pa[i]; p.pair_w[i] = pw[i]; }
-  } else {
-    p.n_pairs = 1;
-    for (int i = 0; i < 6; ++i) p.pair_a[i] = p.pair_w[i] = 0;
-  }
   dim3 grid((a.T + AQ - 1) / AQ, a.H, a.B);
-  attention_tc_kernel<DPAD, NK, NV, NP><<<grid, ATT_TC_THREADS, smem, s>>>(mQ, mK, mV, p);
+  attention_tc_kernel<DPAD, AKV, PARTS><<<grid, ATT_TC_THREADS, smem, s>>>(mQ, mK, mV, p);
   return cudaGetLastError();
 }
 
@@ -352,12 +399,13 @@ cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
   if ((a.parts != 1 && a.parts != 3) || a.d > a.dpad || a.d % 8 || a.T_pad % 8 || a.T_pad < a.T) return cudaErrorInvalidValue;
   // shared memory per CTA: split, dpad 32: 24+3*12+2*12+48 = 132 KB; split, dpad 64: 48+3*24+2*24+48 = 216 KB;
   //                        bf16: a third of that (two CTAs per SM, bounded by 2 x 256 TMEM columns)
+  // shared memory per CTA (KB): Q + nk*K + nv*V^T + P
   if (a.parts == 3) {
-    if (a.dpad == 32) return launch_attn<32, 3, 2, 2>(a, s);   // 24 + 36 + 24 + 96 = 180 KB
-    if (a.dpad == 64) return launch_attn<64, 3, 2, 1>(a, s);   // 48 + 72 + 48 + 48 = 216 KB
-  } else {
-    if (a.dpad == 32) return launch_attn<32, 4, 3, 2>(a, s);
-    if (a.dpad == 64) return launch_attn<64, 4, 3, 2>(a, s);
+    if (a.dpad == 32) return launch_attn<32, 128, 3>(a, 2, 2, 1, 1, s);   // 24 + 2*24 + 2*24 + 96 = 216, TMEM 256 (S) + 96 (O)
+    if (a.dpad == 64) return launch_attn<64, 64, 3>(a, 2, 2, 1, 1, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
+  } else {                                                             // bf16: S and P double-buffered, two CTAs per SM
+    if (a.dpad == 32) return launch_attn<32, 64, 1>(a, 4, 3, 2, 2, s);    //  8 + 4*4 + 3*4 + 2*16 = 68, TMEM 2*64 (S) + 32 (O)
+    if (a.dpad == 64) return launch_attn<64, 64, 1>(a, 4, 3, 2, 2, s);    // 16 + 4*8 + 3*8 + 2*16 = 104
   }
   return cudaErrorNotSupported;
 }
