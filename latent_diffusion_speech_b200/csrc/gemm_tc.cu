@@ -130,6 +130,62 @@ __device__ __forceinline__ void store_qkv32(const TcParams& p, size_t row, int c
   }
 }
 
+// Epilogue of one accumulator row (this thread's TMEM lane) over the 128 columns [n0, n0+128): + bias, SiLU / GEGLU,
+// + fp32 residual, store in the requested representation.  trow = TMEM address of column n0 of this lane.
+__device__ __forceinline__ void epilogue_128(const TcParams& p, uint32_t trow, int n0, size_t grow, bool valid) {
+    const float* rrow = p.R ? p.R + (grow / p.r_div) * p.r_ld : nullptr;
+    if (p.epilogue == EPI_GEGLU) {
+      const int n_out = p.N >> 1;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float v[32], g[32];
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld32(trow + 64 + c * 32, g);
+        const int col_v = n0 + c * 32, col_g = n0 + 64 + c * 32, oc = (n0 >> 1) + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a = v[i], gg = g[i];
+          if (p.bias) { a += __ldg(p.bias + col_v + i); gg += __ldg(p.bias + col_g + i); }
+          v[i] = a * gelu_erf(gg);
+        }
+        if (valid) {
+          if (rrow) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += rrow[oc + i];
+          }
+          store_row32(p, grow, oc, n_out, v);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < TBN / 32; ++c) {
+        float v[32];
+        tmem_ld32(trow + c * 32, v);
+        const int col = n0 + c * 32;
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+        }
+        if (p.epilogue == EPI_SILU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+        }
+        if (valid) {
+          if (rrow) {
+            const float4* r4 = reinterpret_cast<const float4*>(rrow + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = r4[i];
+              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
+          }
+          if (p.out_kind == 3) store_qkv32(p, grow, col, v);
+          else store_row32(p, grow, col, p.N, v);
+        }
+      }
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -210,58 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const size_t grow = (size_t)b * p.rows + (valid ? t : 0);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const uint32_t trow = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    const float* rrow = p.R ? p.R + (grow / p.r_div) * p.r_ld : nullptr;
-    if (p.epilogue == EPI_GEGLU) {
-      const int n_out = p.N >> 1;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float v[32], g[32];
-        tmem_ld32(trow + c * 32, v);
-        tmem_ld32(trow + 64 + c * 32, g);
-        const int col_v = n0 + c * 32, col_g = n0 + 64 + c * 32, oc = (n0 >> 1) + c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float a = v[i], gg = g[i];
-          if (p.bias) { a += __ldg(p.bias + col_v + i); gg += __ldg(p.bias + col_g + i); }
-          v[i] = a * gelu_erf(gg);
-        }
-        if (valid) {
-          if (rrow) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += rrow[oc + i];
-          }
-          store_row32(p, grow, oc, n_out, v);
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < TBN / 32; ++c) {
-        float v[32];
-        tmem_ld32(trow + c * 32, v);
-        const int col = n0 + c * 32;
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
-        }
-        if (p.epilogue == EPI_SILU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
-        }
-        if (valid) {
-          if (rrow) {
-            const float4* r4 = reinterpret_cast<const float4*>(rrow + col);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 q = r4[i];
-              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
-            }
-          }
-          if (p.out_kind == 3) store_qkv32(p, grow, col, v);
-          else store_row32(p, grow, col, p.N, v);
-        }
-      }
-    }
+    epilogue_128(p, tmem_acc + ((uint32_t)(quarter * 32) << 16), n0, grow, valid);
     tc_fence_before();
   }
   __syncthreads();
