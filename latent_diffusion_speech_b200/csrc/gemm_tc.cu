@@ -1,22 +1,36 @@
-// gemm_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM for Conv1d(k=3), Conv1d(k=1) and nn.Linear.
+// gemm_tc.cu — persistent tcgen05 / TMEM / TMA implicit-GEMM for Conv1d(k=3), Conv1d(k=1) and nn.Linear.
 //
 // One kernel serves both precision modes of the library:
 //   * LDS_PREC_BF16 : A and W are bf16, one tcgen05.mma (kind::f16, fp32 accumulate in TMEM) per K slice.
 //   * LDS_PREC_FP32 : "split-bf16" — every fp32 operand is stored as three bf16 planes (hi, mid, lo with
-//     hi+mid+lo == x to 24 bits); the K loop runs the six significant plane products
-//     (lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi — smallest first) into the same fp32 TMEM accumulator,
-//     which recovers fp32-level accuracy on the tensor pipe at 6 MMAs per logical K slice.
+//     hi+mid+lo == x to 24 bits) and the six significant plane products (lo*hi, hi*lo, mid*mid, mid*hi, hi*mid,
+//     hi*hi) are accumulated in fp32, which recovers fp32-level accuracy on the tensor pipe at 6 MMAs per K slice.
 //
-// Structure (B200, sm_100a): CTA tile 128(M) x 128(N) x 64(K); 6 warps, warp-specialised:
+// Structure (B200, sm_100a), v3.  Measured on B200: one tcgen05.mma M128 x K16 costs ~92 cycles for any N <= 128 but
+// 96 / 128 cycles at N = 192 / 256 (tests/micro/bench_umma.cu), so only N >= 192 instructions run the pipe at its rate;
+// and the main loop is bound by the TMA / L2 -> SM fill path: ~51 B/clk/SM with 128-byte box rows (v1: 128x128 tiles,
+// one A and one W tile per plane product = 128 B/clk needed), half of that with 64-byte rows (v2).  Hence:
+//   * CTA tile 128 (M) x BN (N), BN = 256 / 192 / 128 chosen per GEMM so that N % BN == 0; one persistent CTA per SM,
+//     tiles strided over the grid with the N tiles of one row block adjacent (A rows stay hot in L2).
+//   * K blocks of 64 bf16 (128-byte rows, 128B swizzle).  Operand tiles live in TWO shared-memory rings — A slots of
+//     16 KB, W slots of BN x 128 B — filled by the producer in the order the MMA warp needs them and released tile by
+//     tile, so that a plane tile is loaded once per K block and reused by every product that needs it:
+//       pass 1 (split mode), per K block: loads A_lo W_hi A_mid W_mid A_hi W_lo, products lo*hi, mid*hi, mid*mid,
+//                            hi*mid, hi*lo (6 tiles per 5 products instead of 10);
+//       pass 2, per K block: loads A_hi W_hi, product hi*hi (the only product in bf16 mode).
+//     The small products of the whole K range are accumulated before any hi*hi term, exactly as in v1: the tensor
+//     pipe's fp32 accumulate truncates, so accumulation steps taken while the accumulator is still small cost nothing.
+//   * The accumulator (BN fp32 columns) is double-buffered in TMEM (2 x 256 of the 512 columns): the epilogue of
+//     tile i overlaps the main loop of tile i+1.
 //   warp 0      TMA producer  — cp.async.bulk.tensor (3-D map over [channels, frames, utterances] for A so that the
 //                               three taps of a k=3 convolution are three shifted loads of the same tensor and the
-//                               zero padding is TMA out-of-bounds fill; 2-D map for W), 128B swizzle, mbarrier tx
-//   warp 1      MMA issuer    — tcgen05.alloc (128 TMEM columns), one elected lane issues tcgen05.mma.cta_group::1
-//                               and tcgen05.commit to release smem stages / publish the accumulator
-//   warps 2..5  epilogue      — tcgen05.ld 32x32b (one accumulator row per thread), + bias, SiLU / GEGLU, + fp32
-//                               residual, store fp32 / bf16 / 3-plane split bf16
-// 3-stage smem ring (96 KB) so that two CTAs are resident per SM: one CTA's epilogue overlaps the other's
-// main loop.  Reference ops replaced: F.conv1d (lora.py:102), nn.Linear (attention_processor.py:1012-1040,
+//                               zero padding is TMA out-of-bounds fill; 2-D map for W), mbarrier tx counts
+//   warp 1      MMA issuer    — tcgen05.alloc, one elected lane issues tcgen05.mma.cta_group::1 and tcgen05.commit to
+//                               release smem stages / publish an accumulator buffer
+//   warps 2..9  epilogue      — tcgen05.ld 32x32b (one accumulator row per thread, two warps per TMEM lane quarter
+//                               splitting the columns), + bias, SiLU / GEGLU, + fp32 residual, store fp32 / bf16 /
+//                               3-plane split bf16 / attention operands
+// Reference ops replaced: F.conv1d (lora.py:102), nn.Linear (attention_processor.py:1012-1040,
 // attention.py:291,247), GEGLU (attention.py:299-301), residual adds (resnet.py:639, attention.py:161-201).
 #include <cuda.h>
 
@@ -29,16 +43,17 @@
 namespace lds {
 namespace {
 
-constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3, TC_THREADS = 192;
-constexpr int A_STAGE_BYTES = TBM * TBK * 2, W_STAGE_BYTES = TBN * TBK * 2;
-constexpr int TC_SMEM_BYTES = TSTAGES * (A_STAGE_BYTES + W_STAGE_BYTES) + 1024 + 256;
-constexpr int TMEM_COLS = 128;
+constexpr int TBM = 128, TBK = 64, TC_THREADS = 320, N_EPI_THREADS = 256;
+constexpr int A_SLOT_BYTES = TBM * TBK * 2;         // 16 KB: 128 rows x 128 B
+constexpr int MAX_SLOTS = 8;                        // per ring
+constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;    // two accumulator buffers
+constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;
 
 struct TcParams {
-  int rows, batches, tiles_per_batch;   // A: [batches][rows][a_parts*cin]
-  int cin, taps, pad;
-  int w_parts, n_pairs;
-  int pair_a[6], pair_w[6];
+  int rows, batches, tiles_per_batch, n_tiles, total_tiles;   // A: [batches][rows][parts*cin]
+  int cin, taps, pad, parts;
+  int BN, na, nw, w_slot_bytes;         // ring depths (A slots, W slots)
+  int nkb, kb_per_tap;                  // K blocks of TBK per plane (all taps) / per tap
   int N;
   const float* bias;
   const float* R; int r_ld, r_div;
@@ -48,8 +63,6 @@ struct TcParams {
 };
 
 using namespace ptx;
-constexpr uint32_t kIdesc = umma_idesc_bf16(TBM, TBN);
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) { return umma_desc_kmajor(saddr, 128); }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
@@ -95,7 +108,7 @@ __device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int c
 
 // out_kind 3: 32 consecutive columns of the fused [q | k | v] projection (one head, one of q/k/v) as attention operands
 __device__ __forceinline__ void store_qkv32(const TcParams& p, size_t row, int col, const float* v) {
-  const int parts = p.w_parts, HD = p.att_H * p.att_dpad;
+  const int parts = p.parts, HD = p.att_H * p.att_dpad;
   const int region = col / HD, rem = col - region * HD;
   float r[32];
 #pragma unroll
@@ -130,88 +143,91 @@ __device__ __forceinline__ void store_qkv32(const TcParams& p, size_t row, int c
   }
 }
 
-// Epilogue of one accumulator row (this thread's TMEM lane) over the 128 columns [n0, n0+128): + bias, SiLU / GEGLU,
-// + fp32 residual, store in the requested representation.  trow = TMEM address of column n0 of this lane.
-__device__ __forceinline__ void epilogue_128(const TcParams& p, uint32_t trow, int n0, size_t grow, bool valid) {
-    const float* rrow = p.R ? p.R + (grow / p.r_div) * p.r_ld : nullptr;
-    if (p.epilogue == EPI_GEGLU) {
-      const int n_out = p.N >> 1;
+// Epilogue of one accumulator row (this thread's TMEM lane) over this thread's half of the BN columns [n0, n0+BN):
+// + bias, SiLU / GEGLU, + fp32 residual, store in the requested representation.  trow = TMEM address of column n0.
+__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, int n0, size_t grow, bool valid, int half) {
+  const float* rrow = p.R ? p.R + (grow / p.r_div) * p.r_ld : nullptr;
+  if (p.epilogue == EPI_GEGLU) {          // 128-column groups of [64 value | 64 gate]
+    const int n_out = p.N >> 1, upt = p.BN >> 7;   // (group, 32-column chunk) units per thread
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float v[32], g[32];
-        tmem_ld32(trow + c * 32, v);
-        tmem_ld32(trow + 64 + c * 32, g);
-        const int col_v = n0 + c * 32, col_g = n0 + 64 + c * 32, oc = (n0 >> 1) + c * 32;
+    for (int u = half * upt; u < (half + 1) * upt; ++u) {
+      const int grp = u >> 1, c = u & 1;
+      float v[32], g[32];
+      tmem_ld32(trow + grp * 128 + c * 32, v);
+      tmem_ld32(trow + grp * 128 + 64 + c * 32, g);
+      const int col_v = n0 + grp * 128 + c * 32, col_g = col_v + 64, oc = ((n0 + grp * 128) >> 1) + c * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float a = v[i], gg = g[i];
-          if (p.bias) { a += __ldg(p.bias + col_v + i); gg += __ldg(p.bias + col_g + i); }
-          v[i] = a * gelu_erf(gg);
-        }
-        if (valid) {
-          if (rrow) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += rrow[oc + i];
-          }
-          store_row32(p, grow, oc, n_out, v);
-        }
+      for (int i = 0; i < 32; ++i) {
+        float a = v[i], gg = g[i];
+        if (p.bias) { a += __ldg(p.bias + col_v + i); gg += __ldg(p.bias + col_g + i); }
+        v[i] = a * gelu_erf(gg);
       }
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < TBN / 32; ++c) {
-        float v[32];
-        tmem_ld32(trow + c * 32, v);
-        const int col = n0 + c * 32;
-        if (p.bias) {
+      if (valid) {
+        if (rrow) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+          for (int i = 0; i < 32; ++i) v[i] += rrow[oc + i];
         }
-        if (p.epilogue == EPI_SILU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
-        }
-        if (valid) {
-          if (rrow) {
-            const float4* r4 = reinterpret_cast<const float4*>(rrow + col);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 q = r4[i];
-              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
-            }
-          }
-          if (p.out_kind == 3) store_qkv32(p, grow, col, v);
-          else store_row32(p, grow, col, p.N, v);
-        }
+        store_row32(p, grow, oc, n_out, v);
       }
     }
+  } else {
+    const int cpt = p.BN >> 6;            // 32-column chunks per thread
+#pragma unroll 1
+    for (int c = half * cpt; c < (half + 1) * cpt; ++c) {
+      float v[32];
+      tmem_ld32(trow + c * 32, v);
+      const int col = n0 + c * 32;
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+      }
+      if (p.epilogue == EPI_SILU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+      }
+      if (valid) {
+        if (rrow) {
+          const float4* r4 = reinterpret_cast<const float4*>(rrow + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = r4[i];
+            v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+          }
+        }
+        if (p.out_kind == 3) store_qkv32(p, grow, col, v);
+        else store_row32(p, grow, col, p.N, v);
+      }
+    }
+  }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;              // 1024 B alignment required by the 128B swizzle atoms
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t a_base = base, w_base = base + TSTAGES * A_STAGE_BYTES;
-  const uint32_t bar_base = w_base + TSTAGES * W_STAGE_BYTES;   // full[S], empty[S], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TSTAGES * (A_STAGE_BYTES + W_STAGE_BYTES) + 8 * (2 * TSTAGES + 1));
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TSTAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * TSTAGES);
+  const uint32_t a_ring = base, w_ring = base + p.na * A_SLOT_BYTES;
+  const uint32_t ring_bytes = p.na * A_SLOT_BYTES + p.nw * p.w_slot_bytes;
+  const uint32_t bar_base = base + ring_bytes;    // a_full[8], a_empty[8], w_full[8], w_empty[8], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ring_bytes + 8 * (4 * MAX_SLOTS + 4));
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (MAX_SLOTS + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * MAX_SLOTS + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (3 * MAX_SLOTS + s); };
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (4 * MAX_SLOTS + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (4 * MAX_SLOTS + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * TBN;
-  const int b = blockIdx.y / p.tiles_per_batch;
-  const int t0 = (blockIdx.y - b * p.tiles_per_batch) * TBM;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&mapA);
     prefetch_tensormap(&mapW);
-    for (int s = 0; s < TSTAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < 4 * MAX_SLOTS; ++s) mbar_init(bar_base + 8u * s, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), N_EPI_THREADS);
     }
-    mbar_init(tmem_full_bar, 1);
     mbar_fence_init();
   } else if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -219,60 +235,146 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
-  const int kblocks_per_tap = p.cin / TBK;
+  const int n1 = p.parts == 3 ? p.nkb : 0;       // pass-1 K blocks (split mode only)
+
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
-      for (int pr = 0; pr < p.n_pairs; ++pr) {
-        const int a_col0 = p.pair_a[pr] * p.cin;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int w_col0 = (tap * p.w_parts + p.pair_w[pr]) * p.cin;
-          for (int cb = 0; cb < kblocks_per_tap; ++cb, ++it) {
-            const int s = it % TSTAGES;
-            const uint32_t ph = (uint32_t)(it / TSTAGES) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            mbar_expect_tx(full_bar(s), A_STAGE_BYTES + W_STAGE_BYTES);
-            tma_load_3d(a_base + s * A_STAGE_BYTES, &mapA, full_bar(s), a_col0 + cb * TBK, t0 - p.pad + tap, b);
-            tma_load_2d(w_base + s * W_STAGE_BYTES, &mapW, full_bar(s), w_col0 + cb * TBK, n0);
-          }
+      int sa = 0, sw = 0;                        // next slot of each ring
+      uint32_t pha = 0, phw = 0;
+      auto load_a = [&](int col, int row, int b) {
+        mbar_wait(a_empty(sa), pha ^ 1u);
+        mbar_expect_tx(a_full(sa), A_SLOT_BYTES);
+        tma_load_3d(a_ring + sa * A_SLOT_BYTES, &mapA, a_full(sa), col, row, b);
+        if (++sa == p.na) { sa = 0; pha ^= 1u; }
+      };
+      auto load_w = [&](int col, int n0) {
+        mbar_wait(w_empty(sw), phw ^ 1u);
+        mbar_expect_tx(w_full(sw), p.w_slot_bytes);
+        tma_load_2d(w_ring + sw * p.w_slot_bytes, &mapW, w_full(sw), col, n0);
+        if (++sw == p.nw) { sw = 0; phw ^= 1u; }
+      };
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int b = mt / p.tiles_per_batch;
+        const int t0 = (mt - b * p.tiles_per_batch) * TBM;
+        const int n0 = nt * p.BN;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < n1; ++kb) {
+          const int row = t0 - p.pad + tap, acol = cb * TBK, wcol = tap * p.parts * p.cin + cb * TBK;
+          load_a(2 * p.cin + acol, row, b);
+          load_w(wcol, n0);
+          load_a(p.cin + acol, row, b);
+          load_w(wcol + p.cin, n0);
+          load_a(acol, row, b);
+          load_w(wcol + 2 * p.cin, n0);
+          if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
+        }
+        tap = 0; cb = 0;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          load_a(cb * TBK, t0 - p.pad + tap, b);
+          load_w(tap * p.parts * p.cin + cb * TBK, n0);
+          if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const int total = p.n_pairs * p.taps * kblocks_per_tap;
-      for (int it = 0; it < total; ++it) {
-        const int s = it % TSTAGES;
-        const uint32_t ph = (uint32_t)(it / TSTAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
+      const uint32_t idesc = umma_idesc_bf16(TBM, p.BN);
+      int sa = 0, sw = 0;                        // oldest live slot of each ring
+      uint32_t pha = 0, phw = 0;
+      int local = 0;
+      auto next_a = [&]() { if (++sa == p.na) { sa = 0; pha ^= 1u; } };
+      auto next_w = [&]() { if (++sw == p.nw) { sw = 0; phw ^= 1u; } };
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        mbar_wait(tmem_empty_bar(buf), (((uint32_t)local >> 1) & 1u) ^ 1u);   // the epilogue has drained this buffer
         tc_fence_after();
-        const uint64_t ad = umma_smem_desc(a_base + s * A_STAGE_BYTES);
-        const uint64_t wd = umma_smem_desc(w_base + s * W_STAGE_BYTES);
+        const uint32_t acc = tmem_base + buf * ACC_STRIDE;
+        uint32_t accumulate = 0;
+        auto product = [&](int a_slot, int w_slot) {
+          const uint64_t ad = umma_desc_kmajor(a_ring + a_slot * A_SLOT_BYTES, 128);
+          const uint64_t wd = umma_desc_kmajor(w_ring + w_slot * p.w_slot_bytes, 128);
 #pragma unroll
-        for (int k = 0; k < TBK / 16; ++k)   // +32 B (16 bf16) along K inside the swizzle atom per UMMA_K step
-          umma_bf16(tmem_acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), kIdesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar(s));
+          for (int k = 0; k < TBK / 16; ++k) {   // +32 B (16 bf16) along K inside the swizzle atom per UMMA_K step
+            umma_bf16(acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc, accumulate);
+            accumulate = 1;
+          }
+        };
+        for (int kb = 0; kb < n1; ++kb) {
+          // slots (ring order): A: sa -> lo, sa+1 -> mid, sa+2 -> hi ; W: sw -> hi, sw+1 -> mid, sw+2 -> lo
+          const int a_lo = sa, w_hi = sw;
+          mbar_wait(a_full(a_lo), pha);
+          mbar_wait(w_full(w_hi), phw);
+          tc_fence_after();
+          product(a_lo, w_hi);                   // lo * hi
+          umma_commit(a_empty(a_lo));
+          next_a();
+          const int a_mid = sa;
+          mbar_wait(a_full(a_mid), pha);
+          tc_fence_after();
+          product(a_mid, w_hi);                  // mid * hi
+          umma_commit(w_empty(w_hi));
+          next_w();
+          const int w_mid = sw;
+          mbar_wait(w_full(w_mid), phw);
+          tc_fence_after();
+          product(a_mid, w_mid);                 // mid * mid
+          umma_commit(a_empty(a_mid));
+          next_a();
+          const int a_hi = sa;
+          mbar_wait(a_full(a_hi), pha);
+          tc_fence_after();
+          product(a_hi, w_mid);                  // hi * mid
+          umma_commit(w_empty(w_mid));
+          next_w();
+          const int w_lo = sw;
+          mbar_wait(w_full(w_lo), phw);
+          tc_fence_after();
+          product(a_hi, w_lo);                   // hi * lo
+          umma_commit(a_empty(a_hi));
+          umma_commit(w_empty(w_lo));
+          next_a();
+          next_w();
+        }
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(a_full(sa), pha);
+          mbar_wait(w_full(sw), phw);
+          tc_fence_after();
+          product(sa, sw);                       // hi * hi
+          umma_commit(a_empty(sa));
+          umma_commit(w_empty(sw));
+          next_a();
+          next_w();
+        }
+        umma_commit(tmem_full_bar(buf));
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
-    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
-    const int quarter = warp & 3;
+    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps of a quarter split the columns ----
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int r_in_tile = quarter * 32 + lane;
-    const int t = t0 + r_in_tile;
-    const bool valid = t < p.rows;
-    const size_t grow = (size_t)b * p.rows + (valid ? t : 0);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    epilogue_128(p, tmem_acc + ((uint32_t)(quarter * 32) << 16), n0, grow, valid);
-    tc_fence_before();
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int b = mt / p.tiles_per_batch;
+      const int t = (mt - b * p.tiles_per_batch) * TBM + r_in_tile;
+      const bool valid = t < p.rows;
+      const size_t grow = (size_t)b * p.rows + (valid ? t : 0);
+      const int buf = local & 1;
+      mbar_wait(tmem_full_bar(buf), ((uint32_t)local >> 1) & 1u);
+      tc_fence_after();
+      epilogue_row(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, grow, valid, half);
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar(buf));
+    }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -307,7 +409,7 @@ struct MapKeyHash {
   }
 };
 
-// bf16 tensor [d2][d1][d0] (d0 contiguous), box = 64 x box1 x 1, 128B swizzle, zero OOB fill.
+// bf16 tensor [d2][d1][d0] (d0 contiguous), box = TBK x box1 x 1, 128B swizzle, zero OOB fill.
 cudaError_t get_map(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1, CUtensorMap* out) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
@@ -325,14 +427,14 @@ cudaError_t get_map(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint
   if (d2 == 0) {
     const cuuint64_t dims[2] = {d0, d1};
     const cuuint64_t strides[1] = {d0 * 2};
-    const cuuint32_t box[2] = {64, box1};
+    const cuuint32_t box[2] = {TBK, box1};
     const cuuint32_t es[2] = {1, 1};
     r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const cuuint64_t dims[3] = {d0, d1, d2};
     const cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
-    const cuuint32_t box[3] = {64, box1, 1};
+    const cuuint32_t box[3] = {TBK, box1, 1};
     const cuuint32_t es[3] = {1, 1, 1};
     r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -342,6 +444,16 @@ cudaError_t get_map(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint
   cache.emplace(key, m);
   *out = m;
   return cudaSuccess;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+      n = 148;
+  }
+  return n;
 }
 
 }  // namespace
@@ -365,34 +477,42 @@ cudaError_t tc_make_map_bf16(const void* ptr, int rank, const uint64_t* dims, co
 
 cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (a.batches <= 0 || a.rows <= 0 || a.N <= 0) return cudaSuccess;
-  if (a.cin % TBK || a.N % TBN || (a.taps != 1 && a.taps != 3) || a.n_pairs < 1 || a.n_pairs > 6 || a.a_parts < 1 ||
-      a.w_parts < 1 || (a.out_kind != 3 && a.c_ld % 8) || (a.R && a.r_ld % 4) || a.r_div < 1)
+  const bool split = a.a_parts == 3 && a.w_parts == 3 && a.n_pairs == 6;
+  const bool plain = a.a_parts == 1 && a.w_parts == 1 && a.n_pairs == 1;
+  if (a.cin % 64 || a.N % 128 || (a.taps != 1 && a.taps != 3) || (!split && !plain) || (a.out_kind != 3 && a.c_ld % 8) ||
+      (a.R && a.r_ld % 4) || a.r_div < 1)
+    return cudaErrorInvalidValue;
+  if (a.out_kind == 3 && (!a.q_out || !a.k_out || !a.vt_out || a.att_T < 1 || a.att_dpad % 32 || a.N != 3 * a.att_H * a.att_dpad ||
+                          a.epilogue != EPI_NONE))
     return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  TcParams p;
+  p.BN = a.N % 256 == 0 ? 256 : ((a.N % 192 == 0 && a.epilogue != EPI_GEGLU) ? 192 : 128);   // GEGLU groups are 128 wide
+  p.w_slot_bytes = p.BN * TBK * 2;
+  p.na = p.BN == 256 ? 4 : 5;
+  p.nw = (SMEM_BUDGET - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
+  if (p.nw > MAX_SLOTS) p.nw = MAX_SLOTS;
   CUtensorMap mA, mW;
   cudaError_t e = get_map(a.A, (uint64_t)a.a_parts * a.cin, (uint64_t)a.rows, (uint64_t)a.batches, TBM, &mA);
   if (e != cudaSuccess) return e;
-  e = get_map(a.W, (uint64_t)a.taps * a.w_parts * a.cin, (uint64_t)a.N, 0, TBN, &mW);
+  e = get_map(a.W, (uint64_t)a.taps * a.w_parts * a.cin, (uint64_t)a.N, 0, (uint32_t)p.BN, &mW);
   if (e != cudaSuccess) return e;
-  TcParams p;
   p.rows = a.rows; p.batches = a.batches; p.tiles_per_batch = (a.rows + TBM - 1) / TBM;
-  p.cin = a.cin; p.taps = a.taps; p.pad = a.taps == 3 ? 1 : 0;
-  p.w_parts = a.w_parts; p.n_pairs = a.n_pairs;
-  for (int i = 0; i < 6; ++i) { p.pair_a[i] = a.pair_a[i]; p.pair_w[i] = a.pair_w[i]; }
+  p.n_tiles = a.N / p.BN; p.total_tiles = p.n_tiles * p.tiles_per_batch * a.batches;
+  p.cin = a.cin; p.taps = a.taps; p.pad = a.taps == 3 ? 1 : 0; p.parts = a.a_parts;
+  p.kb_per_tap = a.cin / TBK; p.nkb = a.taps * p.kb_per_tap;
   p.N = a.N; p.bias = a.bias; p.R = a.R; p.r_ld = a.r_ld; p.r_div = a.r_div;
   p.C = a.C; p.c_ld = a.c_ld; p.out_kind = a.out_kind; p.epilogue = a.epilogue;
   p.q_out = a.q_out; p.k_out = a.k_out; p.vt_out = a.vt_out;
   p.att_T = a.att_T; p.att_H = a.att_H; p.att_dpad = a.att_dpad; p.att_Tpad = a.att_Tpad;
-  if (a.out_kind == 3 && (!a.q_out || !a.k_out || !a.vt_out || a.att_T < 1 || a.att_dpad % 32 || a.N != 3 * a.att_H * a.att_dpad ||
-                          a.epilogue != EPI_NONE))
-    return cudaErrorInvalidValue;
-  dim3 grid(a.N / TBN, p.tiles_per_batch * a.batches);
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(mA, mW, p);
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + 8 * (4 * MAX_SLOTS + 4) + 16;
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mA, mW, p);
   return cudaGetLastError();
 }
 
