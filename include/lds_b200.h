@@ -64,8 +64,16 @@ typedef enum { LDS_DTYPE_F32 = 0, LDS_DTYPE_BF16 = 1, LDS_DTYPE_F16 = 2 } lds_dt
  *  LDS_SAMPLER_DDPM       (diffusion/diffusion.py:104-121,335-341)
  *     n_rows = n_nfe.    row j: [0]=sqrt_recip_acp [1]=sqrt_recipm1_acp [2]=post_mean_coef1 [3]=post_mean_coef2
  *                               [4]=[t>0]*exp(0.5*post_log_var)   (t = k_step-1-j)
+ *  LDS_SAMPLER_DDIM       (diffusion/diffusion.py:123-132,317-332)   t_j = reversed(range(0, t_total, interval))
+ *     n_rows = n_nfe.    row j: [0]=sqrt(a_t) [1]=sqrt((1-a_prev)/a_prev)-sqrt((1-a_t)/a_t) [2]=sqrt(a_prev),
+ *                               a_prev = alphas_cumprod[max(t-interval,0)]
+ *  LDS_SAMPLER_PNDM       (diffusion/diffusion.py:134-167,300-316)   PLMS, same timesteps
+ *     n_rows = n_nfe-1 (the first step evaluates the denoiser twice: at t_0 and at max(t_0-interval,0)).
+ *                        row j: [0]=a_prev-a_t [1]=1/(sqrt(a_t)*(sqrt(a_t)+sqrt(a_prev)))
+ *                               [2]=1/(sqrt(a_t)*(sqrt((1-a_prev)*a_t)+sqrt((1-a_t)*a_prev)))
  */
-typedef enum { LDS_SAMPLER_DPMPP_2M = 0, LDS_SAMPLER_UNIPC_BH2 = 1, LDS_SAMPLER_DDPM = 2 } lds_sampler;
+typedef enum { LDS_SAMPLER_DPMPP_2M = 0, LDS_SAMPLER_UNIPC_BH2 = 1, LDS_SAMPLER_DDPM = 2, LDS_SAMPLER_DDIM = 3,
+               LDS_SAMPLER_PNDM = 4 } lds_sampler;
 #define LDS_COEF_STRIDE 12
 
 /* Mirrors Unit2Mel.__init__ (diffusion/unit2mel.py:52-71). */
@@ -124,7 +132,7 @@ LDS_API int lds_denoise(lds_handle* h, const float* x_BMT, const float* cond_BTH
  *   lds_sample_steps : runs program steps [k0, k1) ; step_noise[(k1-k0), B, out_dims, T] for DDPM, else NULL
  *   lds_sample_end   : mel[B,T,out_dims] = x^T / acoustic_scale   (diffusion.py:342-343)
  *   lds_sample       : begin + all steps + end
- * Step indices: DPM/UniPC k in [0, steps] (k=0 is the first evaluation), DDPM j in [0, n_nfe). */
+ * Step indices: DPM/UniPC k in [0, steps] (k=0 is the first evaluation), DDPM / DDIM j in [0, n_nfe), PNDM j in [0, n_nfe-1). */
 LDS_API int lds_sample_begin(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, void* stream);
 LDS_API int lds_sample_steps(lds_handle* h, int k0, int k1, const float* step_noise, void* stream);
 LDS_API int lds_sample_end(lds_handle* h, float* mel_BTM, void* stream);

@@ -8,7 +8,8 @@
 // both products are evaluated as the six significant plane products (split-bf16), softmax in fp32 with expf.
 //
 // CTA = 128 queries of one (utterance, head); keys stream in tiles of 64.  Two passes over the keys:
-//   pass A: S = Q K^T -> TMEM, softmax warps reduce the row maximum m (no exponentials)
+//   pass A: S ~ Q_hi K_hi^T (one plane product: the maximum is only needed to ~1 %) -> TMEM, softmax warps reduce the
+//           row maximum m (no exponentials)
 //   pass B: S again, P = exp(S*scale - m) (fp32), row sums in registers, P planes -> shared memory (128B-swizzled,
 //           K-major), O += P V accumulated in TMEM across all key tiles with the accumulate flag (m is final, so O
 //           never needs rescaling)
@@ -76,8 +77,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // accumulator column block per B plane; the softmax / epilogue threads add the blocks.
 struct MmaItem { int a_plane, b_plane0, n_planes, blk; };
 
-template <int DPAD, int AKV, int PARTS>
-__global__ void __launch_bounds__(ATT_TC_THREADS, PARTS == 1 ? 2 : 1)
+// DUAL (split mode, d <= 32): two S accumulator blocks instead of three and 256 TMEM columns, so that two CTAs fit on
+// one SM and the softmax of one overlaps the tensor-pipe work of the other.
+template <int DPAD, int AKV, int PARTS, bool DUAL>
+__global__ void __launch_bounds__(ATT_TC_THREADS, (PARTS == 1 || DUAL) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapVT, const AttnTcParams p) {
   constexpr int SWZ = DPAD * 2;                    // swizzle width of the Q/K tiles (bytes per row)
@@ -113,9 +116,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
   const int nt = (p.T + AKV - 1) / AKV;
   const int HD = p.H * DPAD;
-  constexpr int tmem_cols = parts == 3 ? 512 : 256;
-  constexpr int o_col = parts == 3 ? 256 : 128;    // S buffers start at column 0, O blocks at o_col
-  constexpr int n_sblk = parts == 3 ? (AKV == 64 ? 3 : 2) : 1;
+  constexpr int tmem_cols = (parts == 3 && !DUAL) ? 512 : 256;
+  constexpr int o_col = (parts == 3 && !DUAL) ? 256 : 128;    // S buffers start at column 0, O blocks at o_col
+  constexpr int n_sblk = parts == 3 ? ((AKV == 64 && !DUAL) ? 3 : 2) : 1;
   constexpr int s_stride = n_sblk * AKV;           // TMEM columns per S buffer
   constexpr int n_oblk = parts == 3 ? 3 : 1;
 
@@ -143,9 +146,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       for (int it = 0; it < 2 * nt; ++it) {
         const int jt = it < nt ? it : it - nt;
         const int ks = it % NK;
+        const int kparts = it < nt ? 1 : parts;                  // pass A needs the hi plane only
         mbar_wait(k_empty(ks), ((uint32_t)(it / NK) & 1u) ^ 1u);
-        mbar_expect_tx(k_full(ks), parts * KB);
-        for (int pl = 0; pl < parts; ++pl)
+        mbar_expect_tx(k_full(ks), kparts * KB);
+        for (int pl = 0; pl < kparts; ++pl)
           tma_load_3d(k_s + (ks * parts + pl) * KB, &mapK, k_full(ks), pl * HD + h * DPAD, jt * AKV, b);
         if (it >= nt) {
           const int vs = jt % NV;
@@ -164,7 +168,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       MmaItem qk[4], pv[3];
       int n_qk, n_pv;
       if (parts == 3) {
-        if (AKV == 64) { qk[0] = {0, 0, 3, 0}; qk[1] = {1, 0, 2, 0}; qk[2] = {2, 0, 1, 0}; n_qk = 3; }
+        if (AKV == 64 && !DUAL) { qk[0] = {0, 0, 3, 0}; qk[1] = {1, 0, 2, 0}; qk[2] = {2, 0, 1, 0}; n_qk = 3; }
         else { qk[0] = {0, 0, 2, 0}; qk[1] = {1, 0, 2, 0}; qk[2] = {0, 2, 1, 1}; qk[3] = {2, 0, 1, 0}; n_qk = 4; }
         pv[0] = {0, 0, 3, 0}; pv[1] = {1, 0, 2, 0}; pv[2] = {2, 0, 1, 0}; n_pv = 3;
       } else {
@@ -189,6 +193,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const uint64_t k_stage_step = (uint64_t)((parts * KB) >> 4), v_stage_step = (uint64_t)((parts * KBLK * VBK) >> 4),
                      v_kb_step = (uint64_t)((parts * VBK) >> 4), p_buf_step = (uint64_t)((parts * KBLK * PBK) >> 4),
                      p_kb_step = (uint64_t)(PBK >> 4);
+      const uint64_t q_hi = umma_desc_kmajor(q_s, SWZ), k_hi = umma_desc_kmajor(k_s, SWZ);
+      const uint32_t hi_idesc = umma_idesc_bf16(AQ, AKV);
       mbar_wait(q_full, 0);
       auto issue_qk = [&](int it) {
         const int ks = it % NK, sb = it % NSB;
@@ -197,11 +203,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         tc_fence_after();
         const uint64_t koff = (uint64_t)ks * k_stage_step;
         const uint32_t soff = (uint32_t)(sb * s_stride);
+        if (it < nt) {
+          // pass A only needs the row maximum to ~1 %: hi*hi alone (any m close to the maximum gives the same softmax)
 #pragma unroll
-        for (int k = 0; k < DPAD / 16; ++k)
-          for (int e = 0; e < n_qk; ++e)
-            umma_bf16(qk_dst[e] + soff, qd0[e] + (uint64_t)(2 * k), kd0[e] + koff + (uint64_t)(2 * k), qk_idesc[e],
-                      (k == 0 && e == 0) ? 0u : 1u);
+          for (int k = 0; k < DPAD / 16; ++k)
+            umma_bf16(tmem0 + soff, q_hi + (uint64_t)(2 * k), k_hi + koff + (uint64_t)(2 * k), hi_idesc, k == 0 ? 0u : 1u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < DPAD / 16; ++k)
+            for (int e = 0; e < n_qk; ++e)
+              umma_bf16(qk_dst[e] + soff, qd0[e] + (uint64_t)(2 * k), kd0[e] + koff + (uint64_t)(2 * k), qk_idesc[e],
+                        (k == 0 && e == 0) ? 0u : 1u);
+        }
         umma_commit(k_empty(ks));
         umma_commit(s_full(sb));
       };
@@ -251,7 +264,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
         float s[32];
-        load_s32(sb, c0 + ch * 32, s);
+        tmem_ld32(tmem0 + lane_off + sb * s_stride + c0 + ch * 32, s);   // hi*hi scores live in block 0
         if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
         const int k0 = it * AKV + c0 + ch * 32;
         if (k0 + 32 <= p.T) {
@@ -361,12 +374,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   }
 }
 
-template <int DPAD, int AKV, int PARTS>
+template <int DPAD, int AKV, int PARTS, bool DUAL = false>
 cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, cudaStream_t s) {
   const int parts = a.parts;
   const size_t smem = (size_t)parts * (AQ * DPAD * 2 + nk * AKV * DPAD * 2 + nv * DPAD * AKV * 2 + npb * AQ * AKV * 2) + 1024 +
                       72 + 8 * 16 + 16 + 2 * 128 * 4 + 64;
-  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, AKV, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint64_t HD = (uint64_t)a.H * DPAD;
   CUtensorMap mQ, mK, mV;
@@ -388,7 +401,7 @@ cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, c
   p.scale = 1.0f / sqrtf((float)a.d);
   p.out = a.out;
   dim3 grid((a.T + AQ - 1) / AQ, a.H, a.B);
-  attention_tc_kernel<DPAD, AKV, PARTS><<<grid, ATT_TC_THREADS, smem, s>>>(mQ, mK, mV, p);
+  attention_tc_kernel<DPAD, AKV, PARTS, DUAL><<<grid, ATT_TC_THREADS, smem, s>>>(mQ, mK, mV, p);
   return cudaGetLastError();
 }
 
@@ -401,7 +414,8 @@ cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
   //                        bf16: a third of that (two CTAs per SM, bounded by 2 x 256 TMEM columns)
   // shared memory per CTA (KB): Q + nk*K + nv*V^T + P
   if (a.parts == 3) {
-    if (a.dpad == 32) return launch_attn<32, 128, 3>(a, 2, 2, 1, 1, s);   // 24 + 2*24 + 2*24 + 96 = 216, TMEM 256 (S) + 96 (O)
+    // d <= 32: two CTAs per SM: 24 (Q) + 2*12 (K) + 12 (V^T) + 48 (P) = 108 KB, TMEM 128 (S) + 96 (O) per CTA
+    if (a.dpad == 32) return launch_attn<32, 64, 3, true>(a, 2, 1, 1, 1, s);
     if (a.dpad == 64) return launch_attn<64, 64, 3>(a, 2, 2, 1, 1, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
   } else {                                                             // bf16: S and P double-buffered, two CTAs per SM
     if (a.dpad == 32) return launch_attn<32, 64, 1>(a, 4, 3, 2, 2, s);    //  8 + 4*4 + 3*4 + 2*16 = 68, TMEM 2*64 (S) + 32 (O)

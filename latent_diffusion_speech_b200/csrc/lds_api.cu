@@ -923,10 +923,12 @@ int lds_finalize_weights(lds_handle* h) {
 int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t_sinusoid, int n_rows, const float* coefs) {
   if (!h || !h->finalized) return fail(LDS_ERR_INVALID, "lds_plan: weights not finalized");
   if (B < 1 || T < 1) return fail(LDS_ERR_INVALID, "lds_plan: B and T must be positive");
-  if (sampler < LDS_SAMPLER_DPMPP_2M || sampler > LDS_SAMPLER_DDPM) return fail(LDS_ERR_INVALID, "unknown sampler %d", sampler);
+  if (sampler < LDS_SAMPLER_DPMPP_2M || sampler > LDS_SAMPLER_PNDM) return fail(LDS_ERR_INVALID, "unknown sampler %d", sampler);
   if (n_nfe < 0 || n_rows < 0 || (n_nfe > 0 && !t_sinusoid) || (n_rows > 0 && !coefs)) return fail(LDS_ERR_INVALID, "lds_plan: bad program");
   if (n_nfe > 0) {
-    if (sampler == LDS_SAMPLER_DDPM ? n_rows != n_nfe : n_rows != n_nfe + 1)
+    const int want_rows = (sampler == LDS_SAMPLER_DDPM || sampler == LDS_SAMPLER_DDIM) ? n_nfe
+                          : (sampler == LDS_SAMPLER_PNDM ? n_nfe - 1 : n_nfe + 1);
+    if (n_rows != want_rows || n_rows < 1)
       return fail(LDS_ERR_INVALID, "lds_plan: n_rows=%d inconsistent with n_nfe=%d for sampler %d", n_rows, n_nfe, sampler);
   }
   if ((int64_t)B * T > (1ll << 30)) return fail(LDS_ERR_INVALID, "B*T too large");
@@ -1127,7 +1129,7 @@ int lds_sample_steps(lds_handle* h, int k0, int k1, const float* step_noise, voi
   const int S = h->n_nfe;   // DPM / UniPC: number of solver steps == number of evaluations
   for (int k = k0; k < k1; ++k) {
     const float* c = &h->coefs[(size_t)k * LDS_COEF_STRIDE];
-    float* m0 = h->mbuf[h->m_cur];
+    float* m0 = h->mbuf[h->m_cur % 3];
     float* m1 = h->mbuf[(h->m_cur + 2) % 3];
     float* mfree = h->mbuf[(h->m_cur + 1) % 3];
     if (h->sampler == LDS_SAMPLER_DDPM) {
@@ -1135,6 +1137,32 @@ int lds_sample_steps(lds_handle* h, int k0, int k1, const float* step_noise, voi
       LDS_TRY(launched(h, s, PC_SOLVER, 0, 4 * sb,
                        launch_ddpm_step(h->x, h->eps, step_noise + (size_t)(k - k0) * n, c[0], c[1], c[2], c[3], c[4], h->B,
                                         h->T, h->cfg.out_dims, s), "ddpm_step"));
+      continue;
+    }
+    if (h->sampler == LDS_SAMPLER_DDIM) {
+      LDS_TRY(run_unet(h, s, h->x, h->temb + (size_t)k * h->temb_total, h->eps));
+      LDS_TRY(launched(h, s, PC_SOLVER, 0, 3 * sb, launch_ddim_step(h->x, h->eps, c[0], c[1], c[2], n, s), "ddim_step"));
+      continue;
+    }
+    if (h->sampler == LDS_SAMPLER_PNDM) {
+      // noise-prediction ring {eps, mbuf0, mbuf1, mbuf2}: slot (m_cur) receives this step's prediction, the previous
+      // ones sit behind it (diffusion.py:160-165: noise_list[-1], [-2], [-3])
+      float* ring[4] = {h->eps, h->mbuf[0], h->mbuf[1], h->mbuf[2]};
+      float* e = ring[h->m_cur & 3];
+      const float* h1 = ring[(h->m_cur + 3) & 3];
+      const float* h2 = ring[(h->m_cur + 2) & 3];
+      const float* h3 = ring[(h->m_cur + 1) & 3];
+      LDS_TRY(run_unet(h, s, h->x, h->temb + (size_t)(k == 0 ? 0 : k + 1) * h->temb_total, e));
+      if (k == 0) {   // bootstrap: predictor with e, second evaluation at max(t - interval, 0), average
+        LDS_TRY(launched(h, s, PC_SOLVER, 0, 3 * sb, launch_pndm_update(h->x, e, e, e, e, c[0], c[1], c[2], 0, h->xp, n, s), "pndm_update"));
+        LDS_TRY(run_unet(h, s, h->xp, h->temb + (size_t)h->temb_total, h->xb));
+        LDS_TRY(launched(h, s, PC_SOLVER, 0, 4 * sb, launch_pndm_update(h->x, e, h->xb, e, e, c[0], c[1], c[2], 1, h->x, n, s), "pndm_update"));
+      } else {
+        const int mode = k >= 3 ? 4 : k + 1;
+        LDS_TRY(launched(h, s, PC_SOLVER, 0, (2.0 + mode) * sb, launch_pndm_update(h->x, e, h1, h2, h3, c[0], c[1], c[2], mode, h->x, n, s),
+                         "pndm_update"));
+      }
+      h->m_cur = (h->m_cur + 1) & 3;
       continue;
     }
     if (k == 0) {

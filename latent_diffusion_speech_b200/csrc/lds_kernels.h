@@ -122,4 +122,10 @@ cudaError_t launch_unipc_correct(const float* xb, const float* m0, const float* 
 cudaError_t launch_ddpm_step(float* x, const float* eps, const float* noise_BMT, float c_recip, float c_recipm1,
                              float pm1, float pm2, float sig, int B, int T, int M, cudaStream_t s);
 
+// DDIM step: x = sqrt_aprev * (x / sqrt_at + coef * eps)                                   (diffusion.py:131)
+cudaError_t launch_ddim_step(float* x, const float* eps, float sqrt_at, float coef, float sqrt_aprev, int64_t n, cudaStream_t s);
+// PLMS step: out = x + d*(k1*x - k2*e'), e' = Adams-Bashforth combination selected by mode (solver.cu) (diffusion.py:134-167)
+cudaError_t launch_pndm_update(const float* x, const float* e, const float* h1, const float* h2, const float* h3, float d,
+                               float k1, float k2, int mode, float* out, int64_t n, cudaStream_t s);
+
 }  // namespace lds

@@ -29,13 +29,6 @@ __device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
   return r;
 }
 
-__device__ __forceinline__ Wf wf_of4(float4 v) {
-  const float mean = (v.x + v.y + v.z + v.w) * 0.25f;
-  const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-  Wf r;
-  r.n = 4.f; r.mean = mean; r.m2 = a * a + b * b + c * c + d * d;
-  return r;
-}
 
 __device__ __forceinline__ float4 load_cat(const float* x1, int c1, const float* x2, int c2, size_t row, int c) {
   // channel c of the virtual concat [x1 | x2]; c and c1 are multiples of 4
@@ -43,7 +36,18 @@ __device__ __forceinline__ float4 load_cat(const float* x1, int c1, const float*
                   : __ldg(reinterpret_cast<const float4*>(x2 + row * c2 + (c - c1)));
 }
 
+// Merge of partial (count, mean, M2) triples held by the lanes of one warp (lane-strided entries already folded into
+// n / nm / per-entry arrays by the caller): two shuffle reductions, no division inside the loops.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
 // grid (nchunk, B); block = (C/4) * rpar threads, thread (v, r) owns channel quad v and frames r, r+rpar, ...
+// Phase 1: every thread reduces its own values in registers (exact two-pass mean / M2 over <= GN_ROWS/rpar float4s).
+// Phase 2: warp g merges the per-thread triples of group g with the count-weighted Chan formula.
+constexpr int GN_UNROLL = 8;
 __global__ void gn_stats_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2, int T,
                                 int groups, int rpar, float* __restrict__ part) {
   extern __shared__ float sh[];  // [nthreads][3]
@@ -53,64 +57,128 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int c1, const floa
   const int t0 = chunk * GN_ROWS, t1 = min(t0 + GN_ROWS, T);
   Wf acc{0.f, 0.f, 0.f};
   if (r0 < rpar) {
-    for (int t = t0 + r0; t < t1; t += rpar) acc = wf_merge(acc, wf_of4(load_cat(x1, c1, x2, c2, (size_t)b * T + t, v * 4)));
+    for (int tb = t0 + r0; tb < t1; tb += rpar * GN_UNROLL) {
+      float4 x[GN_UNROLL];
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < GN_UNROLL; ++i) {
+        const int t = tb + i * rpar;
+        if (t < t1) { x[i] = load_cat(x1, c1, x2, c2, (size_t)b * T + t, v * 4); ++cnt; }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < GN_UNROLL; ++i)
+        if (i < cnt) sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+      const float n = 4.f * cnt, mean = sum / n;
+      float m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < GN_UNROLL; ++i)
+        if (i < cnt) {
+          const float d0 = x[i].x - mean, d1 = x[i].y - mean, d2 = x[i].z - mean, d3 = x[i].w - mean;
+          m2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+      acc = wf_merge(acc, Wf{n, mean, m2});
+    }
   }
   sh[threadIdx.x * 3 + 0] = acc.n; sh[threadIdx.x * 3 + 1] = acc.mean; sh[threadIdx.x * 3 + 2] = acc.m2;
   __syncthreads();
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x, vq = cg >> 2;  // quads per group
-    Wf tot{0.f, 0.f, 0.f};
-    for (int r = 0; r < rpar; ++r)
-      for (int q = 0; q < vq; ++q) {
-        const int th = r * V + g * vq + q;
-        tot = wf_merge(tot, Wf{sh[th * 3], sh[th * 3 + 1], sh[th * 3 + 2]});
-      }
-    float* dst = part + (((size_t)b * gridDim.x + chunk) * groups + g) * 3;
-    dst[0] = tot.n; dst[1] = tot.mean; dst[2] = tot.m2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int vq = cg >> 2, entries = rpar * vq;   // quads per group; per-thread triples of one group
+  for (int g = warp; g < groups; g += nwarps) {
+    float n = 0.f, nm = 0.f;
+    for (int e = lane; e < entries; e += 32) {
+      const int th = (e / vq) * V + g * vq + (e % vq);
+      n += sh[th * 3];
+      nm += sh[th * 3] * sh[th * 3 + 1];
+    }
+    n = warp_sum(n);
+    nm = warp_sum(nm);
+    const float mean = n > 0.f ? nm / n : 0.f;
+    float m2 = 0.f;
+    for (int e = lane; e < entries; e += 32) {
+      const int th = (e / vq) * V + g * vq + (e % vq);
+      const float d = sh[th * 3 + 1] - mean;
+      m2 += sh[th * 3 + 2] + sh[th * 3] * d * d;
+    }
+    m2 = warp_sum(m2);
+    if (lane == 0) {
+      float* dst = part + (((size_t)b * gridDim.x + chunk) * groups + g) * 3;
+      dst[0] = n; dst[1] = mean; dst[2] = m2;
+    }
   }
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
-// grid (nchunk, B), 256 threads; each thread handles float4s of the [GN_ROWS, C] slab.
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2,
-                                                       int c2, int T, int groups, const float* __restrict__ part,
-                                                       float eps, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, const float* __restrict__ ss,
-                                                       int silu, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
-                                                       int parts, __nv_bfloat16* __restrict__ rawb) {
+// grid (nchunk, B); block = (C/4) * rpar threads (as gn_stats): thread (v, r) owns channel quad v — its gamma / beta /
+// scale / shift live in registers — and frames r, r+rpar, ... of the [GN_ROWS, C] slab, four loads in flight.
+__global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2,
+                                                        int c2, int T, int groups, int rpar, const float* __restrict__ part,
+                                                        float eps, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ ss,
+                                                        int silu, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+                                                        int parts, __nv_bfloat16* __restrict__ rawb) {
   __shared__ float s_mean[32], s_rstd[32];
   const int C = c1 + c2, V = C >> 2, cg = C / groups;
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
-  if (threadIdx.x < groups) {
-    Wf tot{0.f, 0.f, 0.f};
-    const float* src = part + ((size_t)b * nchunk * groups + threadIdx.x) * 3;
-    for (int c = 0; c < nchunk; ++c, src += groups * 3) tot = wf_merge(tot, Wf{src[0], src[1], src[2]});
-    s_mean[threadIdx.x] = tot.mean;
-    s_rstd[threadIdx.x] = rsqrtf(tot.m2 / tot.n + eps);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < groups; g += nwarps) {   // merge the per-chunk partials of group g
+    const float* src = part + ((size_t)b * nchunk * groups + g) * 3;
+    float n = 0.f, nm = 0.f;
+    for (int c = lane; c < nchunk; c += 32) {
+      const float* e = src + (size_t)c * groups * 3;
+      n += e[0];
+      nm += e[0] * e[1];
+    }
+    n = warp_sum(n);
+    nm = warp_sum(nm);
+    const float mean = nm / n;
+    float m2 = 0.f;
+    for (int c = lane; c < nchunk; c += 32) {
+      const float* e = src + (size_t)c * groups * 3;
+      const float d = e[1] - mean;
+      m2 += e[2] + e[0] * d * d;
+    }
+    m2 = warp_sum(m2);
+    if (lane == 0) { s_mean[g] = mean; s_rstd[g] = rsqrtf(m2 / n + eps); }
   }
   __syncthreads();
-  const int t0 = chunk * GN_ROWS, rows = min(GN_ROWS, T - t0);
-  for (int e = threadIdx.x; e < rows * V; e += blockDim.x) {
-    const int r = e / V, c = (e - r * V) * 4;
-    const size_t row = (size_t)b * T + t0 + r;
-    const float4 xv = load_cat(x1, c1, x2, c2, row, c);
-    const int g = c / cg;
-    const float mean = s_mean[g], rstd = s_rstd[g];
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
-    float o[4] = {(xv.x - mean) * rstd * ga.x + be.x, (xv.y - mean) * rstd * ga.y + be.y,
-                  (xv.z - mean) * rstd * ga.z + be.z, (xv.w - mean) * rstd * ga.w + be.w};
-    if (ss) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
-      const float4 sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
-      o[0] = o[0] * (1.f + sc.x) + sf.x; o[1] = o[1] * (1.f + sc.y) + sf.y;
-      o[2] = o[2] * (1.f + sc.z) + sf.z; o[3] = o[3] * (1.f + sc.w) + sf.w;
+  const int v = threadIdx.x % V, r0 = threadIdx.x / V;
+  if (r0 >= rpar) return;
+  const int c = v * 4, g = c / cg;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sf = sc;
+  if (ss) {
+    sc = __ldg(reinterpret_cast<const float4*>(ss + c));
+    sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+  }
+  const int t0 = chunk * GN_ROWS, t1 = min(t0 + GN_ROWS, T);
+  constexpr int U = 4;
+  for (int tb = t0 + r0; tb < t1; tb += rpar * U) {
+    float4 xv[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int t = tb + i * rpar;
+      if (t < t1) xv[i] = load_cat(x1, c1, x2, c2, (size_t)b * T + t, c);
     }
-    if (silu) { o[0] = silu_f(o[0]); o[1] = silu_f(o[1]); o[2] = silu_f(o[2]); o[3] = silu_f(o[3]); }
-    if (yb) store_planes4(yb + row * (size_t)(parts * C), c, C, parts, o[0], o[1], o[2], o[3]);
-    else *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
-    if (rawb) store_planes4(rawb + row * (size_t)(parts * C), c, C, parts, xv.x, xv.y, xv.z, xv.w);
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int t = tb + i * rpar;
+      if (t >= t1) break;
+      const size_t row = (size_t)b * T + t;
+      float o[4] = {(xv[i].x - mean) * rstd * ga.x + be.x, (xv[i].y - mean) * rstd * ga.y + be.y,
+                    (xv[i].z - mean) * rstd * ga.z + be.z, (xv[i].w - mean) * rstd * ga.w + be.w};
+      if (ss) {
+        o[0] = o[0] * (1.f + sc.x) + sf.x; o[1] = o[1] * (1.f + sc.y) + sf.y;
+        o[2] = o[2] * (1.f + sc.z) + sf.z; o[3] = o[3] * (1.f + sc.w) + sf.w;
+      }
+      if (silu) { o[0] = silu_f(o[0]); o[1] = silu_f(o[1]); o[2] = silu_f(o[2]); o[3] = silu_f(o[3]); }
+      if (yb) store_planes4(yb + row * (size_t)(parts * C), c, C, parts, o[0], o[1], o[2], o[3]);
+      else *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (rawb) store_planes4(rawb + row * (size_t)(parts * C), c, C, parts, xv[i].x, xv[i].y, xv[i].z, xv[i].w);
+    }
   }
 }
 
@@ -182,9 +250,14 @@ cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, in
                             const float* part, float eps, const float* gamma, const float* beta, const float* ss,
                             int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s) {
   const int C = c1 + c2;
-  if (C % (4 * groups) || c1 % 4 || groups > 32) return cudaErrorInvalidValue;
+  if (C % (4 * groups) || c1 % 4 || groups > 32 || C / 4 > 1024) return cudaErrorInvalidValue;
+  const int V = C / 4;
+  int rpar = 256 / V;
+  if (rpar < 1) rpar = 1;
+  if (rpar > GN_ROWS) rpar = GN_ROWS;
+  const int threads = ((V * rpar + 31) / 32) * 32;
   dim3 grid((T + GN_ROWS - 1) / GN_ROWS, B);
-  gn_apply_kernel<<<grid, 256, 0, s>>>(x1, c1, x2, c2, T, groups, part, eps, gamma, beta, ss, silu, y, yb, parts, rawb);
+  gn_apply_kernel<<<grid, threads, 0, s>>>(x1, c1, x2, c2, T, groups, rpar, part, eps, gamma, beta, ss, silu, y, yb, parts, rawb);
   return cudaGetLastError();
 }
 

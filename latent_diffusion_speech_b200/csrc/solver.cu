@@ -10,6 +10,7 @@
 //   DPM-Solver++ first / second order multistep update           dpm_solver_pytorch.py:569-576, 813-831
 //   UniPC-bh2 predictor / corrector                              uni_pc.py:545-568
 //   DDPM ancestral step (x0 clamp, posterior mean, + sigma*z)    diffusion.py:95-121
+//   DDIM step, PLMS / PNDM step (Adams-Bashforth eps combination) diffusion.py:123-167
 //   [B,1,M,T] <-> channels-last [B,T,M], /acoustic_scale         diffusion.py:225,342-343
 #include "lds_kernels.h"
 #include "planes.cuh"
@@ -95,6 +96,41 @@ __global__ void unipc_correct_kernel(const float4* __restrict__ xb, const float4
                       f(base.w, p.w, q.w, t.w));
     }
     x[i] = r;
+  }
+}
+
+// DDIM (diffusion.py:131): x <- sqrt(a_prev) * (x / sqrt(a_t) + coef * eps)
+__global__ void ddim_step_kernel(float4* __restrict__ x, const float4* __restrict__ eps, float sqrt_at, float coef,
+                                 float sqrt_aprev, int64_t n) {
+  LDS_VEC4_LOOP(n) {
+    const float4 a = x[i], e = eps[i];
+    auto f = [&](float xv, float ev) { return mul(sqrt_aprev, add(dvd(xv, sqrt_at), mul(coef, ev))); };
+    x[i] = make_float4(f(a.x, e.x), f(a.y, e.y), f(a.z, e.z), f(a.w, e.w));
+  }
+}
+
+// PLMS (diffusion.py:134-167): e' = combination of the current and up to three previous noise predictions,
+//   mode 0: e   1: (e + e2)/2   2: (3e - h1)/2   3: (23e - 16 h1 + 5 h2)/12   4: (55e - 59 h1 + 37 h2 - 9 h3)/24
+// then out = x + d*(k1*x - k2*e').  Divisions are true divisions (the reference's CPU path).
+__global__ void pndm_update_kernel(const float4* __restrict__ x, const float4* __restrict__ e, const float4* __restrict__ h1,
+                                   const float4* __restrict__ h2, const float4* __restrict__ h3, float d, float k1, float k2,
+                                   int mode, float4* __restrict__ out, int64_t n) {
+  LDS_VEC4_LOOP(n) {
+    const float4 xv = x[i], ev = e[i];
+    float4 a = ev, b = ev, c = ev;
+    if (mode >= 1) a = h1[i];
+    if (mode >= 3) b = h2[i];
+    if (mode >= 4) c = h3[i];
+    auto f = [&](float xs, float es, float as, float bs, float cs) {
+      float ep = es;
+      if (mode == 1) ep = dvd(add(es, as), 2.f);
+      else if (mode == 2) ep = dvd(sub(mul(3.f, es), as), 2.f);
+      else if (mode == 3) ep = dvd(add(sub(mul(23.f, es), mul(16.f, as)), mul(5.f, bs)), 12.f);
+      else if (mode == 4) ep = dvd(sub(add(sub(mul(55.f, es), mul(59.f, as)), mul(37.f, bs)), mul(9.f, cs)), 24.f);
+      return add(xs, mul(d, sub(mul(k1, xs), mul(k2, ep))));
+    };
+    out[i] = make_float4(f(xv.x, ev.x, a.x, b.x, c.x), f(xv.y, ev.y, a.y, b.y, c.y), f(xv.z, ev.z, a.z, b.z, c.z),
+                         f(xv.w, ev.w, a.w, b.w, c.w));
   }
 }
 
@@ -254,6 +290,17 @@ cudaError_t launch_ddpm_step(float* x, const float* eps, const float* noise_BMT,
                              float pm1, float pm2, float sig, int B, int T, int M, cudaStream_t s) {
   dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
   ddpm_step_kernel<<<grid, block, 0, s>>>(x, eps, noise_BMT, c_recip, c_recipm1, pm1, pm2, sig, T, M);
+  return cudaGetLastError();
+}
+cudaError_t launch_ddim_step(float* x, const float* eps, float sqrt_at, float coef, float sqrt_aprev, int64_t n, cudaStream_t s) {
+  if (n % 4) return cudaErrorInvalidValue;
+  ddim_step_kernel<<<grid_for(n / 4), 256, 0, s>>>(V4W(x), V4(eps), sqrt_at, coef, sqrt_aprev, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_pndm_update(const float* x, const float* e, const float* h1, const float* h2, const float* h3, float d,
+                               float k1, float k2, int mode, float* out, int64_t n, cudaStream_t s) {
+  if (n % 4 || mode < 0 || mode > 4) return cudaErrorInvalidValue;
+  pndm_update_kernel<<<grid_for(n / 4), 256, 0, s>>>(V4(x), V4(e), V4(h1), V4(h2), V4(h3), d, k1, k2, mode, V4W(out), n);
   return cudaGetLastError();
 }
 cudaError_t launch_transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, float scale, cudaStream_t s) {

@@ -78,8 +78,13 @@ class GaussianDiffusion(nn.Module):
             elif method == "unipc":
                 kind = st.SAMPLER_UNIPC_BH2
                 t_in, rows = st.unipc_bh2_program(betas, steps)
+            elif method == "ddim":
+                kind = st.SAMPLER_DDIM
+                t_in, rows = st.ddim_program(self.alphas_cumprod, t_total, infer_speedup)
+            elif method == "pndm":
+                kind = st.SAMPLER_PNDM
+                t_in, rows = st.pndm_program(self.alphas_cumprod, t_total, infer_speedup)
             else:
-                # 'pndm' / 'ddim' of the reference (diffusion.py:300-332) are not on the CUDA path yet
                 raise NotImplementedError(method)
         else:
             kind = st.SAMPLER_DDPM

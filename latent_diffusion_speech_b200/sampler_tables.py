@@ -11,7 +11,7 @@ The arithmetic is done with fp32 torch CPU ops in the reference's own evaluation
 coefficients are the very floats the reference's CPU run produces:
   diffusion/dpm_solver_pytorch.py:94-154,271-280,474,547-576,796-831,1171-1213,1253-1292
   diffusion/uni_pc.py:76-138,471-588,606-658
-  diffusion/diffusion.py:95-121 (DDPM ancestral step), embeddings.py:24-64 (timestep sinusoid)
+  diffusion/diffusion.py:95-121 (DDPM ancestral step), :123-167 (DDIM, PLMS), embeddings.py:24-64 (timestep sinusoid)
 Row layouts are documented in include/lds_b200.h.
 """
 from __future__ import annotations
@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 COEF_STRIDE = 12
-SAMPLER_DPMPP_2M, SAMPLER_UNIPC_BH2, SAMPLER_DDPM = 0, 1, 2
+SAMPLER_DPMPP_2M, SAMPLER_UNIPC_BH2, SAMPLER_DDPM, SAMPLER_DDIM, SAMPLER_PNDM = 0, 1, 2, 3, 4
 
 
 def timestep_sinusoid(t: torch.Tensor, dim: int) -> torch.Tensor:
@@ -164,3 +164,36 @@ def ddpm_program(buffers: Dict[str, torch.Tensor], k_step: int) -> Tuple[torch.T
         mask = torch.tensor(0.0 if i == 0 else 1.0)
         rows[j, 4] = float(mask * (0.5 * b["posterior_log_variance_clipped"][i]).exp())
     return ts.float(), rows
+
+
+def _strided_timesteps(t_total: int, interval: int):
+    return list(reversed(range(0, t_total, interval)))
+
+
+def ddim_program(alphas_cumprod: torch.Tensor, t_total: int, interval: int) -> Tuple[torch.Tensor, np.ndarray]:
+    """DDIM, eta = 0 (diffusion.py:123-132,317-332).  Returns (integer timesteps as float [steps], rows [steps, 12])."""
+    acp = alphas_cumprod.detach().to("cpu", torch.float32)
+    ts = _strided_timesteps(t_total, interval)
+    rows = _rows(len(ts))
+    for j, i in enumerate(ts):
+        a_t, a_prev = acp[i], acp[max(i - interval, 0)]
+        rows[j, 0] = float(a_t.sqrt())
+        rows[j, 1] = float(((1 - a_prev) / a_prev).sqrt() - ((1 - a_t) / a_t).sqrt())
+        rows[j, 2] = float(a_prev.sqrt())
+    return torch.tensor(ts, dtype=torch.float32), rows
+
+
+def pndm_program(alphas_cumprod: torch.Tensor, t_total: int, interval: int) -> Tuple[torch.Tensor, np.ndarray]:
+    """PLMS / PNDM (diffusion.py:134-167,300-316).  Denoiser timesteps [steps+1]: t_0, max(t_0-interval,0), t_1, t_2, ...
+    (the first step is bootstrapped with a second evaluation); rows [steps, 12]."""
+    acp = alphas_cumprod.detach().to("cpu", torch.float32)
+    ts = _strided_timesteps(t_total, interval)
+    rows = _rows(len(ts))
+    for j, i in enumerate(ts):
+        a_t, a_prev = acp[i], acp[max(i - interval, 0)]
+        a_t_sq, a_prev_sq = a_t.sqrt(), a_prev.sqrt()
+        rows[j, 0] = float(a_prev - a_t)
+        rows[j, 1] = float(1 / (a_t_sq * (a_t_sq + a_prev_sq)))
+        rows[j, 2] = float(1 / (a_t_sq * (((1 - a_prev) * a_t).sqrt() + ((1 - a_t) * a_prev).sqrt())))
+    evals = [ts[0], max(ts[0] - interval, 0)] + ts[1:]
+    return torch.tensor(evals, dtype=torch.float32), rows

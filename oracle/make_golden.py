@@ -36,6 +36,10 @@ CASES = [
     ("shallow_dpm20_b2_t32", 2, 32, "dpm-solver", 5, 100, 0),
     ("shallow_unipc10_b2_t32", 2, 32, "unipc", 10, 100, 0),
     ("ddpm12_b2_t24", 2, 24, None, 1, 12, 12),                 # shallow start + 12 ancestral steps
+    ("ddim20_b2_t40", 2, 40, "ddim", 50, None, 0),
+    ("shallow_ddim10_b2_t37", 2, 37, "ddim", 10, 100, 0),
+    ("pndm20_b1_t40", 1, 40, "pndm", 50, None, 0),             # the reference's PLMS path only runs for B == 1
+    ("shallow_pndm10_b1_t37", 1, 37, "pndm", 10, 100, 0),
 ]
 
 
@@ -72,6 +76,8 @@ def main():
     torch.set_num_threads(8)
     with torch.no_grad():
         for name, B, T, method, speedup, k_step, n_noise in CASES:
+            if os.path.exists(os.path.join(GOLDEN_DIR, name + ".npz")) and "--force" not in sys.argv:
+                continue
             units, spk, noise, steps, gt = O.synthetic_inputs(B, T, n_step_noises=n_noise, gt=k_step is not None)
             with inject_randn([noise] + steps):
                 if k_step is None:
@@ -90,6 +96,8 @@ def main():
         # single denoiser evaluations (lds_denoise parity): eps for fractional and integer timesteps
         for name, B, T, t in [("nfe_b2_t40_t999", 2, 40, 999.0), ("nfe_b1_t37_t417p25", 1, 37, 417.25),
                               ("nfe_b2_t64_t0", 2, 64, 0.0)]:
+            if os.path.exists(os.path.join(GOLDEN_DIR, name + ".npz")) and "--force" not in sys.argv:
+                continue
             units, spk, noise, _, _ = O.synthetic_inputs(B, T)
             cond = (model.unit_embed(units) + model.spk_embed(spk - 1)).transpose(1, 2)
             inp = torch.cat([noise[:, 0], cond], dim=-2)

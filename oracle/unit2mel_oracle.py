@@ -367,6 +367,56 @@ def sample_ddpm(eps_fn_int, buf: Dict[str, Tensor], x: Tensor, k_step: int, nois
     return x
 
 
+def sample_ddim(eps_fn_int, buf: Dict[str, Tensor], x: Tensor, t_total: int, interval: int) -> Tensor:
+    """DDIM (eta = 0) over t = reversed(range(0, t_total, interval))  (diffusion.py:123-132,317-332).
+    Note a_prev = alphas_cumprod[max(t - interval, 0)]: the last step lands on alphas_cumprod[0], not on 1."""
+    b = x.shape[0]
+    acp = buf["alphas_cumprod"].to(x.device)
+    for i in reversed(range(0, t_total, interval)):
+        t = torch.full((b,), i, device=x.device, dtype=torch.long)
+        a_t = acp.gather(-1, t).reshape(b, 1, 1, 1)
+        a_prev = acp.gather(-1, torch.max(t - interval, torch.zeros_like(t))).reshape(b, 1, 1, 1)
+        eps = eps_fn_int(x, t)
+        x = a_prev.sqrt() * (x / a_t.sqrt() + (((1 - a_prev) / a_prev).sqrt() - ((1 - a_t) / a_t).sqrt()) * eps)
+    return x
+
+
+def sample_pndm(eps_fn_int, buf: Dict[str, Tensor], x: Tensor, t_total: int, interval: int) -> Tensor:
+    """PLMS / PNDM (diffusion.py:134-167,300-316): Adams-Bashforth combination of up to four noise predictions, the
+    first step bootstrapped with a second evaluation at t - interval.  The reference evaluates
+    ``max(t - interval, 0)`` on a [B] tensor (diffusion.py:155), which only works for B == 1; the restatement applies
+    the same element-wise maximum for any B (identical for B == 1)."""
+    b = x.shape[0]
+    acp = buf["alphas_cumprod"].to(x.device)
+    hist: list = []                                    # deque(maxlen=4) of the reference; only the last 3 are read
+
+    def x_pred(x, noise_t, t):
+        a_t = acp.gather(-1, t).reshape(b, 1, 1, 1)
+        a_prev = acp.gather(-1, torch.max(t - interval, torch.zeros_like(t))).reshape(b, 1, 1, 1)
+        a_t_sq, a_prev_sq = a_t.sqrt(), a_prev.sqrt()
+        x_delta = (a_prev - a_t) * ((1 / (a_t_sq * (a_t_sq + a_prev_sq))) * x - 1 / (
+            a_t_sq * (((1 - a_prev) * a_t).sqrt() + ((1 - a_t) * a_prev).sqrt())) * noise_t)
+        return x + x_delta
+
+    for i in reversed(range(0, t_total, interval)):
+        t = torch.full((b,), i, device=x.device, dtype=torch.long)
+        e = eps_fn_int(x, t)
+        if len(hist) == 0:
+            xp = x_pred(x, e, t)
+            e_prev = eps_fn_int(xp, torch.max(t - interval, torch.zeros_like(t)))
+            e_prime = (e + e_prev) / 2
+        elif len(hist) == 1:
+            e_prime = (3 * e - hist[-1]) / 2
+        elif len(hist) == 2:
+            e_prime = (23 * e - 16 * hist[-1] + 5 * hist[-2]) / 12
+        else:
+            e_prime = (55 * e - 59 * hist[-1] + 37 * hist[-2] - 9 * hist[-3]) / 24
+        x = x_pred(x, e_prime, t)
+        hist.append(e)
+        hist = hist[-4:]
+    return x
+
+
 def q_sample(buf, x_start, t_index: int, noise):
     """diffusion.py:169-171 at a single integer t for the whole batch."""
     return buf["sqrt_alphas_cumprod"][t_index].to(x_start.device) * x_start + \
@@ -420,6 +470,9 @@ def unit2mel_infer(sd: Dict[str, Tensor], cfg: dict, units: Tensor, spk_id: Opti
             x = sample_dpm_solver_pp(eps_fn, betas, x, steps)
         elif method == "unipc":
             x = sample_unipc_bh2(eps_fn, betas, x, steps)
+        elif method in ("ddim", "pndm"):
+            bb = buf if calc != torch.float64 else {k: v.double() for k, v in buf.items()}
+            x = (sample_ddim if method == "ddim" else sample_pndm)(eps_fn, bb, x, t_total, infer_speedup)
         else:
             raise NotImplementedError(method)
     else:

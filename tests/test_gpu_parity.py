@@ -90,7 +90,8 @@ def test_sampler_vs_reference_golden(name, precision, host_model, state_dict):
     assert e["max_abs"] <= TOL_VS_REF_FP32, (e, floor)
 
 
-@pytest.mark.parametrize("name", ["dpm20_b2_t40", "unipc10_b2_t37", "shallow_dpm20_b2_t32", "ddpm12_b2_t24"])
+@pytest.mark.parametrize("name", ["dpm20_b2_t40", "unipc10_b2_t37", "shallow_dpm20_b2_t32", "ddpm12_b2_t24", "ddim20_b2_t40",
+                                  "pndm20_b1_t40"])
 def test_sampler_bf16_mode(name, host_model, state_dict):
     """bf16 GEMM operands (tcgen05), fp32 accumulation / norms / solver: relative L2 <= 1e-2 vs the fp64 oracle."""
     gpu_model = gpu_model_for(host_model, "bf16")
@@ -136,4 +137,36 @@ def test_oracle_on_gpu_agrees_at_10s_length(gpu_model, state_dict):
         ref64 = O.unit2mel_infer(sd64, O.DEFAULT_CFG, units.cuda().double(), spk.cuda(), noise.cuda().double(), "dpm-solver", 50).cpu()
     e = G.errs(mel, ref64)
     G.report(test="dpm20_T861_vs_fp64_gpu_oracle", **e)
+    assert e["max_abs"] <= TOL_VS_FP64, e
+
+
+def test_pndm_batch_of_two_vs_fp64_oracle(gpu_model, state_dict):
+    """The reference's PLMS loop only runs for B == 1 (diffusion.py:155 applies Python max() to a [B] tensor); the CUDA
+    path takes any B.  B=2 against the fp64 oracle (element-wise max, identical for B == 1), and utterance 1 against
+    the same utterance run alone (bit-exact)."""
+    B, T = 2, 40
+    units, spk, noise, _, _ = O.synthetic_inputs(B, T)
+    mel = _run_cuda(gpu_model, units, spk, noise, [], None, "pndm", 100, None)
+    with torch.no_grad():
+        ref64 = O.unit2mel_infer(state_dict, O.DEFAULT_CFG, units, spk, noise, "pndm", 100, dtype=torch.float64)
+    e = G.errs(mel, ref64)
+    G.report(test="pndm10_b2_vs_fp64", **e)
+    assert e["max_abs"] <= TOL_VS_FP64, e
+    alone = _run_cuda(gpu_model, units[1:2], spk[1:2], noise[1:2], [], None, "pndm", 100, None)
+    assert torch.equal(mel[1:2], alone)
+
+
+def test_long_sequence_shallow_diffusion_T2584(gpu_model, state_dict):
+    """BASELINE configs[3] shape (30 s = 2584 frames, shallow diffusion k_step=100 from a noised mel) on B=2 utterances,
+    DPM-Solver++ 10 NFE, against the fp64 oracle executed on the same GPU (checker only)."""
+    B, T = 2, 2584
+    units, spk, noise, _, gt = O.synthetic_inputs(B, T, gt=True)
+    mel = _run_cuda(gpu_model, units, spk, noise, [], gt, "dpm-solver", 10, 100)
+    sd64 = {k: v.double().cuda() for k, v in state_dict.items()}
+    with torch.no_grad():
+        ref64 = O.unit2mel_infer(sd64, O.DEFAULT_CFG, units.cuda().double(), spk.cuda(), noise.cuda().double(), "dpm-solver", 10,
+                                 gt_spec=gt.cuda().double(), k_step=100).cpu()
+    e = G.errs(mel, ref64)
+    G.report(test="shallow_dpm10_T2584_vs_fp64_gpu_oracle", **e)
+    assert mel.shape == (B, T, 128) and torch.isfinite(mel).all()
     assert e["max_abs"] <= TOL_VS_FP64, e

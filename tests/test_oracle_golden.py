@@ -7,7 +7,7 @@ from conftest import golden_names, load_golden
 from oracle import unit2mel_oracle as O
 
 CASES = [n for n in golden_names() if not n.startswith("nfe_")]
-FAST = ["dpm8_b1_t24", "unipc10_b2_t37", "ddpm12_b2_t24", "shallow_dpm20_b2_t32"]
+FAST = ["dpm8_b1_t24", "unipc10_b2_t37", "ddpm12_b2_t24", "shallow_dpm20_b2_t32", "shallow_ddim10_b2_t37", "shallow_pndm10_b1_t37"]
 
 
 @pytest.mark.parametrize("name", FAST)

@@ -23,7 +23,7 @@ def inject(noises):
 
 
 @pytest.mark.skipif(not reference_available(), reason="reference tree not present")
-@pytest.mark.parametrize("method,speedup", [("dpm-solver", 100), ("unipc", 200)])
+@pytest.mark.parametrize("method,speedup", [("dpm-solver", 100), ("unipc", 200), ("ddim", 100), ("pndm", 100)])
 def test_oracle_equals_live_reference(method, speedup):
     ref = import_reference()
     torch.manual_seed(1234)

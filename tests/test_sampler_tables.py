@@ -91,6 +91,60 @@ def test_ddpm_program_matches_oracle():
     assert rows[-1, 4] == 0.0 and t_in[-1] == 0.0
 
 
+def emulate_ddim(t_in, rows, x):
+    """csrc/solver.cu ddim_step_kernel: x = c2 * (x / c0 + c1 * eps)."""
+    f = lambda v: torch.tensor(float(v), dtype=torch.float32)
+    B = x.shape[0]
+    for j in range(rows.shape[0]):
+        eps = toy_eps(x, t_in[j].expand(B))
+        x = f(rows[j, 2]) * (x / f(rows[j, 0]) + f(rows[j, 1]) * eps)
+    return x
+
+
+def emulate_pndm(t_in, rows, x):
+    """lds_api.cu PNDM branch + csrc/solver.cu pndm_update_kernel (modes 0..4, ring of noise predictions)."""
+    f = lambda v: torch.tensor(float(v), dtype=torch.float32)
+    B = x.shape[0]
+    upd = lambda xx, ep, r: xx + f(r[0]) * (f(r[1]) * xx - f(r[2]) * ep)
+    hist = []
+    for k in range(rows.shape[0]):
+        r = rows[k]
+        e = toy_eps(x, t_in[0 if k == 0 else k + 1].expand(B))
+        if k == 0:
+            xp = upd(x, e, r)
+            e2 = toy_eps(xp, t_in[1].expand(B))
+            ep = (e + e2) / 2.0
+        elif k == 1:
+            ep = (3.0 * e - hist[-1]) / 2.0
+        elif k == 2:
+            ep = ((23.0 * e - 16.0 * hist[-1]) + 5.0 * hist[-2]) / 12.0
+        else:
+            ep = (((55.0 * e - 59.0 * hist[-1]) + 37.0 * hist[-2]) - 9.0 * hist[-3]) / 24.0
+        x = upd(x, ep, r)
+        hist = (hist + [e])[-3:]
+    return x
+
+
+@pytest.mark.parametrize("method,t_total,interval", [("ddim", 1000, 50), ("ddim", 1000, 30), ("ddim", 100, 10), ("ddim", 1000, 500),
+                                                     ("pndm", 1000, 50), ("pndm", 1000, 30), ("pndm", 100, 10), ("pndm", 1000, 500),
+                                                     ("pndm", 100, 100)])
+def test_ddim_pndm_program_matches_oracle(method, t_total, interval):
+    torch.manual_seed(2)
+    buf = O.diffusion_buffers()
+    x = torch.randn(2, 1, 8, 12)
+    steps = len(range(0, t_total, interval))
+    eps_int = lambda xx, t: toy_eps(xx, t.float())
+    if method == "ddim":
+        t_in, rows = st.ddim_program(buf["alphas_cumprod"], t_total, interval)
+        assert rows.shape == (steps, st.COEF_STRIDE) and t_in.shape == (steps,)
+        got, want = emulate_ddim(t_in, rows, x.clone()), O.sample_ddim(eps_int, buf, x.clone(), t_total, interval)
+    else:
+        t_in, rows = st.pndm_program(buf["alphas_cumprod"], t_total, interval)
+        assert rows.shape == (steps, st.COEF_STRIDE) and t_in.shape == (steps + 1,)
+        got, want = emulate_pndm(t_in, rows, x.clone()), O.sample_pndm(eps_int, buf, x.clone(), t_total, interval)
+    assert torch.equal(got, want), float((got - want).abs().max())
+
+
 def test_timestep_sinusoid_matches_oracle():
     t = torch.tensor([0.0, 1.0, 417.25, 999.0, 998.001])
     assert torch.equal(st.timestep_sinusoid(t, 256), O.timestep_sinusoid(t, 256))
