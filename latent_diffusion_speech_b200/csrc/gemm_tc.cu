@@ -6,33 +6,42 @@
 //     hi+mid+lo == x to 24 bits) and the six significant plane products (lo*hi, hi*lo, mid*mid, mid*hi, hi*mid,
 //     hi*hi) are accumulated in fp32, which recovers fp32-level accuracy on the tensor pipe at 6 MMAs per K slice.
 //
-// Structure (B200, sm_100a), v3.  Measured on B200: one tcgen05.mma M128 x K16 costs ~92 cycles for any N <= 128 but
-// 96 / 128 cycles at N = 192 / 256 (tests/micro/bench_umma.cu), so only N >= 192 instructions run the pipe at its rate;
-// and the main loop is bound by the TMA / L2 -> SM fill path: ~51 B/clk/SM with 128-byte box rows (v1: 128x128 tiles,
-// one A and one W tile per plane product = 128 B/clk needed), half of that with 64-byte rows (v2).  Hence:
-//   * CTA tile 128 (M) x BN (N), BN = 256 / 192 / 128 chosen per GEMM so that N % BN == 0; one persistent CTA per SM,
-//     tiles strided over the grid with the N tiles of one row block adjacent (A rows stay hot in L2).
+// Structure (B200, sm_100a), v4.  Measured on B200 (tests/micro/bench_umma.cu, tests/gpu_gemm_bench.py, ncu captures
+// under profiles/): one tcgen05.mma M128 x K16 costs ~92 cycles for any N <= 128 but 96 / 128 cycles at N = 192 / 256,
+// so only N >= 192 instructions run the pipe at its rate; and the main loop is bound by the bytes the L2 can DELIVER
+// to one SM (~40 B/clk/SM; TMA multicast between two CTAs does not lower it, keeping a smaller share of W per SM does).
+// Hence:
+//   * CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2): the pair computes a 256 (M) x BN (N) tile, each CTA holding
+//     its own 128 accumulator rows in TMEM, its own A tile and HALF of the W tile in shared memory; rank 0 issues every
+//     MMA for both SMs.  BN = 256 / 192 / 128 chosen per GEMM so that N % BN == 0.  Pairs are persistent, items
+//     (M-tile pair, N tile) strided over the clusters with the N tiles of one row block adjacent (A rows stay hot in L2).
+//     An odd M tile count leaves one ghost tile (TMA zero fill, no stores).
 //   * K blocks of 64 bf16 (128-byte rows, 128B swizzle).  Operand tiles live in TWO shared-memory rings — A slots of
-//     16 KB, W slots of BN x 128 B — filled by the producer in the order the MMA warp needs them and released tile by
-//     tile, so that a plane tile is loaded once per K block and reused by every product that needs it:
+//     16 KB, W slots of BN/2 x 128 B — filled by each CTA's producer in the order the MMA warp needs them and released
+//     tile by tile, so that a plane tile is loaded once per K block and reused by every product that needs it:
 //       pass 1 (split mode), per K block: loads A_lo W_hi A_mid W_mid A_hi W_lo, products lo*hi, mid*hi, mid*mid,
 //                            hi*mid, hi*lo (6 tiles per 5 products instead of 10);
 //       pass 2, per K block: loads A_hi W_hi, product hi*hi (the only product in bf16 mode).
-//     The small products of the whole K range are accumulated before any hi*hi term, exactly as in v1: the tensor
-//     pipe's fp32 accumulate truncates, so accumulation steps taken while the accumulator is still small cost nothing.
+//     The small products of the whole K range are accumulated before any hi*hi term: the tensor pipe's fp32
+//     accumulate truncates, so accumulation steps taken while the accumulator is still small cost nothing.
+//   * Barriers: "full" barriers live in the leader and count the TMA bytes of BOTH CTAs (the peer's loads complete on
+//     the leader's barrier, cp.async.bulk.tensor.cta_group::2); "empty" and "accumulator full" barriers exist in both
+//     CTAs and are signalled by the leader's multicast tcgen05.commit; "accumulator empty" lives in the leader and
+//     collects one relaxed remote arrive per epilogue warp of both CTAs.
 //   * The accumulator (BN fp32 columns) is double-buffered in TMEM (2 x 256 of the 512 columns): the epilogue of
 //     tile i overlaps the main loop of tile i+1.
 //   warp 0      TMA producer  — cp.async.bulk.tensor (3-D map over [channels, frames, utterances] for A so that the
 //                               three taps of a k=3 convolution are three shifted loads of the same tensor and the
 //                               zero padding is TMA out-of-bounds fill; 2-D map for W), mbarrier tx counts
-//   warp 1      MMA issuer    — tcgen05.alloc, one elected lane issues tcgen05.mma.cta_group::1 and tcgen05.commit to
+//   warp 1      MMA issuer    — tcgen05.alloc (cta_group::2), one elected lane of the leader issues tcgen05.mma and tcgen05.commit to
 //                               release smem stages / publish an accumulator buffer
 //   warps 2..9  epilogue      — tcgen05.ld 32x32b (one accumulator row per thread, two warps per TMEM lane quarter
-//                               splitting the columns), + bias, SiLU / GEGLU, + fp32 residual, store fp32 / bf16 /
+//                               interleaving the 32-column chunks), + bias, SiLU / GEGLU, + fp32 residual, store fp32 / bf16 /
 //                               3-plane split bf16 / attention operands
 // Reference ops replaced: F.conv1d (lora.py:102), nn.Linear (attention_processor.py:1012-1040,
 // attention.py:291,247), GEGLU (attention.py:299-301), residual adds (resnet.py:639, attention.py:161-201).
 #include <cuda.h>
+#include <cstdlib>
 
 #include <mutex>
 #include <unordered_map>
@@ -43,14 +52,15 @@
 namespace lds {
 namespace {
 
-constexpr int TBM = 128, TBK = 64, TC_THREADS = 320, N_EPI_THREADS = 256;
+constexpr int TBM = 128, TBK = 64, N_EPI_WARPS = 8, TC_THREADS = 64 + 32 * N_EPI_WARPS;
+constexpr int EPI_PARTS = N_EPI_WARPS / 4;          // epilogue warps per TMEM lane quarter: they interleave the 32-column chunks
 constexpr int A_SLOT_BYTES = TBM * TBK * 2;         // 16 KB: 128 rows x 128 B
 constexpr int MAX_SLOTS = 8;                        // per ring
 constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;    // two accumulator buffers
 constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;
 
 struct TcParams {
-  int rows, batches, tiles_per_batch, n_tiles, total_tiles;   // A: [batches][rows][parts*cin]
+  int rows, batches, tiles_per_batch, m_tiles, n_tiles, total_items;   // A: [batches][rows][parts*cin]; item = (M-tile group, N tile)
   int cin, taps, pad, parts;
   int BN, na, nw, w_slot_bytes;         // ring depths (A slots, W slots)
   int nkb, kb_per_tap;                  // K blocks of TBK per plane (all taps) / per tap
@@ -58,7 +68,7 @@ struct TcParams {
   const float* bias;
   const float* R; int r_ld, r_div;
   void* C; int c_ld; int out_kind;      // 0 fp32, 1 bf16, 2 split bf16 (3 planes of c_ld/3 columns), 3 attention operands
-  int epilogue;
+  int epilogue, dbg;
   __nv_bfloat16 *q_out, *k_out, *vt_out; int att_T, att_H, att_dpad, att_Tpad;
 };
 
@@ -67,13 +77,8 @@ using namespace ptx;
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// store 32 consecutive fp32 values of one output row in the requested representation
-__device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int col, int n_out, const float* v) {
+// store 32 consecutive fp32 values of one output row in the requested representation (v is clobbered by the split)
+__device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int col, int n_out, float* v) {
   if (p.out_kind == 0) {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + row * p.c_ld + col);
 #pragma unroll
@@ -82,24 +87,16 @@ __device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int c
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.c_ld + col);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      dst[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                          pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+      dst[i] = make_uint4(pack_pair_bf16(v[8 * i], v[8 * i + 1]), pack_pair_bf16(v[8 * i + 2], v[8 * i + 3]),
+                          pack_pair_bf16(v[8 * i + 4], v[8 * i + 5]), pack_pair_bf16(v[8 * i + 6], v[8 * i + 7]));
   } else {
-    float r[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = v[i];
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.c_ld + col;
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
       uint4* dst = reinterpret_cast<uint4*>(base + (size_t)pl * n_out);
       uint32_t w[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const __nv_bfloat16 a = __float2bfloat16_rn(r[2 * i]), b = __float2bfloat16_rn(r[2 * i + 1]);
-        r[2 * i] -= __bfloat162float(a);
-        r[2 * i + 1] -= __bfloat162float(b);
-        w[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-      }
+      for (int i = 0; i < 16; ++i) w[i] = pl == 2 ? pack_pair_bf16(v[2 * i], v[2 * i + 1]) : split_pair_bf16(v[2 * i], v[2 * i + 1]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
     }
@@ -107,23 +104,15 @@ __device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int c
 }
 
 // out_kind 3: 32 consecutive columns of the fused [q | k | v] projection (one head, one of q/k/v) as attention operands
-__device__ __forceinline__ void store_qkv32(const TcParams& p, size_t row, int col, const float* v) {
+__device__ __forceinline__ void store_qkv32(const TcParams& p, size_t row, int col, float* v) {
   const int parts = p.parts, HD = p.att_H * p.att_dpad;
   const int region = col / HD, rem = col - region * HD;
-  float r[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) r[i] = v[i];
   if (region < 2) {
     __nv_bfloat16* base = (region == 0 ? p.q_out : p.k_out) + row * (size_t)(parts * HD) + rem;
     for (int pl = 0; pl < parts; ++pl) {
       uint32_t w[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const __nv_bfloat16 a = __float2bfloat16_rn(r[2 * i]), b = __float2bfloat16_rn(r[2 * i + 1]);
-        r[2 * i] -= __bfloat162float(a);
-        r[2 * i + 1] -= __bfloat162float(b);
-        w[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-      }
+      for (int i = 0; i < 16; ++i) w[i] = pl == parts - 1 ? pack_pair_bf16(v[2 * i], v[2 * i + 1]) : split_pair_bf16(v[2 * i], v[2 * i + 1]);
       uint4* dst = reinterpret_cast<uint4*>(base + (size_t)pl * HD);
 #pragma unroll
       for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
@@ -134,23 +123,33 @@ __device__ __forceinline__ void store_qkv32(const TcParams& p, size_t row, int c
     for (int pl = 0; pl < parts; ++pl) {
       __nv_bfloat16* dst = p.vt_out + ((size_t)((bb * parts + pl) * p.att_H + hh) * p.att_dpad + j0) * p.att_Tpad + tt;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {          // lanes hold consecutive frames: each store is a coalesced 64 B row segment
-        const __nv_bfloat16 a = __float2bfloat16_rn(r[i]);
-        r[i] -= __bfloat162float(a);
-        dst[(size_t)i * p.att_Tpad] = a;
+      for (int i = 0; i < 32; i += 2) {        // lanes hold consecutive frames: each store is a coalesced 64 B row segment
+        const uint32_t w = pl == parts - 1 ? pack_pair_bf16(v[i], v[i + 1]) : split_pair_bf16(v[i], v[i + 1]);
+        dst[(size_t)i * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w & 0xffffu));
+        dst[(size_t)(i + 1) * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w >> 16));
       }
     }
   }
 }
 
-// Epilogue of one accumulator row (this thread's TMEM lane) over this thread's half of the BN columns [n0, n0+BN):
-// + bias, SiLU / GEGLU, + fp32 residual, store in the requested representation.  trow = TMEM address of column n0.
-__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, int n0, size_t grow, bool valid, int half) {
-  const float* rrow = p.R ? p.R + (grow / p.r_div) * p.r_ld : nullptr;
+// Residual of one 32-column chunk of this thread's row (8 x 16 B).
+struct Res32 { float4 q[8]; };
+__device__ __forceinline__ void load_res32(const float* rrow, int col, Res32& r) {
+  const float4* r4 = reinterpret_cast<const float4*>(rrow + col);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.q[i] = __ldg(r4 + i);
+}
+
+// Epilogue of one accumulator row (this thread's TMEM lane) over this thread's share of the BN columns [n0, n0+BN)
+// (32-column chunks part, part + EPI_PARTS, ...): + bias, SiLU / GEGLU, + fp32 residual, store in the requested
+// representation.  trow = TMEM address of column n0.  The residual chunk is requested right after the TMEM load so
+// that both latencies overlap.
+__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, int n0, size_t grow, bool valid, int part,
+                                             const float* rrow) {
   if (p.epilogue == EPI_GEGLU) {          // 128-column groups of [64 value | 64 gate]
-    const int n_out = p.N >> 1, upt = p.BN >> 7;   // (group, 32-column chunk) units per thread
+    const int n_out = p.N >> 1, units = p.BN >> 6;   // (group, 32-column chunk) units of the tile
 #pragma unroll 1
-    for (int u = half * upt; u < (half + 1) * upt; ++u) {
+    for (int u = part; u < units; u += EPI_PARTS) {
       const int grp = u >> 1, c = u & 1;
       float v[32], g[32];
       tmem_ld32(trow + grp * 128 + c * 32, v);
@@ -171,12 +170,19 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, i
       }
     }
   } else {
-    const int cpt = p.BN >> 6;            // 32-column chunks per thread
+    const int chunks = p.BN >> 5;
 #pragma unroll 1
-    for (int c = half * cpt; c < (half + 1) * cpt; ++c) {
-      float v[32];
-      tmem_ld32(trow + c * 32, v);
+    for (int c = part; c < chunks; c += EPI_PARTS) {
       const int col = n0 + c * 32;
+      uint32_t raw[32];
+      tmem_ld32_issue(trow + c * 32, raw);
+      Res32 r;
+      const bool res = rrow && valid;
+      if (res) load_res32(rrow, col, r);
+      tmem_ld32_wait(raw);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
       if (p.bias) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
@@ -186,12 +192,10 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, i
         for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
       }
       if (valid) {
-        if (rrow) {
-          const float4* r4 = reinterpret_cast<const float4*>(rrow + col);
+        if (res) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 q = r4[i];
-            v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            v[4 * i] += r.q[i].x; v[4 * i + 1] += r.q[i].y; v[4 * i + 2] += r.q[i].z; v[4 * i + 3] += r.q[i].w;
           }
         }
         if (p.out_kind == 3) store_qkv32(p, grow, col, v);
@@ -219,6 +223,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (4 * MAX_SLOTS + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (leader) issues every MMA for both SMs.  full barriers live in the leader and count the bytes
+  // of both CTAs' loads; empty / tmem_full barriers exist in both CTAs and are signalled by the leader's multicast
+  // commits; tmem_empty lives in the leader and collects one arrive per epilogue warp of both CTAs.
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&mapA);
@@ -226,14 +236,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int s = 0; s < 4 * MAX_SLOTS; ++s) mbar_init(bar_base + 8u * s, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), N_EPI_THREADS);
+      mbar_init(tmem_empty_bar(b), 2 * N_EPI_WARPS);
     }
     mbar_fence_init();
   } else if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();                                // the peer's barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -243,20 +254,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int sa = 0, sw = 0;                        // next slot of each ring
       uint32_t pha = 0, phw = 0;
+      const int w_row = (int)crank * (p.BN >> 1);
       auto load_a = [&](int col, int row, int b) {
         mbar_wait(a_empty(sa), pha ^ 1u);
-        mbar_expect_tx(a_full(sa), A_SLOT_BYTES);
-        tma_load_3d(a_ring + sa * A_SLOT_BYTES, &mapA, a_full(sa), col, row, b);
+        if (leader) mbar_expect_tx(a_full(sa), 2 * A_SLOT_BYTES);
+        tma_load_3d_pair(a_ring + sa * A_SLOT_BYTES, &mapA, mapa_u32(a_full(sa), 0), col, row, b);
         if (++sa == p.na) { sa = 0; pha ^= 1u; }
       };
       auto load_w = [&](int col, int n0) {
         mbar_wait(w_empty(sw), phw ^ 1u);
-        mbar_expect_tx(w_full(sw), p.w_slot_bytes);
-        tma_load_2d(w_ring + sw * p.w_slot_bytes, &mapW, w_full(sw), col, n0);
+        if (leader) mbar_expect_tx(w_full(sw), 2 * p.w_slot_bytes);
+        tma_load_2d_pair(w_ring + sw * p.w_slot_bytes, &mapW, mapa_u32(w_full(sw), 0), col, n0 + w_row);
         if (++sw == p.nw) { sw = 0; phw ^= 1u; }
       };
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      for (int item = cid; item < p.total_items; item += ncl) {
+        const int nt = item % p.n_tiles, mt = (item / p.n_tiles) * 2 + (int)crank;
         const int b = mt / p.tiles_per_batch;
         const int t0 = (mt - b * p.tiles_per_batch) * TBM;
         const int n0 = nt * p.BN;
@@ -280,16 +292,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TBM, p.BN);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(2 * TBM, p.BN);
       int sa = 0, sw = 0;                        // oldest live slot of each ring
       uint32_t pha = 0, phw = 0;
       int local = 0;
       auto next_a = [&]() { if (++sa == p.na) { sa = 0; pha ^= 1u; } };
       auto next_w = [&]() { if (++sw == p.nw) { sw = 0; phw ^= 1u; } };
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      for (int item = cid; item < p.total_items; item += ncl, ++local) {
         const int buf = local & 1;
-        mbar_wait(tmem_empty_bar(buf), (((uint32_t)local >> 1) & 1u) ^ 1u);   // the epilogue has drained this buffer
+        mbar_wait(tmem_empty_bar(buf), (((uint32_t)local >> 1) & 1u) ^ 1u);   // both epilogues have drained this buffer
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * ACC_STRIDE;
         uint32_t accumulate = 0;
@@ -298,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint64_t wd = umma_desc_kmajor(w_ring + w_slot * p.w_slot_bytes, 128);
 #pragma unroll
           for (int k = 0; k < TBK / 16; ++k) {   // +32 B (16 bf16) along K inside the swizzle atom per UMMA_K step
-            umma_bf16(acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc, accumulate);
+            umma_bf16_pair(acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc, accumulate);
             accumulate = 1;
           }
         };
@@ -309,32 +321,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(w_full(w_hi), phw);
           tc_fence_after();
           product(a_lo, w_hi);                   // lo * hi
-          umma_commit(a_empty(a_lo));
+          umma_commit_pair(a_empty(a_lo), 3);
           next_a();
           const int a_mid = sa;
           mbar_wait(a_full(a_mid), pha);
           tc_fence_after();
           product(a_mid, w_hi);                  // mid * hi
-          umma_commit(w_empty(w_hi));
+          umma_commit_pair(w_empty(w_hi), 3);
           next_w();
           const int w_mid = sw;
           mbar_wait(w_full(w_mid), phw);
           tc_fence_after();
           product(a_mid, w_mid);                 // mid * mid
-          umma_commit(a_empty(a_mid));
+          umma_commit_pair(a_empty(a_mid), 3);
           next_a();
           const int a_hi = sa;
           mbar_wait(a_full(a_hi), pha);
           tc_fence_after();
           product(a_hi, w_mid);                  // hi * mid
-          umma_commit(w_empty(w_mid));
+          umma_commit_pair(w_empty(w_mid), 3);
           next_w();
           const int w_lo = sw;
           mbar_wait(w_full(w_lo), phw);
           tc_fence_after();
           product(a_hi, w_lo);                   // hi * lo
-          umma_commit(a_empty(a_hi));
-          umma_commit(w_empty(w_lo));
+          umma_commit_pair(a_empty(a_hi), 3);
+          umma_commit_pair(w_empty(w_lo), 3);
           next_a();
           next_w();
         }
@@ -343,38 +355,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(w_full(sw), phw);
           tc_fence_after();
           product(sa, sw);                       // hi * hi
-          umma_commit(a_empty(sa));
-          umma_commit(w_empty(sw));
+          umma_commit_pair(a_empty(sa), 3);
+          umma_commit_pair(w_empty(sw), 3);
           next_a();
           next_w();
         }
-        umma_commit(tmem_full_bar(buf));
+        umma_commit_pair(tmem_full_bar(buf), 3);
       }
     }
   } else {
-    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps of a quarter split the columns ----
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); the EPI_PARTS warps of a quarter interleave the chunks ----
+    const int quarter = warp & 3, part = (warp - 2) >> 2;
     const int r_in_tile = quarter * 32 + lane;
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+    for (int item = cid; item < p.total_items; item += ncl, ++local) {
+      const int nt = item % p.n_tiles, mt = (item / p.n_tiles) * 2 + (int)crank;
       const int b = mt / p.tiles_per_batch;
       const int t = (mt - b * p.tiles_per_batch) * TBM + r_in_tile;
-      const bool valid = t < p.rows;
+      const bool valid = t < p.rows && mt < p.m_tiles;   // the last pair may carry a ghost M tile (TMA zero fill, no stores)
       const size_t grow = (size_t)b * p.rows + (valid ? t : 0);
       const int buf = local & 1;
+      const float* rrow = p.R ? p.R + (grow / p.r_div) * p.r_ld : nullptr;
       mbar_wait(tmem_full_bar(buf), ((uint32_t)local >> 1) & 1u);
       tc_fence_after();
-      epilogue_row(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, grow, valid, half);
+      if (!(p.dbg & 2))
+        epilogue_row(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, grow, valid && !(p.dbg & 1), part, rrow);
       tc_fence_before();
-      mbar_arrive(tmem_empty_bar(buf));
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(buf), 0));
     }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();                                // no CTA exits (or frees TMEM) while the pair still works on it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -456,6 +472,27 @@ int sm_count() {
   return n;
 }
 
+// co-resident clusters of two persistent CTAs (GPC boundaries can strand an SM; asked from the occupancy calculator)
+int max_clusters2() {
+  static int n = 0;
+  if (!n) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * sm_count());
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = 227 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int v = 0;
+    if (cudaOccupancyMaxActiveClusters(&v, gemm_tc_kernel, &cfg) != cudaSuccess || v < 1) v = sm_count() / 2;
+    (void)cudaGetLastError();
+    n = v;
+  }
+  return n;
+}
+
 }  // namespace
 
 // generic bf16 tiled tensor map (rank 2 or 3) with a 32/64/128-byte swizzle and zero out-of-bounds fill
@@ -493,27 +530,40 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   }
   TcParams p;
   p.BN = a.N % 256 == 0 ? 256 : ((a.N % 192 == 0 && a.epilogue != EPI_GEGLU) ? 192 : 128);   // GEGLU groups are 128 wide
-  p.w_slot_bytes = p.BN * TBK * 2;
-  p.na = p.BN == 256 ? 4 : 5;
+  p.w_slot_bytes = (p.BN / 2) * TBK * 2;          // each CTA of the pair holds half of the W tile
+  p.na = 6;
   p.nw = (SMEM_BUDGET - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
   if (p.nw > MAX_SLOTS) p.nw = MAX_SLOTS;
   CUtensorMap mA, mW;
   cudaError_t e = get_map(a.A, (uint64_t)a.a_parts * a.cin, (uint64_t)a.rows, (uint64_t)a.batches, TBM, &mA);
   if (e != cudaSuccess) return e;
-  e = get_map(a.W, (uint64_t)a.taps * a.w_parts * a.cin, (uint64_t)a.N, 0, (uint32_t)p.BN, &mW);
+  p.m_tiles = ((a.rows + TBM - 1) / TBM) * a.batches;
+  const int csize = 2;                            // always a CTA pair; an odd M tile count leaves one ghost tile
+  e = get_map(a.W, (uint64_t)a.taps * a.w_parts * a.cin, (uint64_t)a.N, 0, (uint32_t)(p.BN / csize), &mW);
   if (e != cudaSuccess) return e;
   p.rows = a.rows; p.batches = a.batches; p.tiles_per_batch = (a.rows + TBM - 1) / TBM;
-  p.n_tiles = a.N / p.BN; p.total_tiles = p.n_tiles * p.tiles_per_batch * a.batches;
+  p.n_tiles = a.N / p.BN; p.total_items = p.n_tiles * ((p.m_tiles + csize - 1) / csize);
   p.cin = a.cin; p.taps = a.taps; p.pad = a.taps == 3 ? 1 : 0; p.parts = a.a_parts;
   p.kb_per_tap = a.cin / TBK; p.nkb = a.taps * p.kb_per_tap;
   p.N = a.N; p.bias = a.bias; p.R = a.R; p.r_ld = a.r_ld; p.r_div = a.r_div;
   p.C = a.C; p.c_ld = a.c_ld; p.out_kind = a.out_kind; p.epilogue = a.epilogue;
+  { static const int dbg = getenv("LDS_TC_DEBUG") ? atoi(getenv("LDS_TC_DEBUG")) : 0; p.dbg = dbg; }
   p.q_out = a.q_out; p.k_out = a.k_out; p.vt_out = a.vt_out;
   p.att_T = a.att_T; p.att_H = a.att_H; p.att_dpad = a.att_dpad; p.att_Tpad = a.att_Tpad;
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + 8 * (4 * MAX_SLOTS + 4) + 16;
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(mA, mW, p);
-  return cudaGetLastError();
+  const int max_cl = max_clusters2();
+  const int ncl = p.total_items < max_cl ? p.total_items : max_cl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ncl * csize);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel, mA, mW, p);
 }
 
 }  // namespace lds
