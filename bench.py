@@ -37,6 +37,12 @@ WORKLOADS = {
     "dpm20_b64_t864_ffma": (64, 864, "dpm-solver", 50, None, "fp32_ffma"),  # CUDA-core fp32 implementation (A/B)
     "dpm20_b64_t864_bf16": (64, 864, "dpm-solver", 50, None, "bf16"),
     "unipc10_b64_t864_bf16": (64, 864, "unipc", 100, None, "bf16"),        # per-GPU shard of BASELINE configs[2]
+    "shallow_dpm20_b32_t2584_bf16": (32, 2584, "dpm-solver", 5, 100, "bf16"),   # per-GPU shard of BASELINE configs[3]
+    "shallow_dpm20_b32_t2584_fp32": (32, 2584, "dpm-solver", 5, 100, "fp32"),
+    "ddpm1000_b32_t864_fp32": (32, 864, None, 1, None, "fp32"),            # BASELINE configs[4]: 1000-step ancestral sampling
+    "ddpm1000_b32_t864_bf16": (32, 864, None, 1, None, "bf16"),
+    "ddim20_b64_t864_fp32": (64, 864, "ddim", 50, None, "fp32"),
+    "pndm20_b64_t864_fp32": (64, 864, "pndm", 50, None, "fp32"),
 }
 HEADLINE = "dpm20_b64_t864_fp32"
 CPU_SAMPLE = dict(B=1, T=864)      # bounded CPU sample of the same workload (one utterance of the batch)
@@ -164,7 +170,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, T, method, speedup, k_step, precision = WORKLOADS[args.workload]
-    nfe = 1000 // speedup
+    t_total = k_step if k_step is not None else 1000
+    nfe = t_total // speedup + (1 if method == "pndm" else 0)
 
     torch.manual_seed(1234)
     model = Unit2Mel(1280, 323, 128, 2, [256, 384, 512, 512], 8, 256, 1.0).eval().to(dev)
@@ -177,15 +184,20 @@ def run_ours(args):
     noise = torch.randn(B, 1, 128, T, generator=gn, device=dev)
     units_d, spk_d = units_h.to(dev), spk_h.to(dev)
     eng = model._get_engine(dev)
+    gt_h = (torch.rand(B, T, 128, generator=g) * 14 - 12).pin_memory() if k_step is not None else None   # shallow diffusion start
+    gt_d = None if gt_h is None else gt_h.to(dev)
 
     def step_resident():
-        mel = model(units_d, None, spk_id=spk_d, infer=True, infer_speedup=speedup, method=method, noise=noise)
+        mel = model(units_d, None, spk_id=spk_d, gt_spec=gt_d, k_step=k_step, infer=True, infer_speedup=speedup, method=method,
+                    noise=noise)
         return gather_mels(mel, B * world) if world > 1 else mel
 
     def step_e2e():
         u = units_h.to(dev, non_blocking=True)
         s = spk_h.to(dev, non_blocking=True)
-        mel = model(u, None, spk_id=s, infer=True, infer_speedup=speedup, method=method)   # noise: torch.randn on device, as the reference
+        gt = None if gt_h is None else gt_h.to(dev, non_blocking=True)
+        # noise: torch.randn on the device, as the reference draws it
+        mel = model(u, None, spk_id=s, gt_spec=gt, k_step=k_step, infer=True, infer_speedup=speedup, method=method)
         mel = gather_mels(mel, B * world) if world > 1 else mel
         return mel.to("cpu", non_blocking=False)
 
@@ -262,7 +274,8 @@ def run_ours(args):
     line = None
     if rank == 0:
         cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
+        # bounded CPU sample of the same workload; the 1000-step and shallow workloads would take minutes per utterance
+        if world == 1 and not args.no_cpu_baseline and method is not None and k_step is None:
             cores = os.cpu_count() or 1
             once = cpu_oracle_run(CPU_SAMPLE["B"], T, method, speedup, cores)
             sec = once()
@@ -276,7 +289,8 @@ def run_ours(args):
                        "global_batch": B * world, "precision_mode": precision, "l2_policy": "inputs_exceed_l2 (units 283 MB/step, activations >1 GB)",
                        "parallelism": f"batch-shard x{world}, final NCCL all_gather" if world > 1 else "single GPU"},
             "rtf": (ms_step * 1e-3) / (frames / FRAME_RATE),
-            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(units_h.numel() * 4 + spk_h.numel() * 8),
+            "e2e": {"value": e2e_val, "unit": "frames/s",
+                    "h2d_bytes_per_step": int(units_h.numel() * 4 + spk_h.numel() * 8 + (0 if gt_h is None else gt_h.numel() * 4)),
                     "d2h_bytes_per_step": int(B * world * T * 128 * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,

@@ -36,8 +36,9 @@
 //   warp 1      MMA issuer    — tcgen05.alloc (cta_group::2), one elected lane of the leader issues tcgen05.mma and tcgen05.commit to
 //                               release smem stages / publish an accumulator buffer
 //   warps 2..9  epilogue      — tcgen05.ld 32x32b (one accumulator row per thread, two warps per TMEM lane quarter
-//                               interleaving the 32-column chunks), + bias, SiLU / GEGLU, + fp32 residual, store fp32 / bf16 /
-//                               3-plane split bf16 / attention operands
+//                               interleaving the 32-column chunks), + bias, SiLU / GEGLU, transpose through a per-warp
+//                               shared-memory tile, + fp32 residual, coalesced stores: fp32 / bf16 / 3-plane split bf16 /
+//                               attention operands
 // Reference ops replaced: F.conv1d (lora.py:102), nn.Linear (attention_processor.py:1012-1040,
 // attention.py:291,247), GEGLU (attention.py:299-301), residual adds (resnet.py:639, attention.py:161-201).
 #include <cuda.h>
@@ -57,7 +58,8 @@ constexpr int EPI_PARTS = N_EPI_WARPS / 4;          // epilogue warps per TMEM l
 constexpr int A_SLOT_BYTES = TBM * TBK * 2;         // 16 KB: 128 rows x 128 B
 constexpr int MAX_SLOTS = 8;                        // per ring
 constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;    // two accumulator buffers
-constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;
+constexpr int STAGE_BYTES = 32 * 32 * 4;              // per epilogue warp
+constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 512;    // rings + per-warp staging tiles (split mode)
 
 struct TcParams {
   int rows, batches, tiles_per_batch, m_tiles, n_tiles, total_items;   // A: [batches][rows][parts*cin]; item = (M-tile group, N tile)
@@ -77,7 +79,7 @@ using namespace ptx;
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
-// store 32 consecutive fp32 values of one output row in the requested representation (v is clobbered by the split)
+// Direct path (bf16 mode): store 32 consecutive fp32 values of one output row in the requested representation (v is clobbered by the split)
 __device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int col, int n_out, float* v) {
   if (p.out_kind == 0) {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + row * p.c_ld + col);
@@ -103,82 +105,196 @@ __device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int c
   }
 }
 
-// out_kind 3: 32 consecutive columns of the fused [q | k | v] projection (one head, one of q/k/v) as attention operands
-__device__ __forceinline__ void store_qkv32(const TcParams& p, size_t row, int col, float* v) {
-  const int parts = p.parts, HD = p.att_H * p.att_dpad;
-  const int region = col / HD, rem = col - region * HD;
-  if (region < 2) {
-    __nv_bfloat16* base = (region == 0 ? p.q_out : p.k_out) + row * (size_t)(parts * HD) + rem;
-    for (int pl = 0; pl < parts; ++pl) {
-      uint32_t w[16];
+// ---- epilogue -------------------------------------------------------------------------------------------------------
+// tcgen05.ld hands every thread ONE accumulator row (TMEM lane), so a direct store makes each warp instruction touch 32
+// different rows with 16 bytes each — half-written sectors that cost the L2 as much as full ones, on the same SM <-> L2
+// path the main loop is bound by.  Each epilogue warp therefore transposes its 32 x 32 block through a private 4 KB
+// shared-memory tile (16-byte chunks XOR-swizzled by the row: conflict-free in both directions) and writes it back
+// with 8 lanes per row: full 128-byte lines of C (fp32), full sectors of the bf16 planes, and the residual is read the
+// same way.  V^T of a fused QKV projection (keys contiguous) reads the tile by columns instead.
+struct EpiCtx {
+  float* stage;           // this warp's [32][32] fp32 tile
+  int lane;
+  size_t grow0;           // global row of tile row 0 of this warp's block (b * rows + t)
+  int nvalid;             // rows of the block that exist (0..32)
+};
+
+__device__ __forceinline__ void stage_write(const EpiCtx& e, const float* v) {
+  float4* row = reinterpret_cast<float4*>(e.stage + e.lane * 32);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = pl == parts - 1 ? pack_pair_bf16(v[2 * i], v[2 * i + 1]) : split_pair_bf16(v[2 * i], v[2 * i + 1]);
-      uint4* dst = reinterpret_cast<uint4*>(base + (size_t)pl * HD);
+  for (int j = 0; j < 8; ++j) row[j ^ (e.lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+}
+
+// Residual of this lane's eight 16-byte positions of a 32 x 32 block, requested before the accumulator is waited for so
+// that its latency hides behind the TMEM load and the activation math.  Two lane layouts:
+//   WIDE = false (fp32 output): lane -> columns [4j, 4j+4), j = lane & 7, rows it*4 + (lane >> 3), it = 0..7
+//   WIDE = true  (bf16 outputs): lane -> columns [8j, 8j+8), j = lane & 3, rows it*8 + (lane >> 2), it = 0..3  (two per row)
+struct Res8 { float4 q[8]; };
+template <bool WIDE>
+__device__ __forceinline__ void load_res8(const TcParams& p, const EpiCtx& e, int col, Res8& r) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  for (int i = 0; i < 8; ++i) {
+    const int rr = WIDE ? (i >> 1) * 8 + (e.lane >> 2) : i * 4 + (e.lane >> 3);
+    const int c4 = col + (WIDE ? 8 * (e.lane & 3) + 4 * (i & 1) : 4 * (e.lane & 7));
+    r.q[i] = rr < e.nvalid ? __ldg(reinterpret_cast<const float4*>(p.R + ((e.grow0 + rr) / p.r_div) * p.r_ld + c4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// fp32 output: every instruction writes four full 128-byte lines of C
+__device__ __forceinline__ void stage_store_f32(const TcParams& p, const EpiCtx& e, int col, const Res8& res) {
+  const int j = e.lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (e.lane >> 3);
+    if (rr >= e.nvalid) continue;
+    float4 x = reinterpret_cast<const float4*>(e.stage + rr * 32)[j ^ (rr & 7)];
+    if (p.R) { x.x += res.q[it].x; x.y += res.q[it].y; x.z += res.q[it].z; x.w += res.q[it].w; }
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (e.grow0 + rr) * p.c_ld + col + 4 * j) = x;
+  }
+}
+
+// bf16 outputs (plain, 3-plane split, q / k attention operands): 16-byte stores, every instruction writes eight rows x
+// 64 bytes (two full sectors each) per plane
+__device__ __forceinline__ void stage_store_bf16(const TcParams& p, const EpiCtx& e, int col, int n_out, int q_region, const Res8& res) {
+  const int j = e.lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (e.lane >> 2);
+    if (rr >= e.nvalid) continue;
+    const float4* srow = reinterpret_cast<const float4*>(e.stage + rr * 32);
+    float4 a = srow[(2 * j) ^ (rr & 7)], b = srow[(2 * j + 1) ^ (rr & 7)];
+    if (p.R) {
+      const float4 ra = res.q[2 * it], rb = res.q[2 * it + 1];
+      a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
+      b.x += rb.x; b.y += rb.y; b.z += rb.z; b.w += rb.w;
     }
-  } else {
-    const int bb = (int)(row / p.att_T), tt = (int)(row - (size_t)bb * p.att_T);
-    const int hh = rem / p.att_dpad, j0 = rem - hh * p.att_dpad;
+    const size_t row = e.grow0 + rr;
+    const int c8 = col + 8 * j;
+    __nv_bfloat16* base;
+    int parts, pstride;
+    if (p.out_kind == 1) {
+      base = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.c_ld + c8; parts = 1; pstride = 0;
+    } else if (p.out_kind == 2) {
+      base = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.c_ld + c8; parts = 3; pstride = n_out;
+    } else {                              // q / k operands of the attention kernel: planes [row][parts][H*dpad]
+      const int HD = p.att_H * p.att_dpad;
+      base = (q_region == 0 ? p.q_out : p.k_out) + row * (size_t)(p.parts * HD) + (c8 - q_region * HD); parts = p.parts; pstride = HD;
+    }
     for (int pl = 0; pl < parts; ++pl) {
-      __nv_bfloat16* dst = p.vt_out + ((size_t)((bb * parts + pl) * p.att_H + hh) * p.att_dpad + j0) * p.att_Tpad + tt;
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {        // lanes hold consecutive frames: each store is a coalesced 64 B row segment
-        const uint32_t w = pl == parts - 1 ? pack_pair_bf16(v[i], v[i + 1]) : split_pair_bf16(v[i], v[i + 1]);
-        dst[(size_t)i * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w & 0xffffu));
-        dst[(size_t)(i + 1) * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w >> 16));
+      uint4 w;
+      if (pl == parts - 1) {
+        w = make_uint4(pack_pair_bf16(a.x, a.y), pack_pair_bf16(a.z, a.w), pack_pair_bf16(b.x, b.y), pack_pair_bf16(b.z, b.w));
+      } else {
+        w.x = split_pair_bf16(a.x, a.y); w.y = split_pair_bf16(a.z, a.w);
+        w.z = split_pair_bf16(b.x, b.y); w.w = split_pair_bf16(b.z, b.w);
       }
+      *reinterpret_cast<uint4*>(base + (size_t)pl * pstride) = w;
     }
   }
 }
 
-// Residual of one 32-column chunk of this thread's row (8 x 16 B).
-struct Res32 { float4 q[8]; };
-__device__ __forceinline__ void load_res32(const float* rrow, int col, Res32& r) {
-  const float4* r4 = reinterpret_cast<const float4*>(rrow + col);
+// q / k operands straight from the registers (direct path): planes [row][parts][H*dpad]
+__device__ __forceinline__ void store_qk32(const TcParams& p, size_t row, int col, int region, float* v) {
+  const int HD = p.att_H * p.att_dpad;
+  __nv_bfloat16* base = (region == 0 ? p.q_out : p.k_out) + row * (size_t)(p.parts * HD) + (col - region * HD);
+  for (int pl = 0; pl < p.parts; ++pl) {
+    uint32_t w[16];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r.q[i] = __ldg(r4 + i);
+    for (int i = 0; i < 16; ++i) w[i] = pl == p.parts - 1 ? pack_pair_bf16(v[2 * i], v[2 * i + 1]) : split_pair_bf16(v[2 * i], v[2 * i + 1]);
+    uint4* dst = reinterpret_cast<uint4*>(base + (size_t)pl * HD);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
 }
 
-// Epilogue of one accumulator row (this thread's TMEM lane) over this thread's share of the BN columns [n0, n0+BN)
-// (32-column chunks part, part + EPI_PARTS, ...): + bias, SiLU / GEGLU, + fp32 residual, store in the requested
-// representation.  trow = TMEM address of column n0.  The residual chunk is requested right after the TMEM load so
-// that both latencies overlap.
-__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, int n0, size_t grow, bool valid, int part,
-                                             const float* rrow) {
+// V^T of a fused QKV projection (planes [B][parts][H][dpad][T_pad], frames contiguous): written straight from the
+// accumulator registers — lanes hold consecutive frames, so every store instruction is one fully written 64-byte segment.
+__device__ __forceinline__ void store_vt32(const TcParams& p, size_t row, int col, float* v) {
+  const int HD = p.att_H * p.att_dpad, rem = col - 2 * HD;
+  const int bb = (int)(row / p.att_T), tt = (int)(row - (size_t)bb * p.att_T);
+  const int hh = rem / p.att_dpad, j0 = rem - hh * p.att_dpad;
+  for (int pl = 0; pl < p.parts; ++pl) {
+    __nv_bfloat16* dst = p.vt_out + ((size_t)((bb * p.parts + pl) * p.att_H + hh) * p.att_dpad + j0) * p.att_Tpad + tt;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const uint32_t w = pl == p.parts - 1 ? pack_pair_bf16(v[i], v[i + 1]) : split_pair_bf16(v[i], v[i + 1]);
+      dst[(size_t)i * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w & 0xffffu));
+      dst[(size_t)(i + 1) * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w >> 16));
+    }
+  }
+}
+
+// Epilogue of this warp's 32 accumulator rows over its share of the BN columns [n0, n0+BN) (32-column chunks part,
+// part + EPI_PARTS, ...): + bias, SiLU / GEGLU, + fp32 residual, store in the requested representation.
+// trow = TMEM address of column n0 of this thread's lane.
+template <bool STAGED>
+__device__ __forceinline__ void epilogue_block(const TcParams& p, uint32_t trow, int n0, const EpiCtx& e, int part, bool skip_store) {
+  // Split mode: the main loop is bound by the SM <-> L2 path, so the coalesced (staged) stores pay.  bf16 mode: main
+  // loops are short and the epilogue sits on the critical path, so the lowest-latency direct stores win (measured
+  // in situ: staged -2 % / +10 % step time in split / bf16 mode).
+  constexpr bool staged = STAGED;
+  const bool row_ok = e.lane < e.nvalid;
+  const size_t grow = e.grow0 + (row_ok ? e.lane : 0);
+  const float* rrow = p.R ? p.R + (grow / p.r_div) * p.r_ld : nullptr;
   if (p.epilogue == EPI_GEGLU) {          // 128-column groups of [64 value | 64 gate]
     const int n_out = p.N >> 1, units = p.BN >> 6;   // (group, 32-column chunk) units of the tile
 #pragma unroll 1
     for (int u = part; u < units; u += EPI_PARTS) {
       const int grp = u >> 1, c = u & 1;
+      const int col_v = n0 + grp * 128 + c * 32, col_g = col_v + 64, oc = ((n0 + grp * 128) >> 1) + c * 32;
       float v[32], g[32];
       tmem_ld32(trow + grp * 128 + c * 32, v);
       tmem_ld32(trow + grp * 128 + 64 + c * 32, g);
-      const int col_v = n0 + grp * 128 + c * 32, col_g = col_v + 64, oc = ((n0 + grp * 128) >> 1) + c * 32;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float a = v[i], gg = g[i];
         if (p.bias) { a += __ldg(p.bias + col_v + i); gg += __ldg(p.bias + col_g + i); }
         v[i] = a * gelu_erf(gg);
       }
-      if (valid) {
-        if (rrow) {
+      if (!staged) {
+        if (!skip_store && row_ok) {
+          if (rrow) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += rrow[oc + i];
+            for (int i = 0; i < 32; ++i) v[i] += rrow[oc + i];
+          }
+          store_row32(p, grow, oc, n_out, v);
         }
-        store_row32(p, grow, oc, n_out, v);
+        continue;
       }
+      stage_write(e, v);
+      if (!skip_store) {
+        Res8 res;
+        if (p.out_kind == 0) {
+          if (p.R) load_res8<false>(p, e, oc, res);
+          stage_store_f32(p, e, oc, res);
+        } else {
+          if (p.R) load_res8<true>(p, e, oc, res);
+          stage_store_bf16(p, e, oc, n_out, 0, res);
+        }
+      }
+      __syncwarp();
     }
   } else {
     const int chunks = p.BN >> 5;
+    const int HD = p.att_H * p.att_dpad;
 #pragma unroll 1
     for (int c = part; c < chunks; c += EPI_PARTS) {
       const int col = n0 + c * 32;
+      const int region = p.out_kind == 3 ? col / HD : 0;
       uint32_t raw[32];
       tmem_ld32_issue(trow + c * 32, raw);
-      Res32 r;
-      const bool res = rrow && valid;
-      if (res) load_res32(rrow, col, r);
+      Res8 res;
+      if (p.R && region != 2) {
+        if (!staged) {                      // direct path: this lane's own row, 8 x 16 B
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res.q[i] = __ldg(reinterpret_cast<const float4*>(rrow + col) + i);
+          }
+        } else if (p.out_kind == 0) load_res8<false>(p, e, col, res);
+        else load_res8<true>(p, e, col, res);
+      }
       tmem_ld32_wait(raw);
       float v[32];
 #pragma unroll
@@ -191,20 +307,34 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t trow, i
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
       }
-      if (valid) {
-        if (res) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[4 * i] += r.q[i].x; v[4 * i + 1] += r.q[i].y; v[4 * i + 2] += r.q[i].z; v[4 * i + 3] += r.q[i].w;
-          }
-        }
-        if (p.out_kind == 3) store_qkv32(p, grow, col, v);
-        else store_row32(p, grow, col, p.N, v);
+      if (region == 2) {                  // V^T: straight from the registers
+        if (!skip_store && e.lane < e.nvalid) store_vt32(p, e.grow0 + e.lane, col, v);
+        continue;
       }
+      if (!staged) {
+        if (!skip_store && row_ok) {
+          if (p.R) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i] += res.q[i].x; v[4 * i + 1] += res.q[i].y; v[4 * i + 2] += res.q[i].z; v[4 * i + 3] += res.q[i].w;
+            }
+          }
+          if (p.out_kind == 3) store_qk32(p, grow, col, region, v);
+          else store_row32(p, grow, col, p.N, v);
+        }
+        continue;
+      }
+      stage_write(e, v);
+      if (!skip_store) {
+        if (p.out_kind == 0) stage_store_f32(p, e, col, res);
+        else stage_store_bf16(p, e, col, p.N, region, res);
+      }
+      __syncwarp();
     }
   }
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -215,6 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t ring_bytes = p.na * A_SLOT_BYTES + p.nw * p.w_slot_bytes;
   const uint32_t bar_base = base + ring_bytes;    // a_full[8], a_empty[8], w_full[8], w_empty[8], tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ring_bytes + 8 * (4 * MAX_SLOTS + 4));
+  float* stage_base = reinterpret_cast<float*>(smem + ring_bytes + 512);   // barriers + TMEM slot occupy < 512 B
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (MAX_SLOTS + s); };
   auto w_full = [&](int s) { return bar_base + 8u * (2 * MAX_SLOTS + s); };
@@ -366,20 +497,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); the EPI_PARTS warps of a quarter interleave the chunks ----
     const int quarter = warp & 3, part = (warp - 2) >> 2;
-    const int r_in_tile = quarter * 32 + lane;
+    EpiCtx e;
+    e.stage = stage_base + (warp - 2) * (STAGE_BYTES / 4);
+    e.lane = lane;
     int local = 0;
     for (int item = cid; item < p.total_items; item += ncl, ++local) {
       const int nt = item % p.n_tiles, mt = (item / p.n_tiles) * 2 + (int)crank;
       const int b = mt / p.tiles_per_batch;
-      const int t = (mt - b * p.tiles_per_batch) * TBM + r_in_tile;
-      const bool valid = t < p.rows && mt < p.m_tiles;   // the last pair may carry a ghost M tile (TMA zero fill, no stores)
-      const size_t grow = (size_t)b * p.rows + (valid ? t : 0);
+      const int t_blk = (mt - b * p.tiles_per_batch) * TBM + quarter * 32;     // first frame of this warp's 32 rows
+      // the last pair may carry a ghost M tile (TMA zero fill, no stores)
+      e.nvalid = mt < p.m_tiles ? max(0, min(32, p.rows - t_blk)) : 0;
+      e.grow0 = (size_t)(mt < p.m_tiles ? b : 0) * p.rows + t_blk;
       const int buf = local & 1;
-      const float* rrow = p.R ? p.R + (grow / p.r_div) * p.r_ld : nullptr;
       mbar_wait(tmem_full_bar(buf), ((uint32_t)local >> 1) & 1u);
       tc_fence_after();
       if (!(p.dbg & 2))
-        epilogue_row(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, grow, valid && !(p.dbg & 1), part, rrow);
+        epilogue_block<STAGED>(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, e, part, (p.dbg & 1) != 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(buf), 0));
@@ -486,7 +619,7 @@ int max_clusters2() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int v = 0;
-    if (cudaOccupancyMaxActiveClusters(&v, gemm_tc_kernel, &cfg) != cudaSuccess || v < 1) v = sm_count() / 2;
+    if (cudaOccupancyMaxActiveClusters(&v, gemm_tc_kernel<true>, &cfg) != cudaSuccess || v < 1) v = sm_count() / 2;
     (void)cudaGetLastError();
     n = v;
   }
@@ -524,7 +657,9 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
     return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -532,7 +667,8 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   p.BN = a.N % 256 == 0 ? 256 : ((a.N % 192 == 0 && a.epilogue != EPI_GEGLU) ? 192 : 128);   // GEGLU groups are 128 wide
   p.w_slot_bytes = (p.BN / 2) * TBK * 2;          // each CTA of the pair holds half of the W tile
   p.na = 6;
-  p.nw = (SMEM_BUDGET - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
+  const int stage_bytes = split ? N_EPI_WARPS * STAGE_BYTES : 0;
+  p.nw = (SMEM_BUDGET - stage_bytes - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
   if (p.nw > MAX_SLOTS) p.nw = MAX_SLOTS;
   CUtensorMap mA, mW;
   cudaError_t e = get_map(a.A, (uint64_t)a.a_parts * a.cin, (uint64_t)a.rows, (uint64_t)a.batches, TBM, &mA);
@@ -550,7 +686,7 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   { static const int dbg = getenv("LDS_TC_DEBUG") ? atoi(getenv("LDS_TC_DEBUG")) : 0; p.dbg = dbg; }
   p.q_out = a.q_out; p.k_out = a.k_out; p.vt_out = a.vt_out;
   p.att_T = a.att_T; p.att_H = a.att_H; p.att_dpad = a.att_dpad; p.att_Tpad = a.att_Tpad;
-  const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + 8 * (4 * MAX_SLOTS + 4) + 16;
+  const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + 512 + stage_bytes;
   const int max_cl = max_clusters2();
   const int ncl = p.total_items < max_cl ? p.total_items : max_cl;
   cudaLaunchConfig_t cfg = {};
@@ -563,7 +699,7 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel, mA, mW, p);
+  return split ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, mA, mW, p) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, mA, mW, p);
 }
 
 }  // namespace lds

@@ -110,19 +110,21 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int c1, const floa
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
-// grid (nchunk, B); block = (C/4) * rpar threads (as gn_stats): thread (v, r) owns channel quad v — its gamma / beta /
-// scale / shift live in registers — and frames r, r+rpar, ... of the [GN_ROWS, C] slab, four loads in flight.
-__global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2,
-                                                        int c2, int T, int groups, int rpar, const float* __restrict__ part,
+// grid (ceil(T / slab), B); block = (C/4) * rpar threads: thread (v, r) owns channel quad v — its gamma / beta / scale /
+// shift live in registers — and frames r, r+rpar, ... of the [slab, C] slab, eight 16-byte loads in flight per thread
+// (bytes in flight per SM, not instruction issue, is what bounds this kernel).  The host picks slab = 32 frames when
+// that still yields several waves of blocks and 16 on the small U-Net levels.
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2,
+                                                        int c2, int T, int groups, int rpar, int nchunk, int slab, const float* __restrict__ part,
                                                         float eps, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ ss,
                                                         int silu, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
                                                         int parts, __nv_bfloat16* __restrict__ rawb) {
   __shared__ float s_mean[32], s_rstd[32];
   const int C = c1 + c2, V = C >> 2, cg = C / groups;
-  const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int b = blockIdx.y, chunk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int g = warp; g < groups; g += nwarps) {   // merge the per-chunk partials of group g
+  for (int g = warp; g < groups; g += nwarps) {   // merge the per-chunk partials (nchunk statistics chunks) of group g
     const float* src = part + ((size_t)b * nchunk * groups + g) * 3;
     float n = 0.f, nm = 0.f;
     for (int c = lane; c < nchunk; c += 32) {
@@ -154,8 +156,8 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const float* __restrict_
     sc = __ldg(reinterpret_cast<const float4*>(ss + c));
     sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
   }
-  const int t0 = chunk * GN_ROWS, t1 = min(t0 + GN_ROWS, T);
-  constexpr int U = 4;
+  const int t0 = chunk * slab, t1 = min(t0 + slab, T);
+  constexpr int U = 8;
   for (int tb = t0 + r0; tb < t1; tb += rpar * U) {
     float4 xv[U];
 #pragma unroll
@@ -250,14 +252,16 @@ cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, in
                             const float* part, float eps, const float* gamma, const float* beta, const float* ss,
                             int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s) {
   const int C = c1 + c2;
-  if (C % (4 * groups) || c1 % 4 || groups > 32 || C / 4 > 1024) return cudaErrorInvalidValue;
+  if (C % (4 * groups) || c1 % 4 || groups > 32 || C / 4 > 256) return cudaErrorInvalidValue;
   const int V = C / 4;
   int rpar = 256 / V;
   if (rpar < 1) rpar = 1;
-  if (rpar > GN_ROWS) rpar = GN_ROWS;
+  const int slab = (int64_t)((T + 31) / 32) * B >= 4 * 148 ? 32 : 16;
+  if (rpar > slab) rpar = slab;
   const int threads = ((V * rpar + 31) / 32) * 32;
-  dim3 grid((T + GN_ROWS - 1) / GN_ROWS, B);
-  gn_apply_kernel<<<grid, threads, 0, s>>>(x1, c1, x2, c2, T, groups, rpar, part, eps, gamma, beta, ss, silu, y, yb, parts, rawb);
+  dim3 grid((T + slab - 1) / slab, B);
+  gn_apply_kernel<<<grid, threads, 0, s>>>(x1, c1, x2, c2, T, groups, rpar, (T + GN_ROWS - 1) / GN_ROWS, slab, part, eps, gamma, beta, ss,
+                                           silu, y, yb, parts, rawb);
   return cudaGetLastError();
 }
 

@@ -8,18 +8,21 @@
 
 namespace lds {
 
+// Packs (a, b) to bf16x2 with round-to-nearest and leaves the residuals a - bf16(a), b - bf16(b) in place: one
+// cvt.rn.bf16x2.f32 (full-rate F2FP) + two integer ops + two FADDs per pair instead of per-element F2F conversions.
+__device__ __forceinline__ uint32_t planes_split_pair(float& a, float& b) {
+  uint32_t w;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));   // low half <- a, high half <- b
+  a -= __uint_as_float(w << 16);
+  b -= __uint_as_float(w & 0xffff0000u);
+  return w;
+}
+
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* row, int c, int C, int parts, float v0, float v1, float v2, float v3) {
-  float r[4] = {v0, v1, v2, v3};
   for (int p = 0; p < parts; ++p) {
-    __nv_bfloat16 h[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __float2bfloat16_rn(r[j]);
-      r[j] -= __bfloat162float(h[j]);
-    }
     uint2 w;
-    w.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-    w.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    w.x = planes_split_pair(v0, v1);
+    w.y = planes_split_pair(v2, v3);
     *reinterpret_cast<uint2*>(row + (size_t)p * C + c) = w;
   }
 }

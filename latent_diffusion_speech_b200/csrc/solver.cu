@@ -207,20 +207,7 @@ __global__ void split_cast_kernel(const float4* __restrict__ in, __nv_bfloat16* 
     const int64_t row = i / V;
     const int c = (int)(i - row * V) * 4;
     const float4 q = in[i];
-    float r[4] = {q.x, q.y, q.z, q.w};
-    __nv_bfloat16* dst = out + row * (int64_t)(parts * C) + c;
-    for (int p = 0; p < parts; ++p) {
-      __nv_bfloat16 h[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        h[j] = __float2bfloat16_rn(r[j]);
-        r[j] -= __bfloat162float(h[j]);
-      }
-      uint2 w;
-      w.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-      w.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-      *reinterpret_cast<uint2*>(dst + (int64_t)p * C) = w;
-    }
+    store_planes4(out + row * (int64_t)(parts * C), c, C, parts, q.x, q.y, q.z, q.w);
   }
 }
 
