@@ -258,13 +258,20 @@ def run_ours(args):
     kern = {"fp32": "gemm_tc_kernel (tcgen05/TMEM/TMA implicit-GEMM conv k3 / 1x1 / linear, split-bf16 x6 products, fp32-accurate)",
             "bf16": "gemm_tc_kernel (tcgen05/TMEM/TMA implicit-GEMM conv k3 / 1x1 / linear, bf16 operands)",
             "fp32_ffma": "gemm_f32_kernel (implicit-GEMM conv k3 / 1x1 / linear, fp32 FFMA)"}[precision]
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")     # ncu dram bytes per gemm_tc launch (one capture per change)
+    if os.path.exists(tp) and precision in ("fp32", "bf16") and (B, T) == (64, 864):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj[precision]["traffic_bytes_per_launch"], tj["source"]
+    mma_per_product = 6.0 if precision == "fp32" else 1.0
     roofline = {
         "kernel": kern, "bound": "tensor",
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         "peak_source": f"{peaks['source']} bf16 dense sustained (MEASURED_PEAKS.json); achieved counts ALGORITHMIC (logical fp32) FLOPs - "
                        "the split mode issues 6 bf16 MMAs per logical product, so its tensor-pipe occupancy is 6x this fraction",
         "flops_per_launch": gm["flops"] / max(1, gm["launches"]), "avg_launch_ms": gm["ms"] / max(1, gm["launches"]),
-        "share_of_step": gm["ms"] / tot_ms, "traffic": None,
+        "share_of_step": gm["ms"] / tot_ms, "traffic": traffic, "traffic_source": traffic_src,
+        "tensor_pipe_frac": achieved_tf * mma_per_product / peak_tf if precision != "fp32_ffma" else None,
     }
     classes = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                    "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
