@@ -29,7 +29,7 @@ cudaError_t tc_make_map_bf16(const void* ptr, int rank, const uint64_t* dims, co
 namespace {
 using namespace ptx;
 
-constexpr int AQ = 128, AKV = 64, ATT_TC_THREADS = 320, NSOFT = 256;
+constexpr int AQ = 128, ATT_TC_THREADS = 320, NSOFT = 256;
 
 struct AttnTcParams {
   int T, H, d, C, parts, nk, nv, nsb, npb;   // ring depths: K, V^T tiles (smem), S (TMEM) and P (smem) buffers
@@ -196,13 +196,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const uint64_t q_hi = umma_desc_kmajor(q_s, SWZ), k_hi = umma_desc_kmajor(k_s, SWZ);
       const uint32_t hi_idesc = umma_idesc_bf16(AQ, AKV);
       mbar_wait(q_full, 0);
+      // S buffer of evaluation `it`: pass B rotates over the NSB buffers of the S region; pass A always has two buffers —
+      // with NSB == 1 the second one borrows the (still unused) O region — so that the hi*hi product of tile j+1 runs
+      // while the softmax threads still reduce tile j.  Barrier phases follow per-buffer use counters.
+      uint32_t su0 = 0u, su1 = 0u;
       auto issue_qk = [&](int it) {
-        const int ks = it % NK, sb = it % NSB;
+        const int ks = it % NK;
+        const int sb = it < nt ? (it & 1) : (it - nt) % NSB;
+        const uint32_t soff = it < nt ? (NSB == 1 ? (uint32_t)(sb * o_col) : (uint32_t)(sb * s_stride)) : (uint32_t)(sb * s_stride);
         mbar_wait(k_full(ks), (uint32_t)(it / NK) & 1u);
-        mbar_wait(s_free(sb), ((uint32_t)(it / NSB) & 1u) ^ 1u);   // the softmax threads have read the previous use of this S buffer
+        mbar_wait(s_free(sb), ((sb ? su1 : su0) & 1u) ^ 1u);   // the softmax threads have read the previous use of this S buffer
+        if (sb) ++su1; else ++su0;
         tc_fence_after();
         const uint64_t koff = (uint64_t)ks * k_stage_step;
-        const uint32_t soff = (uint32_t)(sb * s_stride);
         if (it < nt) {
           // pass A only needs the row maximum to ~1 %: hi*hi alone (any m close to the maximum gives the same softmax)
 #pragma unroll
@@ -257,14 +263,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     };
     float m = -INFINITY;
     // ---- pass A: row maximum of the scaled, masked scores ----
+    uint32_t su0 = 0u, su1 = 0u;                         // per-buffer use counters (same sequence as the MMA warp)
     for (int it = 0; it < nt; ++it) {
-      const int sb = it % NSB;
-      mbar_wait(s_full(sb), (uint32_t)(it / NSB) & 1u);
+      const int sb = it & 1;
+      const uint32_t soff = NSB == 1 ? (uint32_t)(sb * o_col) : (uint32_t)(sb * s_stride);
+      mbar_wait(s_full(sb), (sb ? su1 : su0) & 1u);
+      if (sb) ++su1; else ++su0;
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ++ch) {
         float s[32];
-        tmem_ld32(tmem0 + lane_off + sb * s_stride + c0 + ch * 32, s);   // hi*hi scores live in block 0
+        tmem_ld32(tmem0 + lane_off + soff + c0 + ch * 32, s);   // hi*hi scores live in block 0
         if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
         const int k0 = it * AKV + c0 + ch * 32;
         if (k0 + 32 <= p.T) {
@@ -286,8 +295,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     float l = 0.f;
     uint8_t* prow = p_ptr + (row >> 3) * 1024 + (row & 7) * 128;     // 8-row / 1024 B swizzle atoms, 128 B per row
     for (int jb = 0; jb < nt; ++jb) {
-      const int it = nt + jb, sb = it % NSB, pb = jb % NPB;
-      mbar_wait(s_full(sb), (uint32_t)(it / NSB) & 1u);
+      const int sb = jb % NSB, pb = jb % NPB;
+      mbar_wait(s_full(sb), (sb ? su1 : su0) & 1u);
+      if (sb) ++su1; else ++su0;
       tc_fence_after();
       uint32_t w[PARTS][16 * NCH];
 #pragma unroll

@@ -49,12 +49,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Phase 2: warp g merges the per-thread triples of group g with the count-weighted Chan formula.
 constexpr int GN_UNROLL = 8;
 __global__ void gn_stats_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2, int T,
-                                int groups, int rpar, float* __restrict__ part) {
+                                int groups, int rpar, int chunk_rows, float* __restrict__ part) {
   extern __shared__ float sh[];  // [nthreads][3]
   const int C = c1 + c2, V = C >> 2, cg = C / groups;
   const int v = threadIdx.x % V, r0 = threadIdx.x / V;
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const int t0 = chunk * GN_ROWS, t1 = min(t0 + GN_ROWS, T);
+  const int t0 = chunk * chunk_rows, t1 = min(t0 + chunk_rows, T);
   Wf acc{0.f, 0.f, 0.f};
   if (r0 < rpar) {
     for (int tb = t0 + r0; tb < t1; tb += rpar * GN_UNROLL) {
@@ -184,55 +184,73 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   }
 }
 
-// one warp per row; C <= 32*4*MAXV
-constexpr int LN_MAXV = 8;
+// One warp per LN_ROWS consecutive rows (C <= 32*4*LN_MAXV, LN_MAXV instantiated for C <= 256 / 384 / 512): all loads of the rows are issued before the first
+// reduction, so that LN_ROWS x C x 4 bytes per warp are in flight (bytes in flight, not issue, bound this kernel).
+constexpr int LN_ROWS = 4;
+template <int LN_MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int rows, int C,
                                                         float* __restrict__ y, __nv_bfloat16* __restrict__ yb, int parts) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int row0 = warp * LN_ROWS;
+  if (row0 >= rows) return;
   const int V = C >> 2;
-  const float4* src = reinterpret_cast<const float4*>(x + (size_t)warp * C);
-  float4 v[LN_MAXV];
-  float sum = 0.f;
+  float4 v[LN_ROWS][LN_MAXV];
+#pragma unroll
+  for (int r = 0; r < LN_ROWS; ++r) {
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)(row0 + r) * C);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < V && row0 + r < rows) v[r][i] = __ldg(src + q);
+    }
+  }
+  float4 g[LN_MAXV], be[LN_MAXV];
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) {
     const int q = lane + 32 * i;
     if (q < V) {
-      v[i] = __ldg(src + q);
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+      be[i] = __ldg(reinterpret_cast<const float4*>(beta) + q);
     }
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  const float mean = sum / (float)C;
-  float sq = 0.f;
+  for (int r = 0; r < LN_ROWS; ++r) {
+    if (row0 + r >= rows) break;
+    float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int q = lane + 32 * i;
-    if (q < V) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      sq += (a * a + b * b) + (c * c + d * d);
-    }
-  }
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (lane + 32 * i < V) sum += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    sum = warp_sum(sum);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-  const float rstd = rsqrtf(sq / (float)C + eps);
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (lane + 32 * i < V) {
+        const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    sq = warp_sum(sq);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+    const size_t row = (size_t)(row0 + r);
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int q = lane + 32 * i;
-    if (q < V) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
-      const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + q);
-      const float4 o = make_float4((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y,
-                                   (v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
-      if (yb) store_planes4(yb + (size_t)warp * (parts * C), q * 4, C, parts, o.x, o.y, o.z, o.w);
-      else reinterpret_cast<float4*>(y + (size_t)warp * C)[q] = o;
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < V) {
+        const float4 o = make_float4((v[r][i].x - mean) * rstd * g[i].x + be[i].x, (v[r][i].y - mean) * rstd * g[i].y + be[i].y,
+                                     (v[r][i].z - mean) * rstd * g[i].z + be[i].z, (v[r][i].w - mean) * rstd * g[i].w + be[i].w);
+        if (yb) store_planes4(yb + row * (parts * C), q * 4, C, parts, o.x, o.y, o.z, o.w);
+        else reinterpret_cast<float4*>(y + row * C)[q] = o;
+      }
     }
   }
 }
 
 }  // namespace
+
+// Frames per statistics chunk: 64 when that still gives several waves of blocks (the merge phase of a block is then
+// amortised over twice the loads), GN_ROWS = 32 on the small U-Net levels.  `part` is sized for 32-frame chunks.
+static int gn_chunk_rows(int B, int T) { return (int64_t)((T + 63) / 64) * B >= 4 * 148 ? 64 : GN_ROWS; }
 
 cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float* part,
                             cudaStream_t s) {
@@ -243,8 +261,9 @@ cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, in
   if (rpar < 1) rpar = 1;
   if (rpar > GN_ROWS) rpar = GN_ROWS;
   const int threads = ((V * rpar + 31) / 32) * 32;
-  dim3 grid((T + GN_ROWS - 1) / GN_ROWS, B);
-  gn_stats_kernel<<<grid, threads, threads * 3 * sizeof(float), s>>>(x1, c1, x2, c2, T, groups, rpar, part);
+  const int chunk_rows = gn_chunk_rows(B, T);
+  dim3 grid((T + chunk_rows - 1) / chunk_rows, B);
+  gn_stats_kernel<<<grid, threads, threads * 3 * sizeof(float), s>>>(x1, c1, x2, c2, T, groups, rpar, chunk_rows, part);
   return cudaGetLastError();
 }
 
@@ -260,17 +279,20 @@ cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, in
   if (rpar > slab) rpar = slab;
   const int threads = ((V * rpar + 31) / 32) * 32;
   dim3 grid((T + slab - 1) / slab, B);
-  gn_apply_kernel<<<grid, threads, 0, s>>>(x1, c1, x2, c2, T, groups, rpar, (T + GN_ROWS - 1) / GN_ROWS, slab, part, eps, gamma, beta, ss,
+  const int chunk_rows = gn_chunk_rows(B, T);
+  gn_apply_kernel<<<grid, threads, 0, s>>>(x1, c1, x2, c2, T, groups, rpar, (T + chunk_rows - 1) / chunk_rows, slab, part, eps, gamma, beta, ss,
                                            silu, y, yb, parts, rawb);
   return cudaGetLastError();
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
                              __nv_bfloat16* yb, int parts, cudaStream_t s) {
-  if (C % 4 || C > 128 * LN_MAXV) return cudaErrorInvalidValue;
-  const int warps_per_block = 8;
-  const int grid = (rows + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y, yb, parts);
+  if (C % 4 || C > 512) return cudaErrorInvalidValue;
+  const int warps_per_block = 8, rows_per_block = warps_per_block * LN_ROWS;
+  const int grid = (rows + rows_per_block - 1) / rows_per_block;
+  if (C <= 256) layernorm_kernel<2><<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y, yb, parts);
+  else if (C <= 384) layernorm_kernel<3><<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y, yb, parts);
+  else layernorm_kernel<4><<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y, yb, parts);
   return cudaGetLastError();
 }
 
