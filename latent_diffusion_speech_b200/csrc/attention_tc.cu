@@ -20,6 +20,7 @@
 #include "lds_kernels.h"
 #include "tc_ptx.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace lds {
 
@@ -424,8 +425,14 @@ cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
   //                        bf16: a third of that (two CTAs per SM, bounded by 2 x 256 TMEM columns)
   // shared memory per CTA (KB): Q + nk*K + nv*V^T + P
   if (a.parts == 3) {
-    // d <= 32: two CTAs per SM: 24 (Q) + 2*12 (K) + 12 (V^T) + 48 (P) = 108 KB, TMEM 128 (S) + 96 (O) per CTA
-    if (a.dpad == 32) return launch_attn<32, 64, 3, true>(a, 2, 1, 1, 1, s);
+    // d <= 32: two CTAs per SM: 24 (Q) + 2*12 (K) + 12 (V^T) + 48 (P) = 108 KB, TMEM 128 (S) + 96 (O) per CTA.
+    // LDS_ATT_PAIR=1 selects the CTA-pair kernel of attention_pair.cu instead — correct (same tests) but NOT faster:
+    // a cta_group::2 instruction occupies the tensor pipes of BOTH SMs for the same ~92 cycles, so the issue cost per
+    // query row and SM is unchanged (tests/micro/bench_umma.cu, 0.73 vs 0.68 ms per T=864 attention at B=64).
+    if (a.dpad == 32) {
+      static const bool pair = getenv("LDS_ATT_PAIR") && atoi(getenv("LDS_ATT_PAIR")) == 1;
+      return pair ? launch_attention_pair(a, s) : launch_attn<32, 64, 3, true>(a, 2, 1, 1, 1, s);
+    }
     if (a.dpad == 64) return launch_attn<64, 64, 3>(a, 2, 2, 1, 1, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
   } else {                                                             // bf16: S and P double-buffered, two CTAs per SM
     if (a.dpad == 32) return launch_attn<32, 64, 1>(a, 4, 3, 2, 2, s);    //  8 + 4*4 + 3*4 + 2*16 = 68, TMEM 2*64 (S) + 32 (O)

@@ -62,6 +62,8 @@ struct AttnTcArgs {
   int B = 0, T = 0, T_pad = 0, H = 0, d = 0, dpad = 0, parts = 1;
 };
 cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s);
+// CTA-pair (cta_group::2) variant for head dim <= 32 in split mode (attention_pair.cu); chosen by launch_attention_tc.
+cudaError_t launch_attention_pair(const AttnTcArgs& a, cudaStream_t s);
 inline void tc_set_split_pairs(TcGemmArgs& a) {   // lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
   static const int pa[6] = {2, 0, 1, 1, 0, 0}, pw[6] = {0, 2, 1, 0, 1, 0};
   a.a_parts = a.w_parts = 3; a.n_pairs = 6;

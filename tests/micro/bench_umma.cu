@@ -84,6 +84,49 @@ void run_ts(const char* name, int grid) {
   cudaFree(d);
 }
 
+
+// CTA pair: tcgen05.mma.cta_group::2 (M = 256 over two SMs), issued by the leader; cycles per instruction vs N.
+template <int N, int SWZ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) kpair(long long* out, int iters, int ksteps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw), base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar = base + 96 * 1024;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 96 * 1024 + 16);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) tmem_alloc_pair(smem_u32(slot), 256);
+  fence_async_smem();
+  tc_fence_before(); __syncthreads(); cluster_sync(); tc_fence_after();
+  const uint32_t tm = *slot;
+  if (threadIdx.x == 0 && cluster_ctarank() == 0) {
+    const uint64_t ad = umma_desc_kmajor(base, SWZ), bd = umma_desc_kmajor(base + 32 * 1024, SWZ);
+    const uint32_t idesc = umma_idesc_bf16(256, N);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i)
+      for (int ks = 0; ks < ksteps; ++ks) umma_bf16_pair(tm, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+    umma_commit_pair(bar, 1);
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads(); cluster_sync();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc_pair(tm, 256); }
+}
+
+template <int N, int SWZ>
+void run_pair(const char* name, int grid) {
+  long long* d; cudaMalloc(&d, 8);
+  const int iters = 2000, ksteps = SWZ / 32;
+  cudaFuncSetAttribute(kpair<N, SWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  kpair<N, SWZ><<<grid, 128, 100 * 1024>>>(d, iters, ksteps);
+  kpair<N, SWZ><<<grid, 128, 100 * 1024>>>(d, iters, ksteps);
+  long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaGetLastError();
+  printf("PAIR %-21s grid=%3d  %.1f cycles/MMA  (ideal math %d)  %s\n", name, grid, (double)h / (iters * ksteps), 256 * N / 512, cudaGetErrorString(e));
+  cudaFree(d);
+}
+
 template <int N, int SWZ, int NACC = 1>
 void run(const char* name, int grid) {
   long long* d; cudaMalloc(&d, 8);
@@ -117,6 +160,14 @@ int main() {
     run_ts<128, 128>("M128 N128 B:SW128", grid);
     run_ts<192, 128>("M128 N192 B:SW128", grid);
     run_ts<256, 128>("M128 N256 B:SW128", grid);
+    run_pair<32, 128>("M256 N32  SW128", 144);
+    run_pair<64, 128>("M256 N64  SW128", 144);
+    run_pair<64, 64>("M256 N64  SW64", 144);
+    run_pair<96, 128>("M256 N96  SW128", 144);
+    run_pair<128, 128>("M256 N128 SW128", 144);
+    run_pair<128, 64>("M256 N128 SW64", 144);
+    run_pair<192, 128>("M256 N192 SW128", 144);
+    run_pair<256, 128>("M256 N256 SW128", 144);
   }
   return 0;
 }
