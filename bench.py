@@ -34,6 +34,7 @@ WORKLOADS = {
     "dpm20_b8_t864_fp32": (8, 864, "dpm-solver", 50, None, "fp32"),
     "unipc10_b64_t864_fp32": (64, 864, "unipc", 100, None, "fp32"),
     "dpm20_b2_t216_fp32": (2, 216, "dpm-solver", 50, None, "fp32"),       # tiny, for plumbing checks
+    "dpm20_b1_t432_fp32": (1, 432, "dpm-solver", 50, None, "fp32"),       # BASELINE configs[0] shape (single 5 s utterance, latency)
     "dpm20_b64_t864_ffma": (64, 864, "dpm-solver", 50, None, "fp32_ffma"),  # CUDA-core fp32 implementation (A/B)
     "dpm20_b64_t864_bf16": (64, 864, "dpm-solver", 50, None, "bf16"),
     "unipc10_b64_t864_bf16": (64, 864, "unipc", 100, None, "bf16"),        # per-GPU shard of BASELINE configs[2]
