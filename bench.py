@@ -193,14 +193,19 @@ def run_ours(args):
                     noise=noise)
         return gather_mels(mel, B * world) if world > 1 else mel
 
+    # result landing zone in pinned host memory: rank 0 reads the gathered global mel, the other ranks their own shard
+    mel_h = torch.empty((B * world if rank == 0 else B), T, 128, dtype=torch.float32).pin_memory()
+
     def step_e2e():
         u = units_h.to(dev, non_blocking=True)
         s = spk_h.to(dev, non_blocking=True)
         gt = None if gt_h is None else gt_h.to(dev, non_blocking=True)
         # noise: torch.randn on the device, as the reference draws it
         mel = model(u, None, spk_id=s, gt_spec=gt, k_step=k_step, infer=True, infer_speedup=speedup, method=method)
-        mel = gather_mels(mel, B * world) if world > 1 else mel
-        return mel.to("cpu", non_blocking=False)
+        full = gather_mels(mel, B * world) if world > 1 else mel
+        mel_h.copy_(full if rank == 0 else mel, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return mel_h
 
     def barrier():
         if world > 1:

@@ -114,6 +114,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   float* red = reinterpret_cast<float*>(misc + 16);          // [2][128] exchange of row max / row sum between the halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
   const int nt = (p.T + AKV - 1) / AKV;
   const int HD = p.H * DPAD;
@@ -139,6 +140,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem0 = *tmem_slot;
   const uint32_t tmem_o = tmem0 + o_col;
+  pdl_wait();                                    // the set-up above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -413,8 +415,7 @@ cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, c
   p.scale = 1.0f / sqrtf((float)a.d);
   p.out = a.out;
   dim3 grid((a.T + AQ - 1) / AQ, a.H, a.B);
-  attention_tc_kernel<DPAD, AKV, PARTS, DUAL><<<grid, ATT_TC_THREADS, smem, s>>>(mQ, mK, mV, p);
-  return cudaGetLastError();
+  return launch_pdl(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, grid, dim3(ATT_TC_THREADS), smem, s, 1, mQ, mK, mV, p);
 }
 
 }  // namespace

@@ -371,6 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (4 * MAX_SLOTS + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();                                 // the next kernel may start launching behind our last wave
   // CTA pair: rank 0 (leader) issues every MMA for both SMs.  full barriers live in the leader and count the bytes
   // of both CTAs' loads; empty / tmem_full barriers exist in both CTAs and are signalled by the leader's multicast
   // commits; tmem_empty lives in the leader and collects one arrive per epilogue warp of both CTAs.
@@ -395,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   cluster_sync();                                // the peer's barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                    // everything above overlapped the previous kernel's tail; its data is needed from here on
 
   const int n1 = p.parts == 3 ? p.nkb : 0;       // pass-1 K blocks (split mode only)
 
@@ -706,17 +708,8 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + 512 + stage_bytes;
   const int max_cl = max_clusters2();
   const int ncl = p.total_items < max_cl ? p.total_items : max_cl;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ncl * csize);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return split ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, mA, mW, p) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, mA, mW, p);
+  return split ? launch_pdl(gemm_tc_kernel<true>, dim3(ncl * csize), dim3(TC_THREADS), smem, s, csize, mA, mW, p)
+               : launch_pdl(gemm_tc_kernel<false>, dim3(ncl * csize), dim3(TC_THREADS), smem, s, csize, mA, mW, p);
 }
 
 }  // namespace lds

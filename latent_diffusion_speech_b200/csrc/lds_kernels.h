@@ -8,6 +8,37 @@
 
 namespace lds {
 
+// Programmatic dependent launch (PDL).  The hot kernels of the denoiser call pdl_trigger() first (the next kernel of the
+// stream may start launching as soon as every CTA of this one has started) and pdl_wait() before their first access to
+// global memory (blocks until the previous kernel has completed and flushed), and are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: launch latency and the next kernel's prologue (barrier init, TMEM
+// allocation, tensor-map fetch) then hide behind the tail wave of the previous kernel.  LDS_PDL=0 turns the attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+// cudaLaunchKernelEx with the PDL attribute (and an optional cluster size)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 enum Epilogue : int { EPI_NONE = 0, EPI_SILU = 1, EPI_GEGLU = 2 };
 
 // C[M,N] = epi( A (*) W^T + bias ) + R.

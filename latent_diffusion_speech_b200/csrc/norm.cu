@@ -51,6 +51,8 @@ constexpr int GN_UNROLL = 8;
 __global__ void gn_stats_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2, int T,
                                 int groups, int rpar, int chunk_rows, float* __restrict__ part) {
   extern __shared__ float sh[];  // [nthreads][3]
+  pdl_trigger();
+  pdl_wait();
   const int C = c1 + c2, V = C >> 2, cg = C / groups;
   const int v = threadIdx.x % V, r0 = threadIdx.x / V;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -121,6 +123,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                         int silu, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
                                                         int parts, __nv_bfloat16* __restrict__ rawb) {
   __shared__ float s_mean[32], s_rstd[32];
+  pdl_trigger();
+  pdl_wait();
   const int C = c1 + c2, V = C >> 2, cg = C / groups;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -191,6 +195,8 @@ template <int LN_MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int rows, int C,
                                                         float* __restrict__ y, __nv_bfloat16* __restrict__ yb, int parts) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int row0 = warp * LN_ROWS;
   if (row0 >= rows) return;
@@ -263,8 +269,7 @@ cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, in
   const int threads = ((V * rpar + 31) / 32) * 32;
   const int chunk_rows = gn_chunk_rows(B, T);
   dim3 grid((T + chunk_rows - 1) / chunk_rows, B);
-  gn_stats_kernel<<<grid, threads, threads * 3 * sizeof(float), s>>>(x1, c1, x2, c2, T, groups, rpar, chunk_rows, part);
-  return cudaGetLastError();
+  return launch_pdl(gn_stats_kernel, grid, dim3(threads), threads * 3 * sizeof(float), s, 1, x1, c1, x2, c2, T, groups, rpar, chunk_rows, part);
 }
 
 cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups,
@@ -280,9 +285,8 @@ cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, in
   const int threads = ((V * rpar + 31) / 32) * 32;
   dim3 grid((T + slab - 1) / slab, B);
   const int chunk_rows = gn_chunk_rows(B, T);
-  gn_apply_kernel<<<grid, threads, 0, s>>>(x1, c1, x2, c2, T, groups, rpar, (T + chunk_rows - 1) / chunk_rows, slab, part, eps, gamma, beta, ss,
+  return launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, s, 1, x1, c1, x2, c2, T, groups, rpar, (T + chunk_rows - 1) / chunk_rows, slab, part, eps, gamma, beta, ss,
                                            silu, y, yb, parts, rawb);
-  return cudaGetLastError();
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
@@ -290,10 +294,10 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
   if (C % 4 || C > 512) return cudaErrorInvalidValue;
   const int warps_per_block = 8, rows_per_block = warps_per_block * LN_ROWS;
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
-  if (C <= 256) layernorm_kernel<2><<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y, yb, parts);
-  else if (C <= 384) layernorm_kernel<3><<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y, yb, parts);
-  else layernorm_kernel<4><<<grid, warps_per_block * 32, 0, s>>>(x, gamma, beta, eps, rows, C, y, yb, parts);
-  return cudaGetLastError();
+  const dim3 g(grid), b(warps_per_block * 32);
+  if (C <= 256) return launch_pdl(layernorm_kernel<2>, g, b, 0, s, 1, x, gamma, beta, eps, rows, C, y, yb, parts);
+  if (C <= 384) return launch_pdl(layernorm_kernel<3>, g, b, 0, s, 1, x, gamma, beta, eps, rows, C, y, yb, parts);
+  return launch_pdl(layernorm_kernel<4>, g, b, 0, s, 1, x, gamma, beta, eps, rows, C, y, yb, parts);
 }
 
 }  // namespace lds

@@ -12,6 +12,8 @@
 //   DDPM ancestral step (x0 clamp, posterior mean, + sigma*z)    diffusion.py:95-121
 //   DDIM step, PLMS / PNDM step (Adams-Bashforth eps combination) diffusion.py:123-167
 //   [B,1,M,T] <-> channels-last [B,T,M], /acoustic_scale         diffusion.py:225,342-343
+#include <cstdlib>
+
 #include "lds_kernels.h"
 #include "planes.cuh"
 
@@ -201,6 +203,8 @@ __global__ void spk_gather_kernel(const float* __restrict__ table, const int64_t
 
 // fp32 -> bf16 planes; one thread per 4 consecutive channels
 __global__ void split_cast_kernel(const float4* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows, int C, int parts) {
+  pdl_trigger();
+  pdl_wait();
   const int V = C >> 2;
   const int64_t n = rows * V;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -213,6 +217,8 @@ __global__ void split_cast_kernel(const float4* __restrict__ in, __nv_bfloat16* 
 
 __global__ void cast_gather_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int t_in, int t_out, int C,
                                    int parts, int mode, float scale, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   const int V = C >> 2;
   const int taps = mode == 2 ? 3 : 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -244,6 +250,11 @@ inline int grid_for(int64_t nvec) {
 }
 
 }  // namespace
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("LDS_PDL") && atoi(getenv("LDS_PDL")) == 0);
+  return on;
+}
 
 #define V4(p) reinterpret_cast<const float4*>(p)
 #define V4W(p) reinterpret_cast<float4*>(p)
@@ -307,15 +318,13 @@ cudaError_t launch_div_copy(const float* in, float* out, int64_t n, float diviso
 }
 cudaError_t launch_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, cudaStream_t s) {
   if (C % 4 || parts < 1 || parts > 3) return cudaErrorInvalidValue;
-  split_cast_kernel<<<grid_for(rows * (C / 4)), 256, 0, s>>>(V4(in), out, rows, C, parts);
-  return cudaGetLastError();
+  return launch_pdl(split_cast_kernel, dim3(grid_for(rows * (C / 4))), dim3(256), 0, s, 1, V4(in), out, rows, C, parts);
 }
 cudaError_t launch_cast_gather(const float* in, __nv_bfloat16* out, int B, int t_in, int t_out, int C, int parts, int mode,
                                float scale, cudaStream_t s) {
   if (C % 4 || parts < 1 || parts > 3 || (mode != 1 && mode != 2)) return cudaErrorInvalidValue;
   const int64_t n = (int64_t)B * t_out * (mode == 2 ? 3 : 1) * (C / 4);
-  cast_gather_kernel<<<grid_for(n), 256, 0, s>>>(in, out, t_in, t_out, C, parts, mode, scale, n);
-  return cudaGetLastError();
+  return launch_pdl(cast_gather_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, in, out, t_in, t_out, C, parts, mode, scale, n);
 }
 cudaError_t launch_silu(const float* in, float* out, int64_t n, cudaStream_t s) {
   silu_kernel<<<grid_for(n), 256, 0, s>>>(in, out, n);
