@@ -172,6 +172,11 @@ LDS_API int lds_op_attention(const float* qkv, float* out, int B, int T, int C, 
 LDS_API int lds_op_groupnorm(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
                      const float* gamma, const float* beta, const float* scale_shift, int silu, float* part,
                      float* y, void* stream);
+/* Single-pass form of lds_op_groupnorm: one CTA per (utterance, group) keeps its [T, C/groups] slab in shared memory
+ * (x read once).  LDS_ERR_UNSUPPORTED when the slab exceeds 200 KB; the sampler picks it automatically when it fits. */
+LDS_API int lds_op_groupnorm_fused(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
+                           const float* gamma, const float* beta, const float* scale_shift, int silu, float* y,
+                           void* stream);
 LDS_API int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
                      void* stream);
 /* Tensor-core (tcgen05/TMEM/TMA) form of lds_op_gemm on bf16 operands.

@@ -123,6 +123,10 @@ cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, in
 cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups,
                             const float* part, float eps, const float* gamma, const float* beta, const float* ss,
                             int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s);
+// single-pass variant (slab of one (utterance, group) in shared memory); cudaErrorNotSupported when it does not fit
+cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
+                            const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
+                            int parts, __nv_bfloat16* rawb, cudaStream_t s);
 //  (yb != nullptr: write bf16 operand planes [B*T, parts*C] instead of fp32 y; rawb: also copy the un-normalised
 //   concat input as planes — the A operand of the 1x1 shortcut convolution)
 

@@ -188,6 +188,83 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   }
 }
 
+// Single-pass GroupNorm: one CTA per (utterance, group) keeps its whole [T, C/G] slab in shared memory, so x is read
+// from HBM once (statistics + apply: 4 B read + 2*parts B written per element instead of 8 + 2*parts) and the two
+// launches become one.  Exact two-pass mean / M2 over the slab.  Used when the slab fits (T * C/G * 4 B <= ~200 KB),
+// else the stats + apply pair above.  thread (v, r): channel quad v of the group, frames r, r+R, ...
+constexpr int GNF_THREADS = 512;
+__global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2,
+                                                               int T, int groups, float eps, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ ss, int silu,
+                                                               float* __restrict__ y, __nv_bfloat16* __restrict__ yb, int parts,
+                                                               __nv_bfloat16* __restrict__ rawb) {
+  extern __shared__ float4 slab[];               // [T][q]
+  __shared__ float red[GNF_THREADS / 32];
+  __shared__ float s_bcast;
+  pdl_trigger();
+  pdl_wait();
+  const int C = c1 + c2, cg = C / groups, q = cg >> 2;
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int R = GNF_THREADS / q;                 // frames in flight per pass over the block's threads
+  const int v = threadIdx.x % q, r0 = threadIdx.x / q;
+  const int c = g * cg + 4 * v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool active = r0 < R;
+  auto block_sum = [&](float val) {
+    val = warp_sum(val);
+    if (lane == 0) red[warp] = val;
+    __syncthreads();
+    if (warp == 0) {
+      float t = lane < GNF_THREADS / 32 ? red[lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) s_bcast = t;
+    }
+    __syncthreads();
+    return s_bcast;
+  };
+  float sum = 0.f;
+  if (active) {
+    for (int t = r0; t < T; t += R) {
+      const float4 xv = load_cat(x1, c1, x2, c2, (size_t)b * T + t, c);
+      slab[t * q + v] = xv;
+      sum += (xv.x + xv.y) + (xv.z + xv.w);
+    }
+  }
+  const float n = (float)T * (float)cg;
+  const float mean = block_sum(sum) / n;
+  float m2 = 0.f;
+  if (active) {
+    for (int t = r0; t < T; t += R) {
+      const float4 xv = slab[t * q + v];
+      const float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
+      m2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  }
+  const float rstd = rsqrtf(block_sum(m2) / n + eps);
+  if (!active) return;
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sf = sc;
+  if (ss) {
+    sc = __ldg(reinterpret_cast<const float4*>(ss + c));
+    sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+  }
+  for (int t = r0; t < T; t += R) {
+    const float4 xv = slab[t * q + v];
+    const size_t row = (size_t)b * T + t;
+    float o[4] = {(xv.x - mean) * rstd * ga.x + be.x, (xv.y - mean) * rstd * ga.y + be.y,
+                  (xv.z - mean) * rstd * ga.z + be.z, (xv.w - mean) * rstd * ga.w + be.w};
+    if (ss) {
+      o[0] = o[0] * (1.f + sc.x) + sf.x; o[1] = o[1] * (1.f + sc.y) + sf.y;
+      o[2] = o[2] * (1.f + sc.z) + sf.z; o[3] = o[3] * (1.f + sc.w) + sf.w;
+    }
+    if (silu) { o[0] = silu_f(o[0]); o[1] = silu_f(o[1]); o[2] = silu_f(o[2]); o[3] = silu_f(o[3]); }
+    if (yb) store_planes4(yb + row * (size_t)(parts * C), c, C, parts, o[0], o[1], o[2], o[3]);
+    else *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (rawb) store_planes4(rawb + row * (size_t)(parts * C), c, C, parts, xv.x, xv.y, xv.z, xv.w);
+  }
+}
+
 // One warp per LN_ROWS consecutive rows (C <= 32*4*LN_MAXV, LN_MAXV instantiated for C <= 256 / 384 / 512): all loads of the rows are issued before the first
 // reduction, so that LN_ROWS x C x 4 bytes per warp are in flight (bytes in flight, not issue, bound this kernel).
 constexpr int LN_ROWS = 4;
@@ -287,6 +364,25 @@ cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, in
   const int chunk_rows = gn_chunk_rows(B, T);
   return launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, s, 1, x1, c1, x2, c2, T, groups, rpar, (T + chunk_rows - 1) / chunk_rows, slab, part, eps, gamma, beta, ss,
                                            silu, y, yb, parts, rawb);
+}
+
+// cudaErrorNotSupported when the slab of one (utterance, group) does not fit shared memory: use stats + apply then.
+cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
+                            const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
+                            int parts, __nv_bfloat16* rawb, cudaStream_t s) {
+  const int C = c1 + c2;
+  if (C % (4 * groups) || c1 % 4 || groups > 32) return cudaErrorInvalidValue;
+  const int cg = C / groups, q = cg / 4;
+  const size_t smem = (size_t)T * cg * sizeof(float);
+  if (q > GNF_THREADS || smem > 200 * 1024) return cudaErrorNotSupported;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  return launch_pdl(gn_fused_kernel, dim3(groups, B), dim3(GNF_THREADS), smem, s, 1, x1, c1, x2, c2, T, groups, eps, gamma, beta, ss,
+                    silu, y, yb, parts, rawb);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
