@@ -224,10 +224,18 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const float* __re
   };
   float sum = 0.f;
   if (active) {
-    for (int t = r0; t < T; t += R) {
-      const float4 xv = load_cat(x1, c1, x2, c2, (size_t)b * T + t, c);
-      slab[t * q + v] = xv;
-      sum += (xv.x + xv.y) + (xv.z + xv.w);
+    constexpr int U = 8;                         // loads in flight per thread
+    for (int tb = r0; tb < T; tb += R * U) {
+      float4 xv[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i)
+        if (tb + i * R < T) xv[i] = load_cat(x1, c1, x2, c2, (size_t)b * T + tb + i * R, c);
+#pragma unroll
+      for (int i = 0; i < U; ++i)
+        if (tb + i * R < T) {
+          slab[(tb + i * R) * q + v] = xv[i];
+          sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        }
     }
   }
   const float n = (float)T * (float)cg;
