@@ -172,11 +172,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_f32_kernel(const float*
 template <int D>
 cudaError_t launch_d(const float* qkv, float* out, __nv_bfloat16* outb, int parts, int B, int T, int C, int heads, cudaStream_t s) {
   const size_t smem = (size_t)(2 * D * TLD + BKV * D + BKV * TLD) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((T + BQ - 1) / BQ, heads, B);
   attention_f32_kernel<D><<<grid, ATT_THREADS, smem, s>>>(qkv, out, outb, parts, T, C);

@@ -360,11 +360,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
 // d <= 32, split mode.  Operand layouts as attention_tc.cu (a.dpad == 32, a.parts == 3).
 cudaError_t launch_attention_pair(const AttnTcArgs& a, cudaStream_t s) {
   if (a.parts != PARTS || a.dpad != DPAD || a.d > DPAD || a.d % 8 || a.T_pad % 8 || a.T_pad < a.T) return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const uint64_t HD = (uint64_t)a.H * DPAD;
   CUtensorMap mQ, mK, mV;

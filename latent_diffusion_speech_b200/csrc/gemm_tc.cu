@@ -615,19 +615,21 @@ cudaError_t get_map(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint
 }
 
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
-      n = 148;
-  }
-  return n;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = n[dev & 63];
+  if (!v && (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1)) v = 148;
+  return v;
 }
 
 // co-resident clusters of two persistent CTAs (GPC boundaries can strand an SM; asked from the occupancy calculator)
 int max_clusters2() {
-  static int n = 0;
-  if (!n) {
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& slot = n[dev & 63];
+  if (!slot) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * sm_count());
     cfg.blockDim = dim3(TC_THREADS);
@@ -640,9 +642,9 @@ int max_clusters2() {
     int v = 0;
     if (cudaOccupancyMaxActiveClusters(&v, gemm_tc_kernel<true>, &cfg) != cudaSuccess || v < 1) v = sm_count() / 2;
     (void)cudaGetLastError();
-    n = v;
+    slot = v;
   }
-  return n;
+  return slot;
 }
 
 }  // namespace
@@ -674,13 +676,12 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (a.out_kind == 3 && (!a.q_out || !a.k_out || !a.vt_out || a.att_T < 1 || a.att_dpad % 32 || a.N != 3 * a.att_H * a.att_dpad ||
                           a.epilogue != EPI_NONE))
     return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   TcParams p;
   p.BN = a.N % 256 == 0 ? 256 : ((a.N % 192 == 0 && a.epilogue != EPI_GEGLU) ? 192 : 128);   // GEGLU groups are 128 wide

@@ -18,6 +18,15 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 bool pdl_enabled();
+// Kernel attributes (opt-in shared memory) are per device: true exactly once per (call site, device of the calling thread).
+inline bool first_use_on_this_device(unsigned long long& seen) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  if (seen & bit) return false;
+  seen |= bit;
+  return true;
+}
 // cudaLaunchKernelEx with the PDL attribute (and an optional cluster size)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, Args... args) {

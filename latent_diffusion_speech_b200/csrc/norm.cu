@@ -383,11 +383,10 @@ cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, in
   const int cg = C / groups, q = cg / 4;
   const size_t smem = (size_t)T * cg * sizeof(float);
   if (q > GNF_THREADS || smem > 200 * 1024) return cudaErrorNotSupported;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   return launch_pdl(gn_fused_kernel, dim3(groups, B), dim3(GNF_THREADS), smem, s, 1, x1, c1, x2, c2, T, groups, eps, gamma, beta, ss,
                     silu, y, yb, parts, rawb);

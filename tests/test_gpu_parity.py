@@ -170,3 +170,24 @@ def test_long_sequence_shallow_diffusion_T2584(gpu_model, state_dict):
     G.report(test="shallow_dpm10_T2584_vs_fp64_gpu_oracle", **e)
     assert mel.shape == (B, T, 128) and torch.isfinite(mel).all()
     assert e["max_abs"] <= TOL_VS_FP64, e
+
+
+def test_single_speaker_and_acoustic_scale_vs_fp64_oracle():
+    """A configuration other than the default one: n_spk = 1 (no speaker embedding, unit2mel.py:57-58) and
+    acoustic_scale = 2.5 (norm_spec / denorm_spec, diffusion.py:86-87,343), shallow start, UniPC, vs the fp64 oracle."""
+    from latent_diffusion_speech_b200.unit2mel import Unit2Mel
+    torch.manual_seed(4321)
+    model = Unit2Mel(1280, 1, 128, 2, [256, 384, 512, 512], 8, 256, 2.5).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert "spk_embed.weight" not in sd
+    cfg = dict(O.DEFAULT_CFG, n_spk=1, acoustic_scale=2.5)
+    B, T = 2, 48
+    units, _, noise, _, gt = O.synthetic_inputs(B, T, gt=True)
+    model = model.cuda()
+    with torch.no_grad():
+        mel = model(units.cuda(), None, spk_id=None, gt_spec=gt.cuda(), infer=True, infer_speedup=25, method="unipc", k_step=100,
+                    noise=noise.cuda()).cpu()
+        ref64 = O.unit2mel_infer(sd, cfg, units, None, noise, "unipc", 25, gt_spec=gt, k_step=100, dtype=torch.float64)
+    e = G.errs(mel, ref64)
+    G.report(test="nspk1_scale2p5_shallow_unipc4_vs_fp64", **e)
+    assert e["max_abs"] <= TOL_VS_FP64, e
