@@ -7,7 +7,8 @@
 // so that every MMA operand is a K-major, TMA-swizzled tile.  parts = 1: bf16 mode.  parts = 3: fp32-accurate mode,
 // both products are evaluated as the six significant plane products (split-bf16), softmax in fp32 with expf.
 //
-// CTA = 128 queries of one (utterance, head); keys stream in tiles of 64.  Two passes over the keys:
+// Work item = 128 queries of one (utterance, head); persistent CTAs stride over the items; keys stream in tiles of 64.
+// Two passes over the keys:
 //   pass A: S ~ Q_hi K_hi^T (one plane product: the maximum is only needed to ~1 %) -> TMEM, softmax warps reduce the
 //           row maximum m (no exponentials)
 //   pass B: S again, P = exp(S*scale - m) (fp32), row sums in registers, P planes -> shared memory (128B-swizzled,
@@ -33,7 +34,7 @@ using namespace ptx;
 constexpr int AQ = 128, ATT_TC_THREADS = 320, NSOFT = 256;
 
 struct AttnTcParams {
-  int T, H, d, C, parts, nk, nv, nsb, npb;   // ring depths: K, V^T tiles (smem), S (TMEM) and P (smem) buffers
+  int B, T, H, d, C, parts, nk, nv, nsb, npb;   // ring depths: K, V^T tiles (smem), S (TMEM) and P (smem) buffers
   float scale;
   __nv_bfloat16* out;   // planes [B*T][parts*C]
 };
@@ -109,13 +110,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   auto k_empty = [&](int s) { return bar0 + 72 + 8u * (4 + s); };
   auto v_full = [&](int s) { return bar0 + 72 + 8u * (8 + s); };
   auto v_empty = [&](int s) { return bar0 + 72 + 8u * (12 + s); };
-  uint8_t* misc = smem + (bar0 - base) + 72 + 8 * 16;
+  uint8_t* misc = smem + (bar0 - base) + 72 + 8 * 16 + 16;        // + q_empty, o_free
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
   float* red = reinterpret_cast<float*>(misc + 16);          // [2][128] exchange of row max / row sum between the halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
-  const int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
+  // Persistent CTA: work items (utterance, head, query tile) blockIdx.x, blockIdx.x + gridDim.x, ...; every barrier
+  // phase follows a running use counter, so the TMA producer and the MMA warp run ahead into the next item (its Q / K
+  // loads and its pass A overlap the softmax tail, the O read-out and the stores of the current one).
+  const int nq = (p.T + AQ - 1) / AQ, n_items = nq * p.H * p.B;
   const int nt = (p.T + AKV - 1) / AKV;
   const int HD = p.H * DPAD;
   constexpr int tmem_cols = (parts == 3 && !DUAL) ? 512 : 256;
@@ -123,12 +127,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   constexpr int n_sblk = parts == 3 ? ((AKV == 64 && !DUAL) ? 3 : 2) : 1;
   constexpr int s_stride = n_sblk * AKV;           // TMEM columns per S buffer
   constexpr int n_oblk = parts == 3 ? 3 : 1;
+  const uint32_t q_empty = bar0 + 72 + 8 * 16, o_free = q_empty + 8;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&mapQ);
     prefetch_tensormap(&mapK);
     prefetch_tensormap(&mapVT);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, NSOFT);
     for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(s_free(s), NSOFT); mbar_init(p_full(s), NSOFT); mbar_init(pv_done(s), 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
     mbar_fence_init();
@@ -144,24 +151,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, parts * QB);
-      for (int pl = 0; pl < parts; ++pl) tma_load_3d(q_s + pl * QB, &mapQ, q_full, pl * HD + h * DPAD, q0, b);
-      for (int it = 0; it < 2 * nt; ++it) {
-        const int jt = it < nt ? it : it - nt;
-        const int ks = it % NK;
-        const int kparts = it < nt ? 1 : parts;                  // pass A needs the hi plane only
-        mbar_wait(k_empty(ks), ((uint32_t)(it / NK) & 1u) ^ 1u);
-        mbar_expect_tx(k_full(ks), kparts * KB);
-        for (int pl = 0; pl < kparts; ++pl)
-          tma_load_3d(k_s + (ks * parts + pl) * KB, &mapK, k_full(ks), pl * HD + h * DPAD, jt * AKV, b);
-        if (it >= nt) {
-          const int vs = jt % NV;
-          mbar_wait(v_empty(vs), ((uint32_t)(jt / NV) & 1u) ^ 1u);
-          mbar_expect_tx(v_full(vs), parts * KBLK * VBK);
-          for (int kb = 0; kb < KBLK; ++kb)
-            for (int pl = 0; pl < parts; ++pl)
-              tma_load_2d(v_s + ((vs * KBLK + kb) * parts + pl) * VBK, &mapVT, v_full(vs), jt * AKV + kb * 64,
-                          ((b * parts + pl) * p.H + h) * DPAD);
+      uint32_t kc = 0, vc = 0, local = 0;        // K tiles / V^T tiles loaded so far, items started
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+        const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+        mbar_wait(q_empty, (local & 1u) ^ 1u);                   // every Q K^T of the previous item has read Q
+        mbar_expect_tx(q_full, parts * QB);
+        for (int pl = 0; pl < parts; ++pl) tma_load_3d(q_s + pl * QB, &mapQ, q_full, pl * HD + h * DPAD, qt * AQ, b);
+        for (int it = 0; it < 2 * nt; ++it, ++kc) {
+          const int jt = it < nt ? it : it - nt;
+          const int ks = kc % NK;
+          const int kparts = it < nt ? 1 : parts;                // pass A needs the hi plane only
+          mbar_wait(k_empty(ks), ((kc / NK) & 1u) ^ 1u);
+          mbar_expect_tx(k_full(ks), kparts * KB);
+          for (int pl = 0; pl < kparts; ++pl)
+            tma_load_3d(k_s + (ks * parts + pl) * KB, &mapK, k_full(ks), pl * HD + h * DPAD, jt * AKV, b);
+          if (it >= nt) {
+            const int vs = vc % NV;
+            mbar_wait(v_empty(vs), ((vc / NV) & 1u) ^ 1u);
+            mbar_expect_tx(v_full(vs), parts * KBLK * VBK);
+            for (int kb = 0; kb < KBLK; ++kb)
+              for (int pl = 0; pl < parts; ++pl)
+                tma_load_2d(v_s + ((vs * KBLK + kb) * parts + pl) * VBK, &mapVT, v_full(vs), jt * AKV + kb * 64,
+                            ((b * parts + pl) * p.H + h) * DPAD);
+            ++vc;
+          }
         }
       }
     }
@@ -198,17 +211,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                      p_kb_step = (uint64_t)(PBK >> 4);
       const uint64_t q_hi = umma_desc_kmajor(q_s, SWZ), k_hi = umma_desc_kmajor(k_s, SWZ);
       const uint32_t hi_idesc = umma_idesc_bf16(AQ, AKV);
-      mbar_wait(q_full, 0);
-      // S buffer of evaluation `it`: pass B rotates over the NSB buffers of the S region; pass A always has two buffers —
-      // with NSB == 1 the second one borrows the (still unused) O region — so that the hi*hi product of tile j+1 runs
-      // while the softmax threads still reduce tile j.  Barrier phases follow per-buffer use counters.
-      uint32_t su0 = 0u, su1 = 0u;
       const int ksteps = (p.d + 15) / 16;        // head dims beyond d are zero padding (d = 48 in a 64-wide tile): skip their K slices
+      // S buffer of evaluation `it`: pass B rotates over the NSB buffers of the S region; pass A always has two buffers —
+      // with NSB == 1 the second one borrows the O region (idle until the first P V of the item) — so that the hi*hi
+      // product of tile j+1 runs while the softmax threads still reduce tile j.
+      uint32_t su0 = 0u, su1 = 0u, pu0 = 0u, pu1 = 0u, kc = 0u, vc = 0u, local = 0u;
+      bool o_claimed = false;
+      auto claim_o = [&]() {                     // the softmax threads have read the previous item's O
+        if (!o_claimed) {
+          mbar_wait(o_free, (local & 1u) ^ 1u);
+          o_claimed = true;
+        }
+      };
       auto issue_qk = [&](int it) {
-        const int ks = it % NK;
+        const int ks = kc % NK;
         const int sb = it < nt ? (it & 1) : (it - nt) % NSB;
-        const uint32_t soff = it < nt ? (NSB == 1 ? (uint32_t)(sb * o_col) : (uint32_t)(sb * s_stride)) : (uint32_t)(sb * s_stride);
-        mbar_wait(k_full(ks), (uint32_t)(it / NK) & 1u);
+        const bool alt = it < nt && NSB == 1 && sb == 1;
+        const uint32_t soff = alt ? (uint32_t)o_col : (uint32_t)(sb * s_stride);
+        if (alt) claim_o();
+        mbar_wait(k_full(ks), (kc / NK) & 1u);
+        ++kc;
         mbar_wait(s_free(sb), ((sb ? su1 : su0) & 1u) ^ 1u);   // the softmax threads have read the previous use of this S buffer
         if (sb) ++su1; else ++su0;
         tc_fence_after();
@@ -227,25 +249,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         }
         umma_commit(k_empty(ks));
         umma_commit(s_full(sb));
+        if (it == 2 * nt - 1) umma_commit(q_empty);            // last Q K^T of the item: Q may be overwritten
       };
-      for (int it = 0; it < nt; ++it) issue_qk(it);            // pass A
-      issue_qk(nt);                                            // pass B: Q K^T runs one tile ahead of P V
-      for (int jb = 0; jb < nt; ++jb) {
-        if (jb + 1 < nt) issue_qk(nt + jb + 1);
-        const int vs = jb % NV, pb = jb % NPB;
-        mbar_wait(v_full(vs), (uint32_t)(jb / NV) & 1u);
-        mbar_wait(p_full(pb), (uint32_t)(jb / NPB) & 1u);
-        tc_fence_after();
-        const uint64_t poff = (uint64_t)pb * p_buf_step, voff = (uint64_t)vs * v_stage_step;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+        o_claimed = false;
+        mbar_wait(q_full, local & 1u);
+        for (int it = 0; it < nt; ++it) issue_qk(it);            // pass A
+        issue_qk(nt);                                            // pass B: Q K^T runs one tile ahead of P V
+        for (int jb = 0; jb < nt; ++jb) {
+          if (jb + 1 < nt) issue_qk(nt + jb + 1);
+          const int vs = vc % NV, pb = jb % NPB;
+          mbar_wait(v_full(vs), (vc / NV) & 1u);
+          ++vc;
+          mbar_wait(p_full(pb), (pb ? pu1 : pu0) & 1u);
+          if (pb) ++pu1; else ++pu0;
+          if (jb == 0) claim_o();
+          tc_fence_after();
+          const uint64_t poff = (uint64_t)pb * p_buf_step, voff = (uint64_t)vs * v_stage_step;
 #pragma unroll
-        for (int k = 0; k < AKV / 16; ++k) {
-          const uint64_t pk = poff + (uint64_t)(k >> 2) * p_kb_step + (uint64_t)(2 * (k & 3));
-          const uint64_t vk = voff + (uint64_t)(k >> 2) * v_kb_step + (uint64_t)(2 * (k & 3));
-          for (int e = 0; e < n_pv; ++e)
-            umma_bf16(pv_dst[e], pd0[e] + pk, vd0[e] + vk, pv_idesc[e], (jb == 0 && k == 0 && e == 0) ? 0u : 1u);
+          for (int k = 0; k < AKV / 16; ++k) {
+            const uint64_t pk = poff + (uint64_t)(k >> 2) * p_kb_step + (uint64_t)(2 * (k & 3));
+            const uint64_t vk = voff + (uint64_t)(k >> 2) * v_kb_step + (uint64_t)(2 * (k & 3));
+            for (int e = 0; e < n_pv; ++e)
+              umma_bf16(pv_dst[e], pd0[e] + pk, vd0[e] + vk, pv_idesc[e], (jb == 0 && k == 0 && e == 0) ? 0u : 1u);
+          }
+          umma_commit(v_empty(vs));
+          umma_commit(pv_done(pb));
         }
-        umma_commit(v_empty(vs));
-        umma_commit(pv_done(pb));
       }
     }
   } else {
@@ -265,119 +295,133 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         for (int i = 0; i < 32; ++i) s[i] += t[i];
       }
     };
-    float m = -INFINITY;
-    // ---- pass A: row maximum of the scaled, masked scores ----
     uint32_t su0 = 0u, su1 = 0u;                         // per-buffer use counters (same sequence as the MMA warp)
-    for (int it = 0; it < nt; ++it) {
-      const int sb = it & 1;
-      const uint32_t soff = NSB == 1 ? (uint32_t)(sb * o_col) : (uint32_t)(sb * s_stride);
-      mbar_wait(s_full(sb), (sb ? su1 : su0) & 1u);
-      if (sb) ++su1; else ++su0;
-      tc_fence_after();
+    uint32_t pw0 = 0u, pw1 = 0u;                         // P buffer uses == P V completions to expect per buffer
+    uint8_t* prow = p_ptr + (row >> 3) * 1024 + (row & 7) * 128;     // 8-row / 1024 B swizzle atoms, 128 B per row
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+      float m = -INFINITY;
+      // ---- pass A: row maximum of the scaled, masked scores ----
+      for (int it = 0; it < nt; ++it) {
+        const int sb = it & 1;
+        const uint32_t soff = NSB == 1 ? (uint32_t)(sb * o_col) : (uint32_t)(sb * s_stride);
+        mbar_wait(s_full(sb), (sb ? su1 : su0) & 1u);
+        if (sb) ++su1; else ++su0;
+        tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch) {
-        float s[32];
-        tmem_ld32(tmem0 + lane_off + soff + c0 + ch * 32, s);   // hi*hi scores live in block 0
-        if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
-        const int k0 = it * AKV + c0 + ch * 32;
-        if (k0 + 32 <= p.T) {
+        for (int ch = 0; ch < NCH; ++ch) {
+          float s[32];
+          tmem_ld32(tmem0 + lane_off + soff + c0 + ch * 32, s);   // hi*hi scores live in block 0
+          if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
+          const int k0 = it * AKV + c0 + ch * 32;
+          if (k0 + 32 <= p.T) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, s[i]);
-        } else {
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, s[i]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (k0 + i < p.T) m = fmaxf(m, s[i]);
+            for (int i = 0; i < 32; ++i)
+              if (k0 + i < p.T) m = fmaxf(m, s[i]);
+          }
         }
       }
-    }
-    m *= sl2;                                            // row maximum in the log2 domain (sl2 > 0)
-    red[half * 128 + row] = m;
-    softmax_bar();
-    m = fmaxf(m, red[(half ^ 1) * 128 + row]);
-    softmax_bar();
-    // ---- pass B: probabilities, row sum, P planes to shared memory ----
-    float l = 0.f;
-    uint8_t* prow = p_ptr + (row >> 3) * 1024 + (row & 7) * 128;     // 8-row / 1024 B swizzle atoms, 128 B per row
-    for (int jb = 0; jb < nt; ++jb) {
-      const int sb = jb % NSB, pb = jb % NPB;
-      mbar_wait(s_full(sb), (sb ? su1 : su0) & 1u);
-      if (sb) ++su1; else ++su0;
-      tc_fence_after();
-      uint32_t w[PARTS][16 * NCH];
+      m *= sl2;                                            // row maximum in the log2 domain (sl2 > 0)
+      red[half * 128 + row] = m;
+      softmax_bar();
+      m = fmaxf(m, red[(half ^ 1) * 128 + row]);
+      softmax_bar();
+      // ---- pass B: probabilities, row sum, P planes to shared memory ----
+      float l = 0.f;
+      for (int jb = 0; jb < nt; ++jb) {
+        const int sb = jb % NSB, pb = jb % NPB;
+        mbar_wait(s_full(sb), (sb ? su1 : su0) & 1u);
+        if (sb) ++su1; else ++su0;
+        tc_fence_after();
+        uint32_t w[PARTS][16 * NCH];
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        float s[32];
-        load_s32(sb, c0 + ch * 32, s);
-        if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
-        const int k0 = jb * AKV + c0 + ch * 32;
+        for (int ch = 0; ch < NCH; ++ch) {
+          float s[32];
+          load_s32(sb, c0 + ch * 32, s);
+          if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
+          const int k0 = jb * AKV + c0 + ch * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[i] = ex2_approx(fmaf(s[i], sl2, -m));
-        if (k0 + 32 > p.T) {                                           // ragged last tile: keys beyond T contribute nothing
+          for (int i = 0; i < 32; ++i) s[i] = ex2_approx(fmaf(s[i], sl2, -m));
+          if (k0 + 32 > p.T) {                                           // ragged last tile: keys beyond T contribute nothing
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (k0 + i >= p.T) s[i] = 0.f;
+            for (int i = 0; i < 32; ++i)
+              if (k0 + i >= p.T) s[i] = 0.f;
+          }
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) { l0 += s[i]; l1 += s[i + 1]; }
+          l += l0 + l1;
+          // split into bf16 planes in registers, so that only the stores sit behind the P-buffer hand-off
+#pragma unroll
+          for (int pl = 0; pl < PARTS; ++pl) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              w[pl][ch * 16 + i] = (pl == PARTS - 1) ? pack_pair(s[2 * i], s[2 * i + 1]) : split_pair(s[2 * i], s[2 * i + 1]);
+          }
         }
-        float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) { l0 += s[i]; l1 += s[i + 1]; }
-        l += l0 + l1;
-        // split into bf16 planes in registers, so that only the stores sit behind the P-buffer hand-off
+        {                                                                // the P*V that last read this P buffer is done
+          const uint32_t uses = pb ? pw1 : pw0;
+          if (uses > 0) mbar_wait(pv_done(pb), (uses - 1) & 1u);
+          if (pb) ++pw1; else ++pw0;
+        }
 #pragma unroll
         for (int pl = 0; pl < PARTS; ++pl) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            w[pl][ch * 16 + i] = (pl == PARTS - 1) ? pack_pair(s[2 * i], s[2 * i + 1]) : split_pair(s[2 * i], s[2 * i + 1]);
+          for (int cc = 0; cc < 4 * NCH; ++cc) {                         // 16-byte chunk = 8 keys
+            const int key_chunk = (c0 >> 3) + cc;                        // chunk index inside the AKV-key row
+            uint8_t* dst = prow + ((pb * parts + pl) * KBLK + (key_chunk >> 3)) * PBK;
+            *reinterpret_cast<uint4*>(dst + (((key_chunk & 7) ^ (row & 7)) << 4)) =
+                make_uint4(w[pl][4 * cc], w[pl][4 * cc + 1], w[pl][4 * cc + 2], w[pl][4 * cc + 3]);
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(p_full(pb));
+      }
+      red[half * 128 + row] = l;
+      softmax_bar();
+      l += red[(half ^ 1) * 128 + row];
+      // ---- epilogue: O / l -> bf16 planes; this thread writes output columns [half*OC, half*OC + OC) ----
+      {
+        const int pb = (nt - 1) % NPB;
+        mbar_wait(pv_done(pb), ((pb ? pw1 : pw0) - 1) & 1u);           // the last P V of the item
+      }
+      tc_fence_after();
+      const int q = qt * AQ + row;
+      const float inv = 1.f / l;
+      float o[OC];
+      {
+        auto ld = [&](uint32_t addr, float* v) {
+          if constexpr (OC == 32) tmem_ld32(addr, v); else tmem_ld16(addr, v);
+        };
+        ld(tmem_o + lane_off + (n_oblk - 1) * DPAD + half * OC, o);
+        for (int blk = n_oblk - 2; blk >= 0; --blk) {
+          float t[OC];
+          ld(tmem_o + lane_off + blk * DPAD + half * OC, t);
+#pragma unroll
+          for (int i = 0; i < OC; ++i) o[i] += t[i];
         }
       }
-      if (jb >= NPB) mbar_wait(pv_done(pb), (uint32_t)(jb / NPB - 1) & 1u);   // the P*V that last used this P buffer is done
+      tc_fence_before();
+      mbar_arrive(o_free);                                               // the next item may overwrite O
+      const int ncol = min(OC, p.d - half * OC);                        // d = 48: 16 valid columns in the upper half
+      if (q < p.T && ncol > 0) {
+        __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q) * (size_t)(parts * p.C) + h * p.d + half * OC;
 #pragma unroll
-      for (int pl = 0; pl < PARTS; ++pl) {
+        for (int i = 0; i < OC; ++i) o[i] *= inv;
+        for (int pl = 0; pl < parts; ++pl) {
+          uint32_t w[OC / 2];
 #pragma unroll
-        for (int cc = 0; cc < 4 * NCH; ++cc) {                         // 16-byte chunk = 8 keys
-          const int key_chunk = (c0 >> 3) + cc;                        // chunk index inside the AKV-key row
-          uint8_t* dst = prow + ((pb * parts + pl) * KBLK + (key_chunk >> 3)) * PBK;
-          *reinterpret_cast<uint4*>(dst + (((key_chunk & 7) ^ (row & 7)) << 4)) =
-              make_uint4(w[pl][4 * cc], w[pl][4 * cc + 1], w[pl][4 * cc + 2], w[pl][4 * cc + 3]);
+          for (int i = 0; i < OC / 2; ++i) w[i] = split_pair(o[2 * i], o[2 * i + 1]);
+          uint4* dst = reinterpret_cast<uint4*>(orow + (size_t)pl * p.C);
+#pragma unroll
+          for (int i = 0; i < OC / 8; ++i)
+            if (i * 8 < ncol) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
         }
       }
-      fence_async_smem();
-      mbar_arrive(p_full(pb));
-    }
-    red[half * 128 + row] = l;
-    softmax_bar();
-    l += red[(half ^ 1) * 128 + row];
-    // ---- epilogue: O / l -> bf16 planes; this thread writes output columns [half*OC, half*OC + OC) ----
-    mbar_wait(pv_done((nt - 1) % NPB), (uint32_t)((nt - 1) / NPB) & 1u);
-    tc_fence_after();
-    const int q = q0 + row;
-    const float inv = 1.f / l;
-    float o[OC];
-    {
-      auto ld = [&](uint32_t addr, float* v) {
-        if constexpr (OC == 32) tmem_ld32(addr, v); else tmem_ld16(addr, v);
-      };
-      ld(tmem_o + lane_off + (n_oblk - 1) * DPAD + half * OC, o);
-      for (int blk = n_oblk - 2; blk >= 0; --blk) {
-        float t[OC];
-        ld(tmem_o + lane_off + blk * DPAD + half * OC, t);
-#pragma unroll
-        for (int i = 0; i < OC; ++i) o[i] += t[i];
-      }
-    }
-    const int ncol = min(OC, p.d - half * OC);                        // d = 48: 16 valid columns in the upper half
-    if (q < p.T && ncol > 0) {
-      __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q) * (size_t)(parts * p.C) + h * p.d + half * OC;
-#pragma unroll
-      for (int i = 0; i < OC; ++i) o[i] *= inv;
-      for (int pl = 0; pl < parts; ++pl) {
-        uint32_t w[OC / 2];
-#pragma unroll
-        for (int i = 0; i < OC / 2; ++i) w[i] = split_pair(o[2 * i], o[2 * i + 1]);
-        uint4* dst = reinterpret_cast<uint4*>(orow + (size_t)pl * p.C);
-#pragma unroll
-        for (int i = 0; i < OC / 8; ++i)
-          if (i * 8 < ncol) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-      }
+      softmax_bar();                                                     // red[] is reused by the next item
     }
     tc_fence_before();
   }
@@ -392,7 +436,7 @@ template <int DPAD, int AKV, int PARTS, bool DUAL = false>
 cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, cudaStream_t s) {
   const int parts = a.parts;
   const size_t smem = (size_t)parts * (AQ * DPAD * 2 + nk * AKV * DPAD * 2 + nv * DPAD * AKV * 2 + npb * AQ * AKV * 2) + 1024 +
-                      72 + 8 * 16 + 16 + 2 * 128 * 4 + 64;
+                      72 + 8 * 16 + 16 + 16 + 2 * 128 * 4 + 64;
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint64_t HD = (uint64_t)a.H * DPAD;
@@ -411,10 +455,18 @@ cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, c
     if ((e = tc_make_map_bf16(a.vt, 2, dims, str, box, 128, &mV)) != cudaSuccess) return e;
   }
   AttnTcParams p;
-  p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts; p.nk = nk; p.nv = nv; p.nsb = nsb; p.npb = npb;
+  p.B = a.B; p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts; p.nk = nk; p.nv = nv; p.nsb = nsb; p.npb = npb;
   p.scale = 1.0f / sqrtf((float)a.d);
   p.out = a.out;
-  dim3 grid((a.T + AQ - 1) / AQ, a.H, a.B);
+  // persistent: one CTA per resident slot (two per SM in bf16 / DUAL mode), items strided over them
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+  const int n_items = ((a.T + AQ - 1) / AQ) * a.H * a.B;
+  const int slots = sms * ((PARTS == 1 || DUAL) ? 2 : 1);
+  // (bf16, d <= 32: one item per CTA measured 3 % faster than the persistent grid — its items are too short to amortise anything)
+  const bool persist = !(PARTS == 1 && DPAD == 32);
+  dim3 grid(persist && n_items > slots ? slots : n_items);
   return launch_pdl(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, grid, dim3(ATT_TC_THREADS), smem, s, 1, mQ, mK, mV, p);
 }
 
