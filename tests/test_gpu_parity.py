@@ -191,3 +191,23 @@ def test_single_speaker_and_acoustic_scale_vs_fp64_oracle():
     e = G.errs(mel, ref64)
     G.report(test="nspk1_scale2p5_shallow_unipc4_vs_fp64", **e)
     assert e["max_abs"] <= TOL_VS_FP64, e
+
+
+def test_config2_full_size_vs_fp64_gpu_oracle(gpu_model, state_dict):
+    """BASELINE configs[1] at its full size: B=64 x T=864, DPM-Solver++ 20 NFE, fp32-accurate mode, against the oracle
+    executed in fp64 on the same GPU (checker only).  Tolerance as stated by the north star: max-abs <= 1e-3."""
+    B, T = 64, 864
+    units, spk, noise, _, _ = O.synthetic_inputs(B, T)
+    mel = _run_cuda(gpu_model, units, spk, noise, [], None, "dpm-solver", 50, None)
+    sd64 = {k: v.double().cuda() for k, v in state_dict.items()}
+    outs = []
+    with torch.no_grad():
+        for b0 in range(0, B, 16):                      # the fp64 attention scores of 16 utterances are 0.8 GB per call
+            sl = slice(b0, b0 + 16)
+            outs.append(O.unit2mel_infer(sd64, O.DEFAULT_CFG, units[sl].cuda().double(), spk[sl].cuda(), noise[sl].cuda().double(),
+                                         "dpm-solver", 50).cpu())
+    ref64 = torch.cat(outs)
+    e = G.errs(mel, ref64)
+    G.report(test="config2_b64_t864_dpm20_vs_fp64_gpu_oracle", **e)
+    assert mel.shape == (B, T, 128) and torch.isfinite(mel).all()
+    assert e["max_abs"] <= TOL_VS_FP64, e
