@@ -221,3 +221,34 @@ def test_config2_full_size_vs_fp64_gpu_oracle(gpu_model, state_dict):
     G.report(test="config2_b64_t864_dpm20_vs_fp64_gpu_oracle", **e, ref_fp32_vs_fp64_first16=floor, ours_first16=G.errs(mel[:16], ref64[:16]))
     assert mel.shape == (B, T, 128) and torch.isfinite(mel).all()
     assert e["max_abs"] <= TOL_VS_FP64, e
+
+
+def test_config3_bf16_unipc10_full_length_vs_fp64_gpu_oracle(host_model, state_dict):
+    """BASELINE configs[2] shape on a B=8 subset: T=864, UniPC 10 NFE, bf16 mode; relative L2 <= 1e-2 vs the fp64 oracle
+    executed on the same GPU."""
+    gpu_bf16 = gpu_model_for(host_model, "bf16")
+    B, T = 8, 864
+    units, spk, noise, _, _ = O.synthetic_inputs(B, T)
+    mel = _run_cuda(gpu_bf16, units, spk, noise, [], None, "unipc", 100, None)
+    sd64 = {k: v.double().cuda() for k, v in state_dict.items()}
+    with torch.no_grad():
+        ref64 = O.unit2mel_infer(sd64, O.DEFAULT_CFG, units.cuda().double(), spk.cuda(), noise.cuda().double(), "unipc", 100).cpu()
+    e = G.errs(mel, ref64)
+    G.report(test="config3_bf16_unipc10_b8_t864_vs_fp64_gpu_oracle", **e)
+    assert e["rel_l2"] <= TOL_BF16_REL_L2, e
+
+
+def test_ddpm_100_ancestral_steps_vs_fp64_gpu_oracle(gpu_model, state_dict):
+    """BASELINE configs[4] in miniature: 100 consecutive ancestral DDPM steps (shallow start k_step=100, one injected
+    noise draw per step, x0 clamp) — the per-step fused solver kernel path — against the fp64 oracle on the GPU."""
+    B, T, K = 2, 40, 100
+    units, spk, noise, steps, gt = O.synthetic_inputs(B, T, n_step_noises=K, gt=True)
+    mel = _run_cuda(gpu_model, units, spk, noise, steps, gt, None, 1, K)
+    sd64 = {k: v.double().cuda() for k, v in state_dict.items()}
+    with torch.no_grad():
+        ref64 = O.unit2mel_infer(sd64, O.DEFAULT_CFG, units.cuda().double(), spk.cuda(), noise.cuda().double(), None, 1,
+                                 gt_spec=gt.cuda().double(), k_step=K, step_noises=[s.cuda().double() for s in steps]).cpu()
+    e = G.errs(mel, ref64)
+    G.report(test="ddpm100_shallow_b2_t40_vs_fp64_gpu_oracle", **e)
+    assert torch.isfinite(mel).all()
+    assert e["max_abs"] <= TOL_VS_FP64, e
