@@ -279,10 +279,14 @@ def run_ours(args):
         "share_of_step": gm["ms"] / tot_ms, "traffic": traffic, "traffic_source": traffic_src,
         "tensor_pipe_frac": achieved_tf * mma_per_product / peak_tf if precision != "fp32_ffma" else None,
     }
-    classes = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                   "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
-                   "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["flops"] == 0 else None}
-               for k, v in prof.items()}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    classes = {}
+    for k, v in prof.items():
+        tf = (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None
+        gbs = (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["flops"] == 0 else None
+        classes[k] = {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps, "tflops": tf, "gbs": gbs,
+                      # algorithmic bytes / time against the measured copy bandwidth (HBM-bound classes)
+                      "hbm_frac": None if gbs is None else gbs / hbm_peak}
 
     line = None
     if rank == 0:
