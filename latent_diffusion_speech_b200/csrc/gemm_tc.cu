@@ -63,6 +63,7 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 512;    // rings + per-warp stag
 
 struct TcParams {
   int rows, batches, tiles_per_batch, m_tiles, n_tiles, total_items;   // A: [batches][rows][parts*cin]; item = (M-tile group, N tile)
+  int blk_tiling, blks_per_batch, total_blks;   // flat tiling of batched convolutions in 32-row blocks (rows % 32 == 0)
   int cin, taps, pad, parts;
   int BN, na, nw, w_slot_bytes;         // ring depths (A slots, W slots)
   int nkb, kb_per_tap;                  // K blocks of TBK per plane (all taps) / per tap
@@ -405,10 +406,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int sa = 0, sw = 0;                        // next slot of each ring
       uint32_t pha = 0, phw = 0;
       const int w_row = (int)crank * (p.BN >> 1);
+      // Batched convolutions whose utterance length is a multiple of 32 frames are tiled over the FLAT sequence of
+      // 32-frame blocks (a 128-row tile = four blocks, possibly of two utterances; each block is its own TMA box, so the
+      // zero padding at the utterance edges is still out-of-bounds fill): 864-frame utterances then fill 432 tiles
+      // instead of 7 x 64 = 448, which is 3 rounds of the 74 CTA pairs instead of 4.
+      int blk_b[4], blk_t[4];
       auto load_a = [&](int col, int row, int b) {
         mbar_wait(a_empty(sa), pha ^ 1u);
         if (leader) mbar_expect_tx(a_full(sa), 2 * A_SLOT_BYTES);
-        tma_load_3d_pair(a_ring + sa * A_SLOT_BYTES, &mapA, mapa_u32(a_full(sa), 0), col, row, b);
+        const uint32_t dst = a_ring + sa * A_SLOT_BYTES, bar = mapa_u32(a_full(sa), 0);
+        if (p.blk_tiling) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tma_load_3d_pair(dst + q * (A_SLOT_BYTES / 4), &mapA, bar, col, blk_t[q] + row, blk_b[q]);
+        } else {
+          tma_load_3d_pair(dst, &mapA, bar, col, row, b);
+        }
         if (++sa == p.na) { sa = 0; pha ^= 1u; }
       };
       auto load_w = [&](int col, int n0) {
@@ -419,8 +431,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       };
       for (int item = cid; item < p.total_items; item += ncl) {
         const int nt = item % p.n_tiles, mt = (item / p.n_tiles) * 2 + (int)crank;
-        const int b = mt / p.tiles_per_batch;
-        const int t0 = (mt - b * p.tiles_per_batch) * TBM;
+        int b = mt / p.tiles_per_batch;
+        int t0 = (mt - b * p.tiles_per_batch) * TBM;
+        if (p.blk_tiling) {                      // rows passed to load_a become offsets (tap - pad) relative to each block
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int gb = mt * 4 + q;
+            blk_b[q] = gb < p.total_blks ? gb / p.blks_per_batch : p.batches;   // ghost block: out of bounds -> zeros
+            blk_t[q] = (gb % p.blks_per_batch) * 32;
+          }
+          b = 0; t0 = 0;
+        }
         const int n0 = nt * p.BN;
         int tap = 0, cb = 0;
         for (int kb = 0; kb < n1; ++kb) {
@@ -522,11 +543,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int local = 0;
     for (int item = cid; item < p.total_items; item += ncl, ++local) {
       const int nt = item % p.n_tiles, mt = (item / p.n_tiles) * 2 + (int)crank;
-      const int b = mt / p.tiles_per_batch;
-      const int t_blk = (mt - b * p.tiles_per_batch) * TBM + quarter * 32;     // first frame of this warp's 32 rows
       // the last pair may carry a ghost M tile (TMA zero fill, no stores)
-      e.nvalid = mt < p.m_tiles ? max(0, min(32, p.rows - t_blk)) : 0;
-      e.grow0 = (size_t)(mt < p.m_tiles ? b : 0) * p.rows + t_blk;
+      if (p.blk_tiling) {                        // this warp's 32 rows are block mt*4 + quarter of the flat block sequence
+        const int gb = mt * 4 + quarter;
+        e.nvalid = gb < p.total_blks ? 32 : 0;
+        e.grow0 = (size_t)(gb < p.total_blks ? gb : 0) * 32;
+      } else {
+        const int b = mt / p.tiles_per_batch;
+        const int t_blk = (mt - b * p.tiles_per_batch) * TBM + quarter * 32;     // first frame of this warp's 32 rows
+        e.nvalid = mt < p.m_tiles ? max(0, min(32, p.rows - t_blk)) : 0;
+        e.grow0 = (size_t)(mt < p.m_tiles ? b : 0) * p.rows + t_blk;
+      }
       const int buf = local & 1;
       mbar_wait(tmem_full_bar(buf), ((uint32_t)local >> 1) & 1u);
       tc_fence_after();
@@ -691,9 +718,11 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   p.nw = (SMEM_BUDGET - stage_bytes - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
   if (p.nw > MAX_SLOTS) p.nw = MAX_SLOTS;
   CUtensorMap mA, mW;
-  cudaError_t e = get_map(a.A, (uint64_t)a.a_parts * a.cin, (uint64_t)a.rows, (uint64_t)a.batches, TBM, &mA);
+  p.blk_tiling = (a.batches > 1 && a.rows % 32 == 0 && a.rows % TBM != 0) ? 1 : 0;
+  p.blks_per_batch = a.rows / 32; p.total_blks = p.blks_per_batch * a.batches;
+  cudaError_t e = get_map(a.A, (uint64_t)a.a_parts * a.cin, (uint64_t)a.rows, (uint64_t)a.batches, p.blk_tiling ? 32 : TBM, &mA);
   if (e != cudaSuccess) return e;
-  p.m_tiles = ((a.rows + TBM - 1) / TBM) * a.batches;
+  p.m_tiles = p.blk_tiling ? (p.total_blks + 3) / 4 : ((a.rows + TBM - 1) / TBM) * a.batches;
   const int csize = 2;                            // always a CTA pair; an odd M tile count leaves one ghost tile
   e = get_map(a.W, (uint64_t)a.taps * a.w_parts * a.cin, (uint64_t)a.N, 0, (uint32_t)(p.BN / csize), &mW);
   if (e != cudaSuccess) return e;

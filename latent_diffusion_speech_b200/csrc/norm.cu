@@ -111,6 +111,8 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int c1, const floa
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+// bf16 mode only (the result is rounded to bf16): ex2.approx + rcp.approx, ~4 ulp, a third of the instructions
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 // grid (ceil(T / slab), B); block = (C/4) * rpar threads: thread (v, r) owns channel quad v — its gamma / beta / scale /
 // shift live in registers — and frames r, r+rpar, ... of the [slab, C] slab, eight 16-byte loads in flight per thread
@@ -266,7 +268,10 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const float* __re
       o[0] = o[0] * (1.f + sc.x) + sf.x; o[1] = o[1] * (1.f + sc.y) + sf.y;
       o[2] = o[2] * (1.f + sc.z) + sf.z; o[3] = o[3] * (1.f + sc.w) + sf.w;
     }
-    if (silu) { o[0] = silu_f(o[0]); o[1] = silu_f(o[1]); o[2] = silu_f(o[2]); o[3] = silu_f(o[3]); }
+    if (silu) {
+      if (yb && parts == 1) { o[0] = silu_fast(o[0]); o[1] = silu_fast(o[1]); o[2] = silu_fast(o[2]); o[3] = silu_fast(o[3]); }
+      else { o[0] = silu_f(o[0]); o[1] = silu_f(o[1]); o[2] = silu_f(o[2]); o[3] = silu_f(o[3]); }
+    }
     if (yb) store_planes4(yb + row * (size_t)(parts * C), c, C, parts, o[0], o[1], o[2], o[3]);
     else *reinterpret_cast<float4*>(y + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
     if (rawb) store_planes4(rawb + row * (size_t)(parts * C), c, C, parts, xv.x, xv.y, xv.z, xv.w);

@@ -163,7 +163,8 @@ def test_tc_gemm_split_fp32_accuracy(M, N, K):
     assert e["max_abs"] <= 5e-5 * math.sqrt(K / 256), (e, ffma)
 
 
-@pytest.mark.parametrize("B,T,Cin,Cout,parts", [(2, 37, 256, 384, 1), (3, 100, 384, 128, 1), (2, 300, 640, 256, 3), (1, 864, 256, 256, 3)])
+@pytest.mark.parametrize("B,T,Cin,Cout,parts", [(2, 37, 256, 384, 1), (3, 100, 384, 128, 1), (2, 300, 640, 256, 3), (1, 864, 256, 256, 3),
+                                                  (3, 96, 256, 256, 3), (2, 864, 256, 256, 1), (5, 160, 384, 384, 3)])   # last three: flat 32-row block tiling
 def test_tc_conv3(B, T, Cin, Cout, parts):
     x = _rand(B, T, Cin, seed=38)
     w, b = _rand(Cout, Cin, 3, seed=39, scale=(3 * Cin) ** -0.5), _rand(Cout, seed=40)
