@@ -177,6 +177,12 @@ LDS_API int lds_op_groupnorm(const float* x1, int c1, const float* x2, int c2, i
 LDS_API int lds_op_groupnorm_fused(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
                            const float* gamma, const float* beta, const float* scale_shift, int silu, float* y,
                            void* stream);
+/* Cluster form of the single pass: the slab is split along time over a thread-block cluster of 1..8 CTAs that exchange
+ * their partial sums through distributed shared memory (<= ~40 KB per CTA, several CTAs per SM).  This is the form the
+ * sampler uses; LDS_ERR_UNSUPPORTED when an eighth of the slab exceeds 200 KB (the sampler then uses stats + apply). */
+LDS_API int lds_op_groupnorm_cluster(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
+                             const float* gamma, const float* beta, const float* scale_shift, int silu, float* y,
+                             void* stream);
 LDS_API int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
                      void* stream);
 /* Tensor-core (tcgen05/TMEM/TMA) form of lds_op_gemm on bf16 operands.

@@ -25,7 +25,7 @@ EXPORTS = [
     "lds_plan", "lds_cond", "lds_denoise", "lds_sample_begin", "lds_sample_steps", "lds_sample_end", "lds_sample",
     "lds_num_steps", "lds_workspace_bytes", "lds_kernel_launches", "lds_set_profiling", "lds_profile_num_classes",
     "lds_profile_class_name", "lds_profile_class_ms", "lds_profile_class_launches", "lds_profile_class_flops",
-    "lds_profile_class_bytes", "lds_op_gemm", "lds_op_attention", "lds_op_groupnorm", "lds_op_groupnorm_fused", "lds_op_layernorm",
+    "lds_profile_class_bytes", "lds_op_gemm", "lds_op_attention", "lds_op_groupnorm", "lds_op_groupnorm_fused", "lds_op_groupnorm_cluster", "lds_op_layernorm",
     "lds_op_split_cast", "lds_op_gemm_tc", "lds_op_qkv_attention_tc",
 ]
 
@@ -85,6 +85,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "lds_op_attention": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "lds_op_groupnorm": (i32, [vp, i32, vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, i32, vp, vp, vp]),
         "lds_op_groupnorm_fused": (i32, [vp, i32, vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, i32, vp, vp]),
+        "lds_op_groupnorm_cluster": (i32, [vp, i32, vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, i32, vp, vp]),
         "lds_op_layernorm": (i32, [vp, vp, vp, C.c_float, i32, i32, vp, vp]),
         "lds_op_split_cast": (i32, [vp, vp, C.c_int64, i32, i32, vp]),
         "lds_op_gemm_tc": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp]),

@@ -325,8 +325,14 @@ int run_gemm_tc(lds_handle* h, cudaStream_t s, const TcGemmArgs& g) {
 int run_gn_planes(lds_handle* h, cudaStream_t s, const float* x1, int c1, const float* x2, int c2, int T, const NormW& n,
                   float eps, const float* ss, int silu, __nv_bfloat16* yb, __nv_bfloat16* rawb) {
   const double elems = (double)h->B * T * (c1 + c2);
-  static const bool gn_fused = !(getenv("LDS_GN_FUSED") && atoi(getenv("LDS_GN_FUSED")) == 0);
-  if (gn_fused && (int64_t)h->B * h->cfg.norm_groups >= 148) {  // single pass when the slab of one (utterance, group) fits shared memory and there is a CTA per SM
+  // LDS_GN_MODE: 2 (default) cluster single-pass kernel; 1 one-CTA-per-(utterance, group) single pass; 0 stats + apply
+  static const int gn_mode = getenv("LDS_GN_MODE") ? atoi(getenv("LDS_GN_MODE")) : 2;
+  if (gn_mode == 2) {
+    const cudaError_t e = launch_gn_cluster(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, eps, n.g, n.b, ss, silu, nullptr, yb, h->parts, rawb, s);
+    if (e != cudaErrorNotSupported)
+      return launched(h, s, PC_GN_APPLY, 0, (4.0 + 2.0 * h->parts * (rawb ? 2 : 1)) * elems, e, "gn_cluster");
+  }
+  if (gn_mode == 1 && (int64_t)h->B * h->cfg.norm_groups >= 148) {  // single pass when the slab of one (utterance, group) fits shared memory and there is a CTA per SM
     const cudaError_t e = launch_gn_fused(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, eps, n.g, n.b, ss, silu, nullptr, yb, h->parts, rawb, s);
     if (e != cudaErrorNotSupported)
       return launched(h, s, PC_GN_APPLY, 0, (4.0 + 2.0 * h->parts * (rawb ? 2 : 1)) * elems, e, "gn_fused");
@@ -1278,6 +1284,14 @@ int lds_op_groupnorm_fused(const float* x1, int c1, const float* x2, int c2, int
                                              (cudaStream_t)stream);
   if (e == cudaErrorNotSupported) return fail(LDS_ERR_UNSUPPORTED, "lds_op_groupnorm_fused: the [T, C/groups] slab does not fit shared memory");
   return op_status(e, "lds_op_groupnorm_fused");
+}
+int lds_op_groupnorm_cluster(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps, const float* gamma,
+                             const float* beta, const float* scale_shift, int silu, float* y, void* stream) {
+  if (!x1 || !gamma || !beta || !y || (c2 > 0 && !x2)) return fail(LDS_ERR_INVALID, "lds_op_groupnorm_cluster: null tensor");
+  const cudaError_t e = lds::launch_gn_cluster(x1, c1, x2, c2, B, T, groups, eps, gamma, beta, scale_shift, silu, y, nullptr, 1, nullptr,
+                                               (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported) return fail(LDS_ERR_UNSUPPORTED, "lds_op_groupnorm_cluster: an eighth of the [T, C/groups] slab does not fit shared memory");
+  return op_status(e, "lds_op_groupnorm_cluster");
 }
 int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y, void* stream) {
   if (!x || !gamma || !beta || !y) return fail(LDS_ERR_INVALID, "lds_op_layernorm: null tensor");

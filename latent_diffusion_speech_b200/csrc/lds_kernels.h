@@ -136,6 +136,11 @@ cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, in
 cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
                             const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
                             int parts, __nv_bfloat16* rawb, cudaStream_t s);
+// cluster variant: the slab is split along time over a thread-block cluster of 1..8 CTAs (partials exchanged through
+// distributed shared memory) — small CTAs, several per SM, and slabs up to 8 x 200 KB stay single-pass
+cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
+                              const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
+                              int parts, __nv_bfloat16* rawb, cudaStream_t s);
 //  (yb != nullptr: write bf16 operand planes [B*T, parts*C] instead of fp32 y; rawb: also copy the un-normalised
 //   concat input as planes — the A operand of the 1x1 shortcut convolution)
 

@@ -278,6 +278,191 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const float* __re
   }
 }
 
+// Cluster form of the single-pass GroupNorm: the [T, C/G] slab of one (utterance, group) is split along time over the
+// CL CTAs of a thread-block cluster, so that a CTA holds <= ~40 KB and five or more CTAs in different phases (loading /
+// reducing / storing) share an SM — loads and stores overlap instead of alternating, and slabs that do not fit one SM
+// (640-channel concats, T = 2584) stay single-pass.  The per-CTA partial sums travel through distributed shared
+// memory: every CTA reads the CL partials in rank order (identical mean / rstd in all of them), exact two-pass mean /
+// M2 as before.  CL depends on (T, C/G) only, never on the batch: results are batch-composition invariant.
+constexpr int GNC_THREADS = 256;
+__device__ __forceinline__ uint32_t gnc_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t gnc_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// Relaxed arrive: the one thread that published data fences first (fence + relaxed arrive = release); a
+// barrier.cluster.arrive.release in every thread costs an ERRBAR / membar per warp (ncu: 9 % of the stall samples).
+__device__ __forceinline__ void gnc_cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gnc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gnc_publish_fence() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ float gnc_ld_peer(const float* p, uint32_t rank) {   // *p of CTA `rank` of this cluster
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+// x * sigmoid(x) with the reciprocal from rcp.approx + one Newton step (<= 1 ulp) instead of the IEEE division and its
+// slow-path branch; x is clamped at -80 so that 1 + e^-x stays finite (silu(-80) ~ -1e-33 either way).
+__device__ __forceinline__ float silu_newton(float x) {
+  const float t = 1.f + expf(-fmaxf(x, -80.f));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  r = fmaf(r, fmaf(-t, r, 1.f), r);
+  return x * r;
+}
+template <int PARTS>
+__device__ __forceinline__ void store_planes4_ct(uint2* dst, int plane_stride_u2, float v0, float v1, float v2, float v3) {
+#pragma unroll
+  for (int p = 0; p < PARTS; ++p) {
+    uint2 w;
+    if (p == PARTS - 1) {
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(v1), "f"(v0));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(v3), "f"(v2));
+    } else {
+      w.x = planes_split_pair(v0, v1);
+      w.y = planes_split_pair(v2, v3);
+    }
+    dst[p * plane_stride_u2] = w;
+  }
+}
+// PARTS: 0 fp32 output y, 1 / 3 bf16 operand planes yb.  SILU / SS (scale-shift) / RAW (also copy x as planes) are
+// compile-time so that the three loops are branch-free; all addresses advance by constant strides (the first version
+// spent 3/4 of its instructions on index arithmetic and flag tests: 58 instructions per element, issue-bound).
+template <int PARTS, bool SILU, bool SS, bool RAW>
+__global__ void __launch_bounds__(GNC_THREADS, 4) gn_cluster_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2,
+                                                                    int T, int groups, int tc, float eps, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, const float* __restrict__ ss,
+                                                                    float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+                                                                    __nv_bfloat16* __restrict__ rawb) {
+  extern __shared__ float4 slab[];               // [tc][q]: frames [rank*tc, rank*tc + tc) of the group
+  __shared__ float red[GNC_THREADS / 32];
+  __shared__ float s_bcast;
+  __shared__ float s_part[2];                    // this CTA's partial sum / partial M2, read by its cluster peers
+  pdl_trigger();
+  const uint32_t CL = gnc_nctarank(), rank = gnc_ctarank();
+  const int C = c1 + c2, cg = C / groups, q = cg >> 2;
+  const int g = blockIdx.x / CL, b = blockIdx.y;
+  const int t_lo = min(T, (int)rank * tc), nt = min(T, t_lo + tc) - t_lo;
+  const int R = GNC_THREADS / q;                 // frames per pass over the block's threads
+  const int v = threadIdx.x % q, r0 = threadIdx.x / q;
+  const int c = g * cg + 4 * v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool active = r0 < R;
+  const size_t row0 = (size_t)b * T + t_lo;
+  // the virtual concat [x1 | x2] resolves per thread (its channel quad is fixed), not per load
+  const float* src = c < c1 ? x1 + c : x2 + (c - c1);
+  const int ld = c < c1 ? c1 : c2;
+  const int sstep = R * q;                       // slab step (float4) between two frames of this thread
+  pdl_wait();
+  auto block_sum = [&](float val) {
+    val = warp_sum(val);
+    if (lane == 0) red[warp] = val;
+    __syncthreads();
+    if (warp == 0) {
+      float t = lane < GNC_THREADS / 32 ? red[lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) s_bcast = t;
+    }
+    __syncthreads();
+    return s_bcast;
+  };
+  auto cluster_total = [&](int slot, float mine) {   // sum of the CL per-CTA partials, same order in every CTA
+    if (threadIdx.x == 0) { s_part[slot] = mine; gnc_publish_fence(); }
+    gnc_cluster_arrive();
+    gnc_cluster_wait();
+    float tot = 0.f;
+    for (uint32_t r = 0; r < CL; ++r) tot += gnc_ld_peer(&s_part[slot], r);
+    return tot;
+  };
+  float sum = 0.f;
+  if (active) {
+    constexpr int U = 8;                         // loads in flight per thread
+    const float4* p = reinterpret_cast<const float4*>(src + (row0 + r0) * (size_t)ld);
+    const size_t pstep = (size_t)R * (ld >> 2);
+    float4* sp = slab + r0 * q + v;
+    int t = r0;
+    for (; t + (U - 1) * R < nt; t += U * R) {   // full batches: no predicates
+      float4 xv[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) xv[i] = __ldg(p + i * pstep);
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        sp[i * sstep] = xv[i];
+        sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+      }
+      p += U * pstep;
+      sp += U * sstep;
+    }
+    if (t < nt) {                                // tail batch
+      float4 xv[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i)
+        if (t + i * R < nt) xv[i] = __ldg(p + i * pstep);
+#pragma unroll
+      for (int i = 0; i < U; ++i)
+        if (t + i * R < nt) {
+          sp[i * sstep] = xv[i];
+          sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        }
+    }
+  }
+  const float n = (float)T * (float)cg;
+  const float mean = cluster_total(0, block_sum(sum)) / n;
+  float m2 = 0.f;
+  if (active) {
+    const float4* sp = slab + r0 * q + v;
+#pragma unroll 4
+    for (int t = r0; t < nt; t += R, sp += sstep) {
+      const float4 xv = *sp;
+      const float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
+      m2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  }
+  const float rstd = rsqrtf(cluster_total(1, block_sum(m2)) / n + eps);
+  gnc_cluster_arrive();                          // this CTA has read its peers' partials; waited for before exit
+  if (active) {
+    // o = (x - mean) * A + Bc with A = rstd*gamma [*(1+scale)], Bc = beta [*(1+scale) + shift]
+    float4 A = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    float4 Bc = __ldg(reinterpret_cast<const float4*>(beta + c));
+    A.x *= rstd; A.y *= rstd; A.z *= rstd; A.w *= rstd;
+    if (SS) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
+      const float4 sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+      const float k0 = 1.f + sc.x, k1 = 1.f + sc.y, k2 = 1.f + sc.z, k3 = 1.f + sc.w;
+      A.x *= k0; A.y *= k1; A.z *= k2; A.w *= k3;
+      Bc.x = fmaf(Bc.x, k0, sf.x); Bc.y = fmaf(Bc.y, k1, sf.y); Bc.z = fmaf(Bc.z, k2, sf.z); Bc.w = fmaf(Bc.w, k3, sf.w);
+    }
+    const float4* sp = slab + r0 * q + v;
+    constexpr int PW = PARTS > 0 ? PARTS : 1;
+    const int plane_u2 = C >> 2;                                   // one plane of a row in uint2 (4 x bf16) units
+    const size_t ostep = (size_t)R * (PARTS > 0 ? PW * (C >> 2) : (C >> 2));   // uint2 units (planes) / float4 units (fp32)
+    const size_t o0 = (row0 + r0) * (size_t)(PARTS > 0 ? PW * (C >> 2) : (C >> 2)) + (c >> 2);
+    uint2* ybp = PARTS > 0 ? reinterpret_cast<uint2*>(yb) + o0 : nullptr;
+    uint2* rbp = (PARTS > 0 && RAW) ? reinterpret_cast<uint2*>(rawb) + o0 : nullptr;
+    float4* yp = PARTS == 0 ? reinterpret_cast<float4*>(y) + o0 : nullptr;
+#pragma unroll 2
+    for (int t = r0; t < nt; t += R, sp += sstep) {
+      const float4 xv = *sp;
+      float o0v = fmaf(xv.x - mean, A.x, Bc.x), o1v = fmaf(xv.y - mean, A.y, Bc.y), o2v = fmaf(xv.z - mean, A.z, Bc.z),
+            o3v = fmaf(xv.w - mean, A.w, Bc.w);
+      if (SILU) {
+        if (PARTS == 1) { o0v = silu_fast(o0v); o1v = silu_fast(o1v); o2v = silu_fast(o2v); o3v = silu_fast(o3v); }
+        else { o0v = silu_newton(o0v); o1v = silu_newton(o1v); o2v = silu_newton(o2v); o3v = silu_newton(o3v); }
+      }
+      if (PARTS > 0) {
+        store_planes4_ct<PW>(ybp, plane_u2, o0v, o1v, o2v, o3v);
+        ybp += ostep;
+        if (RAW) {
+          store_planes4_ct<PW>(rbp, plane_u2, xv.x, xv.y, xv.z, xv.w);
+          rbp += ostep;
+        }
+      } else {
+        *yp = make_float4(o0v, o1v, o2v, o3v);
+        yp += ostep;
+      }
+    }
+  }
+  gnc_cluster_wait();                            // no CTA of the cluster exits while a peer may still read its s_part
+}
+
 // One warp per LN_ROWS consecutive rows (C <= 32*4*LN_MAXV, LN_MAXV instantiated for C <= 256 / 384 / 512): all loads of the rows are issued before the first
 // reduction, so that LN_ROWS x C x 4 bytes per warp are in flight (bytes in flight, not issue, bound this kernel).
 constexpr int LN_ROWS = 4;
@@ -342,6 +527,77 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+
+// LayerNorm fast path for C == 128 * NV (the denoiser's 256 / 384 / 512): one warp per ROWS consecutive rows, every
+// load of the rows issued before the first reduction, the reductions of the rows interleaved (independent shuffle
+// chains), gamma / beta staged in shared memory before the dependency wait (they are weights), compile-time plane count.
+// ~12 instructions per element and <= 64 registers (the generic kernel: 31 and 128 registers -> two blocks per SM).
+template <int NV, int PARTS, int ROWS>
+__global__ void __launch_bounds__(256, 4) layernorm_fast_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps, int rows,
+                                                                float* __restrict__ y, __nv_bfloat16* __restrict__ yb) {
+  constexpr int C = 128 * NV, V = 32 * NV;
+  __shared__ float4 s_g[V], s_b[V];
+  pdl_trigger();
+  if (threadIdx.x < V) {
+    s_g[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(gamma) + threadIdx.x);
+    s_b[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(beta) + threadIdx.x);
+  }
+  pdl_wait();
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int row0 = warp * ROWS;
+  if (row0 >= rows) return;
+  float4 v[ROWS][NV];
+  const float4* src = reinterpret_cast<const float4*>(x) + (size_t)row0 * V + lane;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const bool ok = row0 + r < rows;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[r][i] = ok ? __ldg(src + r * V + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float sum[ROWS], sq[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    sum[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sum[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], off);
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    sum[r] = sum[r] / (float)C;                   // mean
+    sq[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[r][i].x -= sum[r]; v[r][i].y -= sum[r]; v[r][i].z -= sum[r]; v[r][i].w -= sum[r];
+      sq[r] += (v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y) + (v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], off);
+  constexpr int PW = PARTS > 0 ? PARTS : 1;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (row0 + r >= rows) break;
+    const float rstd = rsqrtf(sq[r] / (float)C + eps);
+    const size_t row = (size_t)(row0 + r);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 g = s_g[lane + 32 * i], be = s_b[lane + 32 * i];
+      const float o0 = v[r][i].x * rstd * g.x + be.x, o1 = v[r][i].y * rstd * g.y + be.y, o2 = v[r][i].z * rstd * g.z + be.z,
+                  o3 = v[r][i].w * rstd * g.w + be.w;
+      if (PARTS > 0) store_planes4_ct<PW>(reinterpret_cast<uint2*>(yb) + row * (PW * V) + lane + 32 * i, V, o0, o1, o2, o3);
+      else reinterpret_cast<float4*>(y)[row * V + lane + 32 * i] = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
 }  // namespace
 
 // Frames per statistics chunk: 64 when that still gives several waves of blocks (the merge phase of a block is then
@@ -397,9 +653,72 @@ cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, in
                     silu, y, yb, parts, rawb);
 }
 
+// Cluster single-pass GroupNorm.  cudaErrorNotSupported when even an eighth of the slab does not fit shared memory.
+namespace {
+template <int PARTS, bool SILU, bool SS, bool RAW>
+cudaError_t launch_gnc(dim3 grid, size_t smem, int cl, cudaStream_t s, const float* x1, int c1, const float* x2, int c2, int T, int groups,
+                       int tc, float eps, const float* gamma, const float* beta, const float* ss, float* y, __nv_bfloat16* yb,
+                       __nv_bfloat16* rawb) {
+  static unsigned long long configured = 0;
+  if (first_use_on_this_device(configured)) {
+    cudaError_t e = cudaFuncSetAttribute(gn_cluster_kernel<PARTS, SILU, SS, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gn_cluster_kernel<PARTS, SILU, SS, RAW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+  }
+  return launch_pdl(gn_cluster_kernel<PARTS, SILU, SS, RAW>, grid, dim3(GNC_THREADS), smem, s, cl, x1, c1, x2, c2, T, groups, tc, eps, gamma,
+                    beta, ss, y, yb, rawb);
+}
+template <int PARTS, typename... A>
+cudaError_t launch_gnc_flags(bool silu, bool has_ss, bool raw, A... a) {
+  if (PARTS == 0) raw = false;
+  const int f = (silu ? 4 : 0) | (has_ss ? 2 : 0) | (raw ? 1 : 0);
+  switch (f) {
+    case 0: return launch_gnc<PARTS, false, false, false>(a...);
+    case 1: return launch_gnc<PARTS, false, false, PARTS != 0>(a...);
+    case 2: return launch_gnc<PARTS, false, true, false>(a...);
+    case 3: return launch_gnc<PARTS, false, true, PARTS != 0>(a...);
+    case 4: return launch_gnc<PARTS, true, false, false>(a...);
+    case 5: return launch_gnc<PARTS, true, false, PARTS != 0>(a...);
+    case 6: return launch_gnc<PARTS, true, true, false>(a...);
+    default: return launch_gnc<PARTS, true, true, PARTS != 0>(a...);
+  }
+}
+}  // namespace
+cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
+                              const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
+                              int parts, __nv_bfloat16* rawb, cudaStream_t s) {
+  const int C = c1 + c2;
+  if (C % (4 * groups) || c1 % 4 || groups > 32 || B <= 0 || T <= 0) return cudaErrorInvalidValue;
+  if (yb ? (parts != 1 && parts != 3) : (y == nullptr)) return cudaErrorInvalidValue;
+  const int cg = C / groups, q = cg / 4;
+  if (q > GNC_THREADS) return cudaErrorNotSupported;
+  int cl = 1;                                    // a function of (T, cg) only: batch-composition invariance
+  while (cl < 8 && (size_t)((T + cl - 1) / cl) * cg * sizeof(float) > 40 * 1024) cl *= 2;
+  const int tc = (T + cl - 1) / cl;
+  const size_t smem = (size_t)tc * cg * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorNotSupported;
+  const dim3 grid(groups * cl, B);
+  const bool raw = yb && rawb;
+  if (!yb) return launch_gnc_flags<0>(silu != 0, ss != nullptr, false, grid, smem, cl, s, x1, c1, x2, c2, T, groups, tc, eps, gamma, beta, ss, y, yb, rawb);
+  if (parts == 1) return launch_gnc_flags<1>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, tc, eps, gamma, beta, ss, y, yb, rawb);
+  return launch_gnc_flags<3>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, tc, eps, gamma, beta, ss, y, yb, rawb);
+}
+
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
                              __nv_bfloat16* yb, int parts, cudaStream_t s) {
   if (C % 4 || C > 512) return cudaErrorInvalidValue;
+  if (yb && parts != 1 && parts != 3) return cudaErrorInvalidValue;
+  if (C == 256 || C == 384 || C == 512) {        // the denoiser's widths: specialised kernel
+    const int pk = yb ? parts : 0;
+    auto go = [&](auto kernel, int rows_per_warp) {
+      const int rows_per_block = 8 * rows_per_warp;
+      return launch_pdl(kernel, dim3((rows + rows_per_block - 1) / rows_per_block), dim3(256), 0, s, 1, x, gamma, beta, eps, rows, y, yb);
+    };
+    if (C == 256) return pk == 0 ? go(layernorm_fast_kernel<2, 0, 4>, 4) : pk == 1 ? go(layernorm_fast_kernel<2, 1, 4>, 4) : go(layernorm_fast_kernel<2, 3, 4>, 4);
+    if (C == 384) return pk == 0 ? go(layernorm_fast_kernel<3, 0, 2>, 2) : pk == 1 ? go(layernorm_fast_kernel<3, 1, 2>, 2) : go(layernorm_fast_kernel<3, 3, 2>, 2);
+    return pk == 0 ? go(layernorm_fast_kernel<4, 0, 2>, 2) : pk == 1 ? go(layernorm_fast_kernel<4, 1, 2>, 2) : go(layernorm_fast_kernel<4, 3, 2>, 2);
+  }
   const int warps_per_block = 8, rows_per_block = warps_per_block * LN_ROWS;
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
   const dim3 g(grid), b(warps_per_block * 32);

@@ -85,6 +85,15 @@ def op_groupnorm_fused(x1, x2, B, T, groups, eps, gamma, beta, ss=None, silu=0):
     return y
 
 
+def op_groupnorm_cluster(x1, x2, B, T, groups, eps, gamma, beta, ss=None, silu=0):
+    c1 = x1.shape[-1]
+    c2 = 0 if x2 is None else x2.shape[-1]
+    y = torch.empty(B * T, c1 + c2, device=x1.device, dtype=torch.float32)
+    check(lib().lds_op_groupnorm_cluster(ptr(x1), c1, ptr(x2), c2, B, T, groups, float(eps), ptr(gamma), ptr(beta), ptr(ss), silu,
+                                         ptr(y), stream()), "lds_op_groupnorm_cluster")
+    return y
+
+
 def op_layernorm(x, gamma, beta, eps=1e-5):
     y = torch.empty_like(x)
     check(lib().lds_op_layernorm(ptr(x), ptr(gamma), ptr(beta), float(eps), x.shape[0], x.shape[1], ptr(y), stream()),
