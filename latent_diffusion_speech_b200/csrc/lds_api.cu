@@ -1290,7 +1290,7 @@ int lds_op_groupnorm_cluster(const float* x1, int c1, const float* x2, int c2, i
   if (!x1 || !gamma || !beta || !y || (c2 > 0 && !x2)) return fail(LDS_ERR_INVALID, "lds_op_groupnorm_cluster: null tensor");
   const cudaError_t e = lds::launch_gn_cluster(x1, c1, x2, c2, B, T, groups, eps, gamma, beta, scale_shift, silu, y, nullptr, 1, nullptr,
                                                (cudaStream_t)stream);
-  if (e == cudaErrorNotSupported) return fail(LDS_ERR_UNSUPPORTED, "lds_op_groupnorm_cluster: an eighth of the [T, C/groups] slab does not fit shared memory");
+  if (e == cudaErrorNotSupported) return fail(LDS_ERR_UNSUPPORTED, "lds_op_groupnorm_cluster: two buffers of an eighth of the [T, C/groups] slab do not fit shared memory");
   return op_status(e, "lds_op_groupnorm_cluster");
 }
 int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y, void* stream) {

@@ -10,6 +10,7 @@
 //   nn.LayerNorm(C)                        attention.py:83,102,118
 #include "lds_kernels.h"
 #include "planes.cuh"
+#include <algorithm>
 
 namespace lds {
 namespace {
@@ -29,6 +30,18 @@ __device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
   return r;
 }
 
+
+// branch-free variant (empty partials allowed), approximate reciprocal: f only weights the mean correction
+__device__ __forceinline__ Wf wf_merge_fast(Wf a, Wf b) {
+  const float n = a.n + b.n;
+  const float f = n > 0.f ? __fdividef(b.n, n) : 0.f;
+  const float d = b.mean - a.mean;
+  Wf r;
+  r.n = n;
+  r.mean = fmaf(d, f, a.mean);
+  r.m2 = a.m2 + b.m2 + d * d * a.n * f;
+  return r;
+}
 
 __device__ __forceinline__ float4 load_cat(const float* x1, int c1, const float* x2, int c2, size_t row, int c) {
   // channel c of the virtual concat [x1 | x2]; c and c1 are multiples of 4
@@ -284,7 +297,7 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const float* __re
 // (640-channel concats, T = 2584) stay single-pass.  The per-CTA partial sums travel through distributed shared
 // memory: every CTA reads the CL partials in rank order (identical mean / rstd in all of them), exact two-pass mean /
 // M2 as before.  CL depends on (T, C/G) only, never on the batch: results are batch-composition invariant.
-constexpr int GNC_THREADS = 256;
+constexpr int GNC_THREADS = 128;   // 13.5 instead of 6.75 channel quads per thread and item at T = 864: the per-item fixed cost halves
 __device__ __forceinline__ uint32_t gnc_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t gnc_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 // Relaxed arrive: the one thread that published data fences first (fence + relaxed arrive = release); a
@@ -323,144 +336,185 @@ __device__ __forceinline__ void store_planes4_ct(uint2* dst, int plane_stride_u2
     dst[p * plane_stride_u2] = w;
   }
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // PARTS: 0 fp32 output y, 1 / 3 bf16 operand planes yb.  SILU / SS (scale-shift) / RAW (also copy x as planes) are
-// compile-time so that the three loops are branch-free; all addresses advance by constant strides (the first version
-// spent 3/4 of its instructions on index arithmetic and flag tests: 58 instructions per element, issue-bound).
+// compile-time so that the loops are branch-free; all addresses advance by constant strides (the first version spent
+// 3/4 of its instructions on index arithmetic and flag tests: 58 instructions per element).
+// Persistent and double-buffered: cluster k handles the (utterance, group) items k, k + n_clusters, ...; the slab of the
+// next item streams into the other shared-memory buffer with cp.async (no registers) while the current one is reduced,
+// normalised and stored — without that, the CTAs of an SM run their load / barrier / store phases in lockstep and
+// HBM idles during the barriers (measured 3.7 TB/s effective whatever the instruction count).
 template <int PARTS, bool SILU, bool SS, bool RAW>
-__global__ void __launch_bounds__(GNC_THREADS, 4) gn_cluster_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2,
-                                                                    int T, int groups, int tc, float eps, const float* __restrict__ gamma,
-                                                                    const float* __restrict__ beta, const float* __restrict__ ss,
-                                                                    float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
-                                                                    __nv_bfloat16* __restrict__ rawb) {
-  extern __shared__ float4 slab[];               // [tc][q]: frames [rank*tc, rank*tc + tc) of the group
-  __shared__ float red[GNC_THREADS / 32];
-  __shared__ float s_bcast;
-  __shared__ float s_part[2];                    // this CTA's partial sum / partial M2, read by its cluster peers
+__global__ void __launch_bounds__(GNC_THREADS, 8) gn_cluster_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2,
+                                                                    int T, int groups, int n_items, int tc, float eps,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    const float* __restrict__ ss, float* __restrict__ y,
+                                                                    __nv_bfloat16* __restrict__ yb, __nv_bfloat16* __restrict__ rawb) {
+  extern __shared__ float4 slab[];               // [2][tc][q]: frames [rank*tc, rank*tc + tc) of the group, two items
+  __shared__ float red[GNC_THREADS / 32][3];     // per-warp (count, mean, M2)
+  __shared__ float s_part[2][3];                 // this CTA's (count, mean, M2), read by its cluster peers; per item parity
   pdl_trigger();
   const uint32_t CL = gnc_nctarank(), rank = gnc_ctarank();
   const int C = c1 + c2, cg = C / groups, q = cg >> 2;
-  const int g = blockIdx.x / CL, b = blockIdx.y;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
   const int t_lo = min(T, (int)rank * tc), nt = min(T, t_lo + tc) - t_lo;
   const int R = GNC_THREADS / q;                 // frames per pass over the block's threads
   const int v = threadIdx.x % q, r0 = threadIdx.x / q;
-  const int c = g * cg + 4 * v;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool active = r0 < R;
-  const size_t row0 = (size_t)b * T + t_lo;
-  // the virtual concat [x1 | x2] resolves per thread (its channel quad is fixed), not per load
-  const float* src = c < c1 ? x1 + c : x2 + (c - c1);
-  const int ld = c < c1 ? c1 : c2;
   const int sstep = R * q;                       // slab step (float4) between two frames of this thread
+  const int buf_f4 = tc * q;                     // one slab buffer in float4
+  const uint32_t slab_u32 = (uint32_t)__cvta_generic_to_shared(slab);
+  // streams the frames of item `item` owned by this thread into buffer `buf`
+  const uint32_t dst0 = slab_u32 + (uint32_t)(r0 * q + v) * 16u, dstep = (uint32_t)sstep * 16u;
+  const int nfr = (active && r0 < nt) ? (nt - r0 + R - 1) / R : 0;   // frames of this thread in every item
+  auto prefetch = [&](int item, int buf) {
+    if (nfr > 0) {
+      const int g = item % groups, b = item / groups;
+      const int c = g * cg + 4 * v;
+      // the virtual concat [x1 | x2] resolves per thread (its channel quad is fixed), not per load
+      const float* src = c < c1 ? x1 + c : x2 + (c - c1);
+      const int ld = c < c1 ? c1 : c2;
+      const char* p = reinterpret_cast<const char*>(src + ((size_t)b * T + t_lo + r0) * (size_t)ld);
+      const size_t pstep = (size_t)R * ld * sizeof(float);
+      uint32_t dst = dst0 + (uint32_t)(buf * buf_f4) * 16u;
+#pragma unroll 4
+      for (int i = 0; i < nfr; ++i, p += pstep, dst += dstep) cp_async16(dst, p);
+    }
+    cp_async_commit();
+  };
+  const float n = (float)T * (float)cg;
+  constexpr int PW = PARTS > 0 ? PARTS : 1;
+  const int plane_u2 = C >> 2;                   // one plane of a row in uint2 (4 x bf16) units
+  const int orow = PARTS > 0 ? PW * (C >> 2) : (C >> 2);   // one output row in uint2 (planes) / float4 (fp32) units
+  const size_t ostep = (size_t)R * orow;
   pdl_wait();
-  auto block_sum = [&](float val) {
-    val = warp_sum(val);
-    if (lane == 0) red[warp] = val;
-    __syncthreads();
-    if (warp == 0) {
-      float t = lane < GNC_THREADS / 32 ? red[lane] : 0.f;
-      t = warp_sum(t);
-      if (lane == 0) s_bcast = t;
+  if (cluster_id < n_items) prefetch(cluster_id, 0);
+  int buf = 0;
+  for (int item = cluster_id; item < n_items; item += n_clusters, buf ^= 1) {
+    const int g = item % groups, b = item / groups;
+    const int c = g * cg + 4 * v;
+    cp_async_wait_all();
+    __syncthreads();                             // slab[buf] complete and visible; every thread is done with slab[buf ^ 1]
+    if (item + n_clusters < n_items) prefetch(item + n_clusters, buf ^ 1);
+    // coefficients of this thread's channel quad: requested now, needed after the two reductions
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), Bc = A, sc = A, sf = A;
+    if (active) {
+      A = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      Bc = __ldg(reinterpret_cast<const float4*>(beta + c));
+      if (SS) {
+        sc = __ldg(reinterpret_cast<const float4*>(ss + c));
+        sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+      }
+    }
+    const float4* sp0 = slab + buf * buf_f4 + r0 * q + v;
+    // One exchange per item.  Each warp takes the mean of its lanes' first channel quads as a pivot k (within
+    // sigma/sqrt(128) of the mean: the shifted moments below lose no bits), accumulates sum(x-k) and sum((x-k)^2) in ONE
+    // pass over shared memory, and turns them into an exact-enough (count, mean, M2) triple; the 4 warp triples and then
+    // the CL CTA triples merge with the count-weighted Chan formula (one shared-memory hop, one cluster hop).  The
+    // first versions (two block sums + two cluster barriers, then a per-thread Chan tree) spent more instructions on
+    // the reductions than on the normalisation itself: 44 instructions per element, issue-bound (ncu).
+    float s1 = 0.f, s2 = 0.f, k = 0.f;
+    {
+      float pv = 0.f;
+      if (nfr > 0) { const float4 x0 = *sp0; pv = (x0.x + x0.y) + (x0.z + x0.w); }
+      const float cntl = nfr > 0 ? 4.f : 0.f;
+      const float pvs = warp_sum(pv), cnts = warp_sum(cntl);
+      k = cnts > 0.f ? pvs / cnts : 0.f;
+    }
+    {
+      const float4* sp = sp0;
+#pragma unroll 4
+      for (int i = 0; i < nfr; ++i, sp += sstep) {
+        const float4 xv = *sp;
+        const float d0 = xv.x - k, d1 = xv.y - k, d2 = xv.z - k, d3 = xv.w - k;
+        s1 += (d0 + d1) + (d2 + d3);
+        s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      }
+    }
+    float nw = 4.f * (float)nfr;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+      nw += __shfl_xor_sync(0xffffffffu, nw, off);
+    }
+    if (lane == 0) {
+      const float dm = nw > 0.f ? s1 / nw : 0.f;           // mean - k of this warp's elements
+      red[warp][0] = nw; red[warp][1] = k + dm; red[warp][2] = fmaxf(s2 - s1 * dm, 0.f);
     }
     __syncthreads();
-    return s_bcast;
-  };
-  auto cluster_total = [&](int slot, float mine) {   // sum of the CL per-CTA partials, same order in every CTA
-    if (threadIdx.x == 0) { s_part[slot] = mine; gnc_publish_fence(); }
+    const int par = buf;                         // s_part slot alternates per item (a fast peer may already publish the next item)
+    if (warp == 0) {
+      Wf w{0.f, 0.f, 0.f};
+      if (lane < GNC_THREADS / 32) { w.n = red[lane][0]; w.mean = red[lane][1]; w.m2 = red[lane][2]; }
+#pragma unroll
+      for (int off = GNC_THREADS / 64; off > 0; off >>= 1) {
+        Wf o;
+        o.n = __shfl_xor_sync(0xffffffffu, w.n, off);
+        o.mean = __shfl_xor_sync(0xffffffffu, w.mean, off);
+        o.m2 = __shfl_xor_sync(0xffffffffu, w.m2, off);
+        w = wf_merge_fast(w, o);
+      }
+      if (lane == 0) {
+        s_part[par][0] = w.n; s_part[par][1] = w.mean; s_part[par][2] = w.m2;
+        gnc_publish_fence();
+      }
+    }
     gnc_cluster_arrive();
     gnc_cluster_wait();
-    float tot = 0.f;
-    for (uint32_t r = 0; r < CL; ++r) tot += gnc_ld_peer(&s_part[slot], r);
-    return tot;
-  };
-  float sum = 0.f;
-  if (active) {
-    constexpr int U = 8;                         // loads in flight per thread
-    const float4* p = reinterpret_cast<const float4*>(src + (row0 + r0) * (size_t)ld);
-    const size_t pstep = (size_t)R * (ld >> 2);
-    float4* sp = slab + r0 * q + v;
-    int t = r0;
-    for (; t + (U - 1) * R < nt; t += U * R) {   // full batches: no predicates
-      float4 xv[U];
-#pragma unroll
-      for (int i = 0; i < U; ++i) xv[i] = __ldg(p + i * pstep);
-#pragma unroll
-      for (int i = 0; i < U; ++i) {
-        sp[i * sstep] = xv[i];
-        sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    Wf tot{0.f, 0.f, 0.f};
+    for (uint32_t r = 0; r < CL; ++r) {          // rank order: identical statistics in every CTA of the cluster
+      Wf o;
+      o.n = gnc_ld_peer(&s_part[par][0], r);
+      o.mean = gnc_ld_peer(&s_part[par][1], r);
+      o.m2 = gnc_ld_peer(&s_part[par][2], r);
+      tot = wf_merge_fast(tot, o);
+    }
+    const float mean = tot.mean;
+    const float rstd = rsqrtf(tot.m2 / n + eps);
+    if (active) {
+      // o = (x - mean) * A + Bc with A = rstd*gamma [*(1+scale)], Bc = beta [*(1+scale) + shift]
+      A.x *= rstd; A.y *= rstd; A.z *= rstd; A.w *= rstd;
+      if (SS) {
+        const float k0 = 1.f + sc.x, k1 = 1.f + sc.y, k2 = 1.f + sc.z, k3 = 1.f + sc.w;
+        A.x *= k0; A.y *= k1; A.z *= k2; A.w *= k3;
+        Bc.x = fmaf(Bc.x, k0, sf.x); Bc.y = fmaf(Bc.y, k1, sf.y); Bc.z = fmaf(Bc.z, k2, sf.z); Bc.w = fmaf(Bc.w, k3, sf.w);
       }
-      p += U * pstep;
-      sp += U * sstep;
-    }
-    if (t < nt) {                                // tail batch
-      float4 xv[U];
-#pragma unroll
-      for (int i = 0; i < U; ++i)
-        if (t + i * R < nt) xv[i] = __ldg(p + i * pstep);
-#pragma unroll
-      for (int i = 0; i < U; ++i)
-        if (t + i * R < nt) {
-          sp[i * sstep] = xv[i];
-          sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
-        }
-    }
-  }
-  const float n = (float)T * (float)cg;
-  const float mean = cluster_total(0, block_sum(sum)) / n;
-  float m2 = 0.f;
-  if (active) {
-    const float4* sp = slab + r0 * q + v;
-#pragma unroll 4
-    for (int t = r0; t < nt; t += R, sp += sstep) {
-      const float4 xv = *sp;
-      const float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
-      m2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-    }
-  }
-  const float rstd = rsqrtf(cluster_total(1, block_sum(m2)) / n + eps);
-  gnc_cluster_arrive();                          // this CTA has read its peers' partials; waited for before exit
-  if (active) {
-    // o = (x - mean) * A + Bc with A = rstd*gamma [*(1+scale)], Bc = beta [*(1+scale) + shift]
-    float4 A = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    float4 Bc = __ldg(reinterpret_cast<const float4*>(beta + c));
-    A.x *= rstd; A.y *= rstd; A.z *= rstd; A.w *= rstd;
-    if (SS) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
-      const float4 sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
-      const float k0 = 1.f + sc.x, k1 = 1.f + sc.y, k2 = 1.f + sc.z, k3 = 1.f + sc.w;
-      A.x *= k0; A.y *= k1; A.z *= k2; A.w *= k3;
-      Bc.x = fmaf(Bc.x, k0, sf.x); Bc.y = fmaf(Bc.y, k1, sf.y); Bc.z = fmaf(Bc.z, k2, sf.z); Bc.w = fmaf(Bc.w, k3, sf.w);
-    }
-    const float4* sp = slab + r0 * q + v;
-    constexpr int PW = PARTS > 0 ? PARTS : 1;
-    const int plane_u2 = C >> 2;                                   // one plane of a row in uint2 (4 x bf16) units
-    const size_t ostep = (size_t)R * (PARTS > 0 ? PW * (C >> 2) : (C >> 2));   // uint2 units (planes) / float4 units (fp32)
-    const size_t o0 = (row0 + r0) * (size_t)(PARTS > 0 ? PW * (C >> 2) : (C >> 2)) + (c >> 2);
-    uint2* ybp = PARTS > 0 ? reinterpret_cast<uint2*>(yb) + o0 : nullptr;
-    uint2* rbp = (PARTS > 0 && RAW) ? reinterpret_cast<uint2*>(rawb) + o0 : nullptr;
-    float4* yp = PARTS == 0 ? reinterpret_cast<float4*>(y) + o0 : nullptr;
+      const float4* sp = sp0;
+      const size_t o0 = ((size_t)b * T + t_lo + r0) * (size_t)orow + (c >> 2);
+      uint2* ybp = PARTS > 0 ? reinterpret_cast<uint2*>(yb) + o0 : nullptr;
+      uint2* rbp = (PARTS > 0 && RAW) ? reinterpret_cast<uint2*>(rawb) + o0 : nullptr;
+      float4* yp = PARTS == 0 ? reinterpret_cast<float4*>(y) + o0 : nullptr;
 #pragma unroll 2
-    for (int t = r0; t < nt; t += R, sp += sstep) {
-      const float4 xv = *sp;
-      float o0v = fmaf(xv.x - mean, A.x, Bc.x), o1v = fmaf(xv.y - mean, A.y, Bc.y), o2v = fmaf(xv.z - mean, A.z, Bc.z),
-            o3v = fmaf(xv.w - mean, A.w, Bc.w);
-      if (SILU) {
-        if (PARTS == 1) { o0v = silu_fast(o0v); o1v = silu_fast(o1v); o2v = silu_fast(o2v); o3v = silu_fast(o3v); }
-        else { o0v = silu_newton(o0v); o1v = silu_newton(o1v); o2v = silu_newton(o2v); o3v = silu_newton(o3v); }
-      }
-      if (PARTS > 0) {
-        store_planes4_ct<PW>(ybp, plane_u2, o0v, o1v, o2v, o3v);
-        ybp += ostep;
-        if (RAW) {
-          store_planes4_ct<PW>(rbp, plane_u2, xv.x, xv.y, xv.z, xv.w);
-          rbp += ostep;
+      for (int i = 0; i < nfr; ++i, sp += sstep) {
+        const float4 xv = *sp;
+        float o0v = fmaf(xv.x - mean, A.x, Bc.x), o1v = fmaf(xv.y - mean, A.y, Bc.y), o2v = fmaf(xv.z - mean, A.z, Bc.z),
+              o3v = fmaf(xv.w - mean, A.w, Bc.w);
+        if (SILU) {
+          if (PARTS == 1) { o0v = silu_fast(o0v); o1v = silu_fast(o1v); o2v = silu_fast(o2v); o3v = silu_fast(o3v); }
+          else { o0v = silu_newton(o0v); o1v = silu_newton(o1v); o2v = silu_newton(o2v); o3v = silu_newton(o3v); }
         }
-      } else {
-        *yp = make_float4(o0v, o1v, o2v, o3v);
-        yp += ostep;
+        if (PARTS > 0) {
+          store_planes4_ct<PW>(ybp, plane_u2, o0v, o1v, o2v, o3v);
+          ybp += ostep;
+          if (RAW) {
+            store_planes4_ct<PW>(rbp, plane_u2, xv.x, xv.y, xv.z, xv.w);
+            rbp += ostep;
+          }
+        } else {
+          *yp = make_float4(o0v, o1v, o2v, o3v);
+          yp += ostep;
+        }
       }
     }
   }
-  gnc_cluster_wait();                            // no CTA of the cluster exits while a peer may still read its s_part
+  gnc_cluster_arrive();                          // no CTA of the cluster exits while a peer may still read its s_part
+  gnc_cluster_wait();
 }
 
 // One warp per LN_ROWS consecutive rows (C <= 32*4*LN_MAXV, LN_MAXV instantiated for C <= 256 / 384 / 512): all loads of the rows are issued before the first
@@ -657,7 +711,7 @@ cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, in
 namespace {
 template <int PARTS, bool SILU, bool SS, bool RAW>
 cudaError_t launch_gnc(dim3 grid, size_t smem, int cl, cudaStream_t s, const float* x1, int c1, const float* x2, int c2, int T, int groups,
-                       int tc, float eps, const float* gamma, const float* beta, const float* ss, float* y, __nv_bfloat16* yb,
+                       int n_items, int tc, float eps, const float* gamma, const float* beta, const float* ss, float* y, __nv_bfloat16* yb,
                        __nv_bfloat16* rawb) {
   static unsigned long long configured = 0;
   if (first_use_on_this_device(configured)) {
@@ -666,8 +720,8 @@ cudaError_t launch_gnc(dim3 grid, size_t smem, int cl, cudaStream_t s, const flo
     e = cudaFuncSetAttribute(gn_cluster_kernel<PARTS, SILU, SS, RAW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
   }
-  return launch_pdl(gn_cluster_kernel<PARTS, SILU, SS, RAW>, grid, dim3(GNC_THREADS), smem, s, cl, x1, c1, x2, c2, T, groups, tc, eps, gamma,
-                    beta, ss, y, yb, rawb);
+  return launch_pdl(gn_cluster_kernel<PARTS, SILU, SS, RAW>, grid, dim3(GNC_THREADS), smem, s, cl, x1, c1, x2, c2, T, groups, n_items, tc, eps,
+                    gamma, beta, ss, y, yb, rawb);
 }
 template <int PARTS, typename... A>
 cudaError_t launch_gnc_flags(bool silu, bool has_ss, bool raw, A... a) {
@@ -693,16 +747,26 @@ cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, 
   if (yb ? (parts != 1 && parts != 3) : (y == nullptr)) return cudaErrorInvalidValue;
   const int cg = C / groups, q = cg / 4;
   if (q > GNC_THREADS) return cudaErrorNotSupported;
-  int cl = 1;                                    // a function of (T, cg) only: batch-composition invariance
-  while (cl < 8 && (size_t)((T + cl - 1) / cl) * cg * sizeof(float) > 40 * 1024) cl *= 2;
+  // cluster size: a function of (T, cg) only (batch-composition invariance); slices of <= 36 KB, two buffers per CTA
+  int cl = 1;
+  while (cl < 8 && (size_t)((T + cl - 1) / cl) * cg * sizeof(float) > 36 * 1024) cl *= 2;
   const int tc = (T + cl - 1) / cl;
-  const size_t smem = (size_t)tc * cg * sizeof(float);
+  const size_t smem = 2 * (size_t)tc * cg * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorNotSupported;
-  const dim3 grid(groups * cl, B);
+  // persistent grid: at most eight CTAs of 128 threads per SM (register bound), every cluster gets the same number of items when possible
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (226 * 1024) / (smem + 1200)));
+  const int n_items = B * groups;
+  const int max_clusters = std::max(1, sms * per_sm / cl);
+  const int rounds = (n_items + max_clusters - 1) / max_clusters;
+  const int n_clusters = (n_items + rounds - 1) / rounds;
+  const dim3 grid(n_clusters * cl);
   const bool raw = yb && rawb;
-  if (!yb) return launch_gnc_flags<0>(silu != 0, ss != nullptr, false, grid, smem, cl, s, x1, c1, x2, c2, T, groups, tc, eps, gamma, beta, ss, y, yb, rawb);
-  if (parts == 1) return launch_gnc_flags<1>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, tc, eps, gamma, beta, ss, y, yb, rawb);
-  return launch_gnc_flags<3>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, tc, eps, gamma, beta, ss, y, yb, rawb);
+  if (!yb) return launch_gnc_flags<0>(silu != 0, ss != nullptr, false, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
+  if (parts == 1) return launch_gnc_flags<1>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
+  return launch_gnc_flags<3>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
