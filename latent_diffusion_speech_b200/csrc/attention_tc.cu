@@ -35,6 +35,7 @@ constexpr int AQ = 128, ATT_TC_THREADS = 320, NSOFT = 256;
 
 struct AttnTcParams {
   int B, T, H, d, C, parts, nk, nv, nsb, npb;   // ring depths: K, V^T tiles (smem), S (TMEM) and P (smem) buffers
+  int pa_tiles;         // 64-key tiles per pass-A step: 1, or 2 (split mode: the two hi-plane tiles fill plane slots 0 and 1 of a K stage -> one N = 128 instruction)
   float scale;
   __nv_bfloat16* out;   // planes [B*T][parts*C]
 };
@@ -121,6 +122,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   // loads and its pass A overlap the softmax tail, the O read-out and the stores of the current one).
   const int nq = (p.T + AQ - 1) / AQ, n_items = nq * p.H * p.B;
   const int nt = (p.T + AKV - 1) / AKV;
+  const int PA = p.pa_tiles, ntA = (nt + PA - 1) / PA;      // pass-A steps of PA key tiles
   const int HD = p.H * DPAD;
   constexpr int tmem_cols = (parts == 3 && !DUAL) ? 512 : 256;
   constexpr int o_col = (parts == 3 && !DUAL) ? 256 : 128;    // S buffers start at column 0, O blocks at o_col
@@ -157,15 +159,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         mbar_wait(q_empty, (local & 1u) ^ 1u);                   // every Q K^T of the previous item has read Q
         mbar_expect_tx(q_full, parts * QB);
         for (int pl = 0; pl < parts; ++pl) tma_load_3d(q_s + pl * QB, &mapQ, q_full, pl * HD + h * DPAD, qt * AQ, b);
-        for (int it = 0; it < 2 * nt; ++it, ++kc) {
-          const int jt = it < nt ? it : it - nt;
+        for (int it = 0; it < ntA + nt; ++it, ++kc) {
+          const int jt = it < ntA ? it : it - ntA;
           const int ks = kc % NK;
-          const int kparts = it < nt ? 1 : parts;                // pass A needs the hi plane only
           mbar_wait(k_empty(ks), ((kc / NK) & 1u) ^ 1u);
-          mbar_expect_tx(k_full(ks), kparts * KB);
-          for (int pl = 0; pl < kparts; ++pl)
-            tma_load_3d(k_s + (ks * parts + pl) * KB, &mapK, k_full(ks), pl * HD + h * DPAD, jt * AKV, b);
-          if (it >= nt) {
+          if (it < ntA) {                                        // pass A needs the hi plane only: PA consecutive key tiles per stage
+            mbar_expect_tx(k_full(ks), PA * KB);
+            for (int u = 0; u < PA; ++u)                         // (a tile beyond T is all out-of-bounds: zero fill, full byte count)
+              tma_load_3d(k_s + (ks * parts + u) * KB, &mapK, k_full(ks), h * DPAD, (jt * PA + u) * AKV, b);
+          } else {
+            mbar_expect_tx(k_full(ks), parts * KB);
+            for (int pl = 0; pl < parts; ++pl)
+              tma_load_3d(k_s + (ks * parts + pl) * KB, &mapK, k_full(ks), pl * HD + h * DPAD, jt * AKV, b);
+          }
+          if (it >= ntA) {
             const int vs = vc % NV;
             mbar_wait(v_empty(vs), ((vc / NV) & 1u) ^ 1u);
             mbar_expect_tx(v_full(vs), parts * KBLK * VBK);
@@ -210,7 +217,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                      v_kb_step = (uint64_t)((parts * VBK) >> 4), p_buf_step = (uint64_t)((parts * KBLK * PBK) >> 4),
                      p_kb_step = (uint64_t)(PBK >> 4);
       const uint64_t q_hi = umma_desc_kmajor(q_s, SWZ), k_hi = umma_desc_kmajor(k_s, SWZ);
-      const uint32_t hi_idesc = umma_idesc_bf16(AQ, AKV);
+      const uint32_t hi_idesc = umma_idesc_bf16(AQ, PA * AKV);
       const int ksteps = (p.d + 15) / 16;        // head dims beyond d are zero padding (d = 48 in a 64-wide tile): skip their K slices
       // S buffer of evaluation `it`: pass B rotates over the NSB buffers of the S region; pass A always has two buffers —
       // with NSB == 1 the second one borrows the O region (idle until the first P V of the item) — so that the hi*hi
@@ -223,11 +230,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           o_claimed = true;
         }
       };
+      // `it` < ntA: pass-A step; else pass-B tile it - ntA.  Pass A with PA == 2 always uses [0, 128) and the O region.
       auto issue_qk = [&](int it) {
         const int ks = kc % NK;
-        const int sb = it < nt ? (it & 1) : (it - nt) % NSB;
-        const bool alt = it < nt && NSB == 1 && sb == 1;
-        const uint32_t soff = alt ? (uint32_t)o_col : (uint32_t)(sb * s_stride);
+        const bool passA = it < ntA;
+        const int sb = passA ? (it & 1) : (it - ntA) % NSB;
+        const bool alt = passA && (NSB == 1 || PA == 2) && sb == 1;
+        const uint32_t soff = alt ? (uint32_t)o_col : (uint32_t)((passA && PA == 2) ? 0 : sb * s_stride);
         if (alt) claim_o();
         mbar_wait(k_full(ks), (kc / NK) & 1u);
         ++kc;
@@ -235,7 +244,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         if (sb) ++su1; else ++su0;
         tc_fence_after();
         const uint64_t koff = (uint64_t)ks * k_stage_step;
-        if (it < nt) {
+        if (passA) {
           // pass A only needs the row maximum to ~1 %: hi*hi alone (any m close to the maximum gives the same softmax)
 #pragma unroll
           for (int k = 0; k < DPAD / 16; ++k)
@@ -249,15 +258,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         }
         umma_commit(k_empty(ks));
         umma_commit(s_full(sb));
-        if (it == 2 * nt - 1) umma_commit(q_empty);            // last Q K^T of the item: Q may be overwritten
+        if (it == ntA + nt - 1) umma_commit(q_empty);          // last Q K^T of the item: Q may be overwritten
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
         o_claimed = false;
         mbar_wait(q_full, local & 1u);
-        for (int it = 0; it < nt; ++it) issue_qk(it);            // pass A
-        issue_qk(nt);                                            // pass B: Q K^T runs one tile ahead of P V
+        for (int it = 0; it < ntA; ++it) issue_qk(it);           // pass A
+        issue_qk(ntA);                                           // pass B: Q K^T runs one tile ahead of P V
         for (int jb = 0; jb < nt; ++jb) {
-          if (jb + 1 < nt) issue_qk(nt + jb + 1);
+          if (jb + 1 < nt) issue_qk(ntA + jb + 1);
           const int vs = vc % NV, pb = jb % NPB;
           mbar_wait(v_full(vs), (vc / NV) & 1u);
           ++vc;
@@ -302,18 +311,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
       float m = -INFINITY;
       // ---- pass A: row maximum of the scaled, masked scores ----
-      for (int it = 0; it < nt; ++it) {
+      const int nchA = NCH * PA, c0A = c0 * PA;            // this thread's half of a pass-A step of PA * AKV keys
+      for (int it = 0; it < ntA; ++it) {
         const int sb = it & 1;
-        const uint32_t soff = NSB == 1 ? (uint32_t)(sb * o_col) : (uint32_t)(sb * s_stride);
+        const uint32_t soff = (NSB == 1 || PA == 2) ? (uint32_t)(sb * o_col) : (uint32_t)(sb * s_stride);
         mbar_wait(s_full(sb), (sb ? su1 : su0) & 1u);
         if (sb) ++su1; else ++su0;
         tc_fence_after();
 #pragma unroll 1
-        for (int ch = 0; ch < NCH; ++ch) {
+        for (int ch = 0; ch < nchA; ++ch) {
           float s[32];
-          tmem_ld32(tmem0 + lane_off + soff + c0 + ch * 32, s);   // hi*hi scores live in block 0
-          if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
-          const int k0 = it * AKV + c0 + ch * 32;
+          tmem_ld32(tmem0 + lane_off + soff + c0A + ch * 32, s);  // hi*hi scores live in block 0
+          if (ch == nchA - 1) { tc_fence_before(); mbar_arrive(s_free(sb)); }
+          const int k0 = it * PA * AKV + c0A + ch * 32;
           if (k0 + 32 <= p.T) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) m = fmaxf(m, s[i]);
@@ -456,6 +466,8 @@ cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, c
   }
   AttnTcParams p;
   p.B = a.B; p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts; p.nk = nk; p.nv = nv; p.nsb = nsb; p.npb = npb;
+  static const bool pa128 = !(getenv("LDS_ATT_PA128") && atoi(getenv("LDS_ATT_PA128")) == 0);
+  p.pa_tiles = (PARTS == 3 && AKV == 64 && pa128) ? 2 : 1;
   p.scale = 1.0f / sqrtf((float)a.d);
   p.out = a.out;
   // persistent: one CTA per resident slot (two per SM in bf16 / DUAL mode), items strided over them
