@@ -98,7 +98,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int parts = PARTS;
   const int NK = p.nk, NV = p.nv;
-  const uint32_t q_s = base, k_s = q_s + parts * QB, v_s = k_s + NK * parts * KB, p_s = v_s + NV * parts * KBLK * VBK;
+  const int KSL = parts > p.pa_tiles ? parts : p.pa_tiles;     // K tiles (plane slots) per stage of the K ring
+  const uint32_t q_s = base, k_s = q_s + parts * QB, v_s = k_s + NK * KSL * KB, p_s = v_s + NV * parts * KBLK * VBK;
   const int NSB = p.nsb, NPB = p.npb;
   const uint32_t bar0 = p_s + NPB * parts * KBLK * PBK;
   uint8_t* p_ptr = smem + (p_s - base);
@@ -166,11 +167,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           if (it < ntA) {                                        // pass A needs the hi plane only: PA consecutive key tiles per stage
             mbar_expect_tx(k_full(ks), PA * KB);
             for (int u = 0; u < PA; ++u)                         // (a tile beyond T is all out-of-bounds: zero fill, full byte count)
-              tma_load_3d(k_s + (ks * parts + u) * KB, &mapK, k_full(ks), h * DPAD, (jt * PA + u) * AKV, b);
+              tma_load_3d(k_s + (ks * KSL + u) * KB, &mapK, k_full(ks), h * DPAD, (jt * PA + u) * AKV, b);
           } else {
             mbar_expect_tx(k_full(ks), parts * KB);
             for (int pl = 0; pl < parts; ++pl)
-              tma_load_3d(k_s + (ks * parts + pl) * KB, &mapK, k_full(ks), pl * HD + h * DPAD, jt * AKV, b);
+              tma_load_3d(k_s + (ks * KSL + pl) * KB, &mapK, k_full(ks), pl * HD + h * DPAD, jt * AKV, b);
           }
           if (it >= ntA) {
             const int vs = vc % NV;
@@ -213,7 +214,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         pv_idesc[e] = umma_idesc_bf16(AQ, pv[e].n_planes * DPAD);
         pv_dst[e] = tmem_o + pv[e].blk * DPAD;
       }
-      const uint64_t k_stage_step = (uint64_t)((parts * KB) >> 4), v_stage_step = (uint64_t)((parts * KBLK * VBK) >> 4),
+      const uint64_t k_stage_step = (uint64_t)((KSL * KB) >> 4), v_stage_step = (uint64_t)((parts * KBLK * VBK) >> 4),
                      v_kb_step = (uint64_t)((parts * VBK) >> 4), p_buf_step = (uint64_t)((parts * KBLK * PBK) >> 4),
                      p_kb_step = (uint64_t)(PBK >> 4);
       const uint64_t q_hi = umma_desc_kmajor(q_s, SWZ), k_hi = umma_desc_kmajor(k_s, SWZ);
@@ -241,6 +242,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         mbar_wait(k_full(ks), (kc / NK) & 1u);
         ++kc;
         mbar_wait(s_free(sb), ((sb ? su1 : su0) & 1u) ^ 1u);   // the softmax threads have read the previous use of this S buffer
+        // a 128-column pass-A step into [0, 128) also covers pass-B buffer 1 ([64, 128) when NSB == 2): its last use too
+        if (passA && PA == 2 && NSB == 2 && sb == 0) mbar_wait(s_free(1), (su1 & 1u) ^ 1u);
         if (sb) ++su1; else ++su0;
         tc_fence_after();
         const uint64_t koff = (uint64_t)ks * k_stage_step;
@@ -445,7 +448,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 template <int DPAD, int AKV, int PARTS, bool DUAL = false>
 cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, cudaStream_t s) {
   const int parts = a.parts;
-  const size_t smem = (size_t)parts * (AQ * DPAD * 2 + nk * AKV * DPAD * 2 + nv * DPAD * AKV * 2 + npb * AQ * AKV * 2) + 1024 +
+  // LDS_ATT_PA128: 0 off; 1 split mode and bf16 d <= 32; 2 (default) also bf16 d > 32 (its K ring then has two stages)
+  static const int pa128 = getenv("LDS_ATT_PA128") ? atoi(getenv("LDS_ATT_PA128")) : 2;
+  const bool wide_ok = PARTS == 3 || DPAD == 32 || pa128 == 2;
+  const int pa_tiles = (AKV == 64 && pa128 != 0 && wide_ok) ? 2 : 1;
+  if (PARTS == 1 && DPAD == 64) nk = pa_tiles == 2 ? 2 : 4;
+  const int ksl = parts > pa_tiles ? parts : pa_tiles;
+  const size_t smem = (size_t)parts * (AQ * DPAD * 2 + nv * DPAD * AKV * 2 + npb * AQ * AKV * 2) + (size_t)ksl * nk * AKV * DPAD * 2 + 1024 +
                       72 + 8 * 16 + 16 + 16 + 2 * 128 * 4 + 64;
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -466,8 +475,7 @@ cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, c
   }
   AttnTcParams p;
   p.B = a.B; p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts; p.nk = nk; p.nv = nv; p.nsb = nsb; p.npb = npb;
-  static const bool pa128 = !(getenv("LDS_ATT_PA128") && atoi(getenv("LDS_ATT_PA128")) == 0);
-  p.pa_tiles = (PARTS == 3 && AKV == 64 && pa128) ? 2 : 1;
+  p.pa_tiles = pa_tiles;
   p.scale = 1.0f / sqrtf((float)a.d);
   p.out = a.out;
   // persistent: one CTA per resident slot (two per SM in bf16 / DUAL mode), items strided over them
@@ -502,8 +510,9 @@ cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
     // (a second P buffer in exchange for a one-deep V^T ring measured 14 % slower: 0.47 vs 0.41 ms at T=432, B=64)
     if (a.dpad == 64) return launch_attn<64, 64, 3>(a, 2, 2, 1, 1, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
   } else {                                                             // bf16: S and P double-buffered, two CTAs per SM
-    if (a.dpad == 32) return launch_attn<32, 64, 1>(a, 4, 3, 2, 2, s);    //  8 + 4*4 + 3*4 + 2*16 = 68, TMEM 2*64 (S) + 32 (O)
-    if (a.dpad == 64) return launch_attn<64, 64, 1>(a, 4, 3, 2, 2, s);    // 16 + 4*8 + 3*8 + 2*16 = 104
+    // K stages hold two 64-key tiles (pass A runs over 128-key steps): 4 (2) stages of 8 (16) KB
+    if (a.dpad == 32) return launch_attn<32, 64, 1>(a, 4, 3, 2, 2, s);    //  8 + 4*8 + 3*4 + 2*16 = 84, TMEM 2*64 (S) + 32 (O)
+    if (a.dpad == 64) return launch_attn<64, 64, 1>(a, 2, 3, 2, 2, s);    // 16 + 2*16 + 3*8 + 2*16 = 104
   }
   return cudaErrorNotSupported;
 }
