@@ -495,9 +495,8 @@ cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, c
 cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
   if ((a.parts != 1 && a.parts != 3) || a.d > a.dpad || a.d % 8 || a.T_pad % 8 || a.T_pad < a.T) return cudaErrorInvalidValue;
-  // shared memory per CTA: split, dpad 32: 24+3*12+2*12+48 = 132 KB; split, dpad 64: 48+3*24+2*24+48 = 216 KB;
-  //                        bf16: a third of that (two CTAs per SM, bounded by 2 x 256 TMEM columns)
-  // shared memory per CTA (KB): Q + nk*K + nv*V^T + P
+  // shared memory per CTA (KB): Q + nk*K + nv*V^T + P; a K stage holds max(parts, 2) 64-key tiles (pass A loads two
+  // hi-plane tiles per stage), two CTAs per SM in bf16 and DUAL mode (bounded by 2 x 256 TMEM columns)
   if (a.parts == 3) {
     // d <= 32: two CTAs per SM: 24 (Q) + 2*12 (K) + 12 (V^T) + 48 (P) = 108 KB, TMEM 128 (S) + 96 (O) per CTA.
     // LDS_ATT_PAIR=1 selects the CTA-pair kernel of attention_pair.cu instead — correct (same tests) but NOT faster:
