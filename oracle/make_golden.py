@@ -40,6 +40,7 @@ CASES = [
     ("shallow_ddim10_b2_t37", 2, 37, "ddim", 10, 100, 0),
     ("pndm20_b1_t40", 1, 40, "pndm", 50, None, 0),             # the reference's PLMS path only runs for B == 1
     ("shallow_pndm10_b1_t37", 1, 37, "pndm", 10, 100, 0),
+    ("dpm20_b1_t432", 1, 432, "dpm-solver", 50, None, 0),       # BASELINE configs[0]: one ~5 s utterance, 20-step DPM-Solver
 ]
 
 
