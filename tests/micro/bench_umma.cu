@@ -140,7 +140,66 @@ void run(const char* name, int grid) {
   cudaFree(d);
 }
 
-int main() {
+// Generic shape / operand-major probe for the attention redesign: M = 64 or 128, any N, B operand K-major
+// or MN-major (instruction-descriptor bit 16; the shared-memory descriptor then strides 16 rows of 128 bytes per k-step).
+// Operands are zeros: only the issue cost is measured.
+template <int M, int N, int BMN>
+__global__ void __launch_bounds__(128) kx(long long* out, int iters, int ksteps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw), base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar = base + 96 * 1024;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 96 * 1024 + 16);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(slot), 256);
+  fence_async_smem();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = *slot;
+  if (threadIdx.x == 0) {
+    const uint64_t ad = umma_desc_kmajor(base, 128);
+    uint64_t bd = umma_desc_kmajor(base + 32 * 1024, 128);
+    if (BMN) bd |= (uint64_t)(1024 >> 4) << 16;            // leading byte offset between 64-element column blocks (MN-major)
+    const uint32_t idesc = umma_idesc_bf16(M, N) | ((uint32_t)BMN << 16);
+    const uint64_t bstep = BMN ? 128 : 2;                  // 16-byte units per k-step of 16 elements
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i)
+      for (int ks = 0; ks < ksteps; ++ks) umma_bf16(tm, ad + 2 * ks, bd + bstep * ks, idesc, 1u);
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 256); }
+}
+
+template <int M, int N, int BMN>
+void run_x(const char* name, int grid) {
+  long long* d; cudaMalloc(&d, 8);
+  const int iters = 2000, ksteps = 4;
+  cudaFuncSetAttribute(kx<M, N, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  kx<M, N, BMN><<<grid, 128, 100 * 1024>>>(d, iters, ksteps);
+  kx<M, N, BMN><<<grid, 128, 100 * 1024>>>(d, iters, ksteps);
+  long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaGetLastError();
+  printf("X %-26s grid=%3d  %.1f cycles/MMA  (ideal math %d)  %s\n", name, grid, (double)h / (iters * ksteps), M * N / 256, cudaGetErrorString(e));
+  cudaFree(d);
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'x') {                     // bench_umma x : only the probes of the attention redesign
+    const int grid = 148;
+    run_x<128, 128, 0>("M128 N128 B:K-major", grid);
+    run_x<128, 256, 0>("M128 N256 B:K-major", grid);
+    run_x<128, 128, 1>("M128 N128 B:MN-major", grid);
+    run_x<128, 256, 1>("M128 N256 B:MN-major", grid);
+    run_x<64, 64, 0>("M64  N64  B:K-major", grid);
+    run_x<64, 128, 0>("M64  N128 B:K-major", grid);
+    run_x<64, 256, 0>("M64  N256 B:K-major", grid);
+    run_x<64, 256, 1>("M64  N256 B:MN-major", grid);
+    return 0;
+  }
   for (int grid : {148}) {
     run<32, 128>("M128 N32  SW128", grid);
     run<64, 128>("M128 N64  SW128", grid);
