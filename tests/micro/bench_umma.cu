@@ -188,6 +188,14 @@ void run_x(const char* name, int grid) {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 's') {                     // bench_umma s : K-major M = 64 probes only
+    const int grid = 148;
+    run_x<128, 256, 0>("M128 N256 B:K-major", grid);
+    run_x<64, 64, 0>("M64  N64  B:K-major", grid);
+    run_x<64, 128, 0>("M64  N128 B:K-major", grid);
+    run_x<64, 256, 0>("M64  N256 B:K-major", grid);
+    return 0;
+  }
   if (argc > 1 && argv[1][0] == 'x') {                     // bench_umma x : only the probes of the attention redesign
     const int grid = 148;
     run_x<128, 128, 0>("M128 N128 B:K-major", grid);
