@@ -292,11 +292,11 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const float* __re
 }
 
 // Cluster form of the single-pass GroupNorm: the [T, C/G] slab of one (utterance, group) is split along time over the
-// CL CTAs of a thread-block cluster, so that a CTA holds <= ~40 KB and five or more CTAs in different phases (loading /
-// reducing / storing) share an SM — loads and stores overlap instead of alternating, and slabs that do not fit one SM
-// (640-channel concats, T = 2584) stay single-pass.  The per-CTA partial sums travel through distributed shared
-// memory: every CTA reads the CL partials in rank order (identical mean / rstd in all of them), exact two-pass mean /
-// M2 as before.  CL depends on (T, C/G) only, never on the batch: results are batch-composition invariant.
+// CL CTAs of a thread-block cluster (slices of <= 36 KB), so that several small CTAs share an SM and slabs that do not
+// fit one SM (640-channel concats, T = 2584 at 256 channels) stay single-pass.  The per-CTA (count, mean, M2) partials
+// travel through distributed shared memory: every CTA reads the CL partials in rank order (identical mean / rstd in
+// all of them).  CL depends on (T, C/G) only, never on the batch: results are batch-composition invariant.
+// History of the kernel and the ncu evidence behind each step: profiles/r01_groupnorm_layernorm_investigation.md.
 constexpr int GNC_THREADS = 128;   // 13.5 instead of 6.75 channel quads per thread and item at T = 864: the per-item fixed cost halves
 __device__ __forceinline__ uint32_t gnc_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t gnc_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
