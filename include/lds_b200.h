@@ -13,8 +13,10 @@
  *     contiguous; the caller keeps ownership and must keep them alive until the stream work
  *     enqueued by the call has completed.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
- *     enqueued asynchronously on it; no call synchronises the device except lds_plan,
- *     lds_finalize_weights and lds_destroy.
+ *     enqueued asynchronously on it; no call synchronises the device except lds_finalize_weights,
+ *     lds_destroy and an lds_plan that has to GROW the workspace or change the sampler program
+ *     (a re-plan for a batch that fits the existing workspace neither synchronises nor allocates;
+ *     callers that switch streams between calls order them themselves).
  *   - a handle is bound to one device and is not thread-safe.
  *   - there is no random number generation inside the library: initial noise and per-step
  *     DDPM noise are produced by the caller (reference: torch.randn at diffusion.py:207,170,118).
@@ -134,6 +136,11 @@ LDS_API int lds_denoise(lds_handle* h, const float* x_BMT, const float* cond_BTH
  *   lds_sample       : begin + all steps + end
  * Step indices: DPM/UniPC k in [0, steps] (k=0 is the first evaluation), DDPM / DDIM j in [0, n_nfe), PNDM j in [0, n_nfe-1). */
 LDS_API int lds_sample_begin(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, void* stream);
+/* Shallow-diffusion start (diffusion.py:208-212 + q_sample :169-171 + norm_spec :86): one fused kernel computes
+ *   x <- sqrt_acp * (gt_spec[B,T,out_dims] * acoustic_scale) + sqrt_1m_acp * noise[B,out_dims,T]
+ * (sqrt_acp = sqrt_alphas_cumprod[k_step-1], sqrt_1m_acp = sqrt_one_minus_alphas_cumprod[k_step-1]) and binds cond. */
+LDS_API int lds_sample_begin_shallow(lds_handle* h, const float* cond_BTH, const float* gt_spec_BTM, const float* noise_BMT,
+                             float sqrt_acp, float sqrt_1m_acp, void* stream);
 LDS_API int lds_sample_steps(lds_handle* h, int k0, int k1, const float* step_noise, void* stream);
 LDS_API int lds_sample_end(lds_handle* h, float* mel_BTM, void* stream);
 LDS_API int lds_sample(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, const float* step_noise,
@@ -200,6 +207,41 @@ LDS_API int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, i
  *   scratch sizes (bf16 elements): q, k: B*T*parts*H*dpad; vt: B*parts*H*dpad*T_pad, T_pad = round_up(T, 8). */
 LDS_API int lds_op_qkv_attention_tc(const void* x_planes, const void* w_qkv, int B, int T, int C, int H, int dpad, int parts,
                             void* q_scratch, void* k_scratch, void* vt_scratch, void* out_planes, void* stream);
+
+/* The per-step sampler arithmetic and the layout kernels (csrc/solver.cu), one entry point per kernel, so that each is
+ * testable bit-for-bit against the PyTorch expressions it replaces.  State tensors are flat fp32 arrays of n elements
+ * (n % 4 == 0) in the channels-last layout [B,T,M]; the arithmetic uses round-to-nearest mul/add/sub/div in the
+ * reference's evaluation order (no FMA contraction), so results are torch.equal to the eager expressions:
+ *   lds_op_x0_pred       m = (x - sigma*eps)/alpha                               dpm_solver_pytorch.py:433-442, uni_pc.py:285-294
+ *   lds_op_dpm_update    order 1: x = cx*x - cm*m0                                dpm_solver_pytorch.py:569-576
+ *                        order 2: x = cx*x - cm*m0 - hcm*(ir0*(m0-m1))            dpm_solver_pytorch.py:813-831
+ *   lds_op_unipc_predict xb = cx*x - cmE*m0; xp = xb - aB*(rho_p*((m1-m0)/rk))     uni_pc.py:545-556 (order 1: xp = xb)
+ *   lds_op_unipc_correct x = xb - aB*(rho_c0*((m1-m0)/rk) + rho_c1*(mt-m0))        uni_pc.py:557-568 (order 1: first term absent)
+ *   lds_op_ddpm_step     x = pm1*clamp(cr*x - crm1*eps, -1, 1) + pm2*x + sig*noise  diffusion.py:95-121 (noise [B,M,T])
+ *   lds_op_ddim_step     x = sqrt_aprev*(x/sqrt_at + coef*eps)                     diffusion.py:123-132
+ *   lds_op_pndm_update   out = x + d*(k1*x - k2*e'), e' by mode 0..4               diffusion.py:134-167
+ *   lds_op_q_sample      x = sqrt_acp*(gt*acoustic_scale) + sqrt_1m_acp*noise^T     diffusion.py:169-171,208-212
+ *   lds_op_cast_gather   mode 1 nearest upsample, mode 2 k3/s2/p1 im2col -> bf16 planes   resnet.py:157-160,200
+ *   lds_op_transpose     [B,C,T] <-> [B,T,C] (* scale)                             diffusion.py:225,342
+ *   lds_op_div_copy      out = in / divisor                                         diffusion.py:343 (denorm_spec :87) */
+LDS_API int lds_op_x0_pred(const float* x, const float* eps, float sigma, float alpha, float* m, int64_t n, void* stream);
+LDS_API int lds_op_dpm_update(float* x, const float* m0, const float* m1, float cx, float cm, float hcm, float ir0, int order,
+                      int64_t n, void* stream);
+LDS_API int lds_op_unipc_predict(const float* x, const float* m0, const float* m1, float cx, float cmE, float aB, float rk,
+                         float rho_p, int order, float* xb, float* xp, int64_t n, void* stream);
+LDS_API int lds_op_unipc_correct(const float* xb, const float* m0, const float* m1, const float* mt, float aB, float rk,
+                         float rho_c0, float rho_c1, int order, float* x, int64_t n, void* stream);
+LDS_API int lds_op_ddpm_step(float* x_BTM, const float* eps_BTM, const float* noise_BMT, float c_recip, float c_recipm1, float pm1,
+                     float pm2, float sig, int B, int T, int M, void* stream);
+LDS_API int lds_op_ddim_step(float* x, const float* eps, float sqrt_at, float coef, float sqrt_aprev, int64_t n, void* stream);
+LDS_API int lds_op_pndm_update(const float* x, const float* e, const float* h1, const float* h2, const float* h3, float d, float k1,
+                       float k2, int mode, float* out, int64_t n, void* stream);
+LDS_API int lds_op_q_sample(float* x_BTM, const float* gt_BTM, const float* noise_BMT, float acoustic_scale, float sqrt_acp,
+                    float sqrt_1m_acp, int B, int T, int M, void* stream);
+LDS_API int lds_op_cast_gather(const float* in, void* out_bf16, int B, int t_in, int t_out, int C, int parts, int mode, float scale,
+                       void* stream);
+LDS_API int lds_op_transpose(const float* in, float* out, int B, int C, int T, float scale, int to_channels_last, void* stream);
+LDS_API int lds_op_div_copy(const float* in, float* out, int64_t n, float divisor, void* stream);
 
 #ifdef __cplusplus
 }

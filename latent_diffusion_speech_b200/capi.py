@@ -22,11 +22,14 @@ DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 
 EXPORTS = [
     "lds_version", "lds_last_error", "lds_create", "lds_destroy", "lds_load_weight", "lds_finalize_weights",
-    "lds_plan", "lds_cond", "lds_denoise", "lds_sample_begin", "lds_sample_steps", "lds_sample_end", "lds_sample",
+    "lds_plan", "lds_cond", "lds_denoise", "lds_sample_begin", "lds_sample_begin_shallow", "lds_sample_steps", "lds_sample_end",
+    "lds_sample",
     "lds_num_steps", "lds_workspace_bytes", "lds_kernel_launches", "lds_set_profiling", "lds_profile_num_classes",
     "lds_profile_class_name", "lds_profile_class_ms", "lds_profile_class_launches", "lds_profile_class_flops",
     "lds_profile_class_bytes", "lds_op_gemm", "lds_op_attention", "lds_op_groupnorm", "lds_op_groupnorm_fused", "lds_op_groupnorm_cluster", "lds_op_layernorm",
     "lds_op_split_cast", "lds_op_gemm_tc", "lds_op_qkv_attention_tc",
+    "lds_op_x0_pred", "lds_op_dpm_update", "lds_op_unipc_predict", "lds_op_unipc_correct", "lds_op_ddpm_step", "lds_op_ddim_step",
+    "lds_op_pndm_update", "lds_op_q_sample", "lds_op_cast_gather", "lds_op_transpose", "lds_op_div_copy",
 ]
 
 
@@ -57,6 +60,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
             "(nvcc, sm_100a).  There is no CPU fallback for the diffusion sampling path.")
     lib = C.CDLL(p)
     vp, i32, i64p, fp = C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_float)
+    f32, i64 = C.c_float, C.c_int64
     sig = {
         "lds_version": (i32, []),
         "lds_last_error": (C.c_char_p, []),
@@ -68,6 +72,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "lds_cond": (i32, [vp, vp, vp, vp, vp]),
         "lds_denoise": (i32, [vp, vp, vp, fp, vp, vp]),
         "lds_sample_begin": (i32, [vp, vp, vp, vp]),
+        "lds_sample_begin_shallow": (i32, [vp, vp, vp, vp, C.c_float, C.c_float, vp]),
         "lds_sample_steps": (i32, [vp, i32, i32, vp, vp]),
         "lds_sample_end": (i32, [vp, vp, vp]),
         "lds_sample": (i32, [vp, vp, vp, vp, vp, vp]),
@@ -90,6 +95,17 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "lds_op_split_cast": (i32, [vp, vp, C.c_int64, i32, i32, vp]),
         "lds_op_gemm_tc": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp]),
         "lds_op_qkv_attention_tc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+        "lds_op_x0_pred": (i32, [vp, vp, f32, f32, vp, i64, vp]),
+        "lds_op_dpm_update": (i32, [vp, vp, vp, f32, f32, f32, f32, i32, i64, vp]),
+        "lds_op_unipc_predict": (i32, [vp, vp, vp, f32, f32, f32, f32, f32, i32, vp, vp, i64, vp]),
+        "lds_op_unipc_correct": (i32, [vp, vp, vp, vp, f32, f32, f32, f32, i32, vp, i64, vp]),
+        "lds_op_ddpm_step": (i32, [vp, vp, vp, f32, f32, f32, f32, f32, i32, i32, i32, vp]),
+        "lds_op_ddim_step": (i32, [vp, vp, f32, f32, f32, i64, vp]),
+        "lds_op_pndm_update": (i32, [vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, i64, vp]),
+        "lds_op_q_sample": (i32, [vp, vp, vp, f32, f32, f32, i32, i32, i32, vp]),
+        "lds_op_cast_gather": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
+        "lds_op_transpose": (i32, [vp, vp, i32, i32, i32, f32, i32, vp]),
+        "lds_op_div_copy": (i32, [vp, vp, i64, f32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)           # AttributeError if the symbol is not exported
@@ -163,8 +179,9 @@ class Engine:
         n_rows = 0 if coefs is None else int(coefs.shape[0])
         ts = None if t_sin is None else np.ascontiguousarray(t_sin, dtype=np.float32)
         cf = None if coefs is None else np.ascontiguousarray(coefs, dtype=np.float32)
+        # lds_plan synchronises the device itself, and only when it has to grow the workspace or replace the
+        # time-conditioning table (include/lds_b200.h); there is no synchronisation here.
         with torch.cuda.device(self.index):
-            torch.cuda.synchronize()
             check(self.lib, self.lib.lds_plan(self.handle, B, T, sampler, n_nfe, None if ts is None else _fptr(ts), n_rows,
                                               None if cf is None else _fptr(cf)), "lds_plan")
         self.plan_key, self.B, self.T = key, B, T
@@ -210,12 +227,22 @@ class Engine:
                                                   self._stream()), "lds_sample_begin")
         self._keep = [cond, x]
 
+    def sample_begin_shallow(self, cond_bth: torch.Tensor, gt_spec_btm: torch.Tensor, noise_bmt: torch.Tensor,
+                             sqrt_acp: float, sqrt_1m_acp: float) -> None:
+        """x <- sqrt_acp * norm_spec(gt_spec)^T + sqrt_1m_acp * noise  (q_sample at t = k_step - 1) in one kernel."""
+        cond, gt, nz = self._dev(cond_bth), self._dev(gt_spec_btm), self._dev(noise_bmt)
+        check(self.lib, self.lib.lds_sample_begin_shallow(self.handle, C.c_void_p(cond.data_ptr()), C.c_void_p(gt.data_ptr()),
+                                                          C.c_void_p(nz.data_ptr()), float(sqrt_acp), float(sqrt_1m_acp),
+                                                          self._stream()), "lds_sample_begin_shallow")
+        self._keep = [cond, gt, nz]
+
     def sample_steps(self, k0: int, k1: int, step_noise: Optional[torch.Tensor] = None) -> None:
         nz = None if step_noise is None else self._dev(step_noise)
         check(self.lib, self.lib.lds_sample_steps(self.handle, k0, k1, C.c_void_p(nz.data_ptr()) if nz is not None else None,
                                                   self._stream()), "lds_sample_steps")
-        if nz is not None:
-            self._keep.append(nz)
+        # No keep-alive for the noise chunk: it is allocated on the stream the library enqueues on, so torch's caching
+        # allocator already orders its reuse behind the kernels that read it (a 1000-step DDPM run would otherwise pin
+        # every chunk: ~14 GB at B=32, T=864).
 
     def sample_end(self) -> torch.Tensor:
         mel = torch.empty(self.B, self.T, self.cfg.out_dims, device=self.device, dtype=torch.float32)

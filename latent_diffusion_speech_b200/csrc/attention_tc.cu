@@ -25,8 +25,8 @@
 
 namespace lds {
 
-cudaError_t tc_make_map_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                             int swizzle_bytes, CUtensorMap* out);
+cudaError_t tc_make_map_bf16_cached(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                    int swizzle_bytes, CUtensorMap* out);
 
 namespace {
 using namespace ptx;
@@ -449,29 +449,33 @@ template <int DPAD, int AKV, int PARTS, bool DUAL = false>
 cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, cudaStream_t s) {
   const int parts = a.parts;
   // LDS_ATT_PA128: 0 off; 1 split mode and bf16 d <= 32; 2 (default) also bf16 d > 32 (its K ring then has two stages)
-  static const int pa128 = getenv("LDS_ATT_PA128") ? atoi(getenv("LDS_ATT_PA128")) : 2;
+  const int pa128 = knobs().att_pa128;
   const bool wide_ok = PARTS == 3 || DPAD == 32 || pa128 == 2;
   const int pa_tiles = (AKV == 64 && pa128 != 0 && wide_ok) ? 2 : 1;
   if (PARTS == 1 && DPAD == 64) nk = pa_tiles == 2 ? 2 : 4;
   const int ksl = parts > pa_tiles ? parts : pa_tiles;
   const size_t smem = (size_t)parts * (AQ * DPAD * 2 + nv * DPAD * AKV * 2 + npb * AQ * AKV * 2) + (size_t)ksl * nk * AKV * DPAD * 2 + 1024 +
                       72 + 8 * 16 + 16 + 16 + 2 * 128 * 4 + 64;
-  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  static unsigned long long configured = 0;      // per template instance: the shared-memory size of an instance is fixed
+  if (first_use_on_this_device(configured)) {
+    e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   const uint64_t HD = (uint64_t)a.H * DPAD;
   CUtensorMap mQ, mK, mV;
   {
     const uint64_t dims[3] = {(uint64_t)parts * HD, (uint64_t)a.T, (uint64_t)a.B};
     const uint64_t str[2] = {(uint64_t)parts * HD * 2, (uint64_t)parts * HD * 2 * a.T};
     const uint32_t boxq[3] = {(uint32_t)DPAD, (uint32_t)AQ, 1}, boxk[3] = {(uint32_t)DPAD, (uint32_t)AKV, 1};
-    if ((e = tc_make_map_bf16(a.q, 3, dims, str, boxq, DPAD * 2, &mQ)) != cudaSuccess) return e;
-    if ((e = tc_make_map_bf16(a.k, 3, dims, str, boxk, DPAD * 2, &mK)) != cudaSuccess) return e;
+    if ((e = tc_make_map_bf16_cached(a.q, 3, dims, str, boxq, DPAD * 2, &mQ)) != cudaSuccess) return e;
+    if ((e = tc_make_map_bf16_cached(a.k, 3, dims, str, boxk, DPAD * 2, &mK)) != cudaSuccess) return e;
   }
   {
     const uint64_t dims[2] = {(uint64_t)a.T, (uint64_t)a.B * parts * HD};
     const uint64_t str[1] = {(uint64_t)a.T_pad * 2};
     const uint32_t box[2] = {64u, (uint32_t)DPAD};
-    if ((e = tc_make_map_bf16(a.vt, 2, dims, str, box, 128, &mV)) != cudaSuccess) return e;
+    if ((e = tc_make_map_bf16_cached(a.vt, 2, dims, str, box, 128, &mV)) != cudaSuccess) return e;
   }
   AttnTcParams p;
   p.B = a.B; p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts; p.nk = nk; p.nv = nv; p.nsb = nsb; p.npb = npb;
@@ -499,13 +503,10 @@ cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
   // hi-plane tiles per stage), two CTAs per SM in bf16 and DUAL mode (bounded by 2 x 256 TMEM columns)
   if (a.parts == 3) {
     // d <= 32: two CTAs per SM: 24 (Q) + 2*12 (K) + 12 (V^T) + 48 (P) = 108 KB, TMEM 128 (S) + 96 (O) per CTA.
-    // LDS_ATT_PAIR=1 selects the CTA-pair kernel of attention_pair.cu instead — correct (same tests) but NOT faster:
-    // a cta_group::2 instruction occupies the tensor pipes of BOTH SMs for the same ~92 cycles, so the issue cost per
-    // query row and SM is unchanged (tests/micro/bench_umma.cu, 0.73 vs 0.68 ms per T=864 attention at B=64).
-    if (a.dpad == 32) {
-      static const bool pair = getenv("LDS_ATT_PAIR") && atoi(getenv("LDS_ATT_PAIR")) == 1;
-      return pair ? launch_attention_pair(a, s) : launch_attn<32, 64, 3, true>(a, 2, 1, 1, 1, s);
-    }
+    // (A CTA-pair variant, tests/micro/attention_pair.cu, is parity-green but NOT faster: a cta_group::2 instruction
+    // occupies the tensor pipes of BOTH SMs for the same ~92 cycles, so the issue cost per query row and SM is unchanged —
+    // tests/micro/bench_umma.cu, 0.73 vs 0.68 ms per T=864 attention at B=64.  It is not part of the library.)
+    if (a.dpad == 32) return launch_attn<32, 64, 3, true>(a, 2, 1, 1, 1, s);
     // (a second P buffer in exchange for a one-deep V^T ring measured 14 % slower: 0.47 vs 0.41 ms at T=432, B=64)
     if (a.dpad == 64) return launch_attn<64, 64, 3>(a, 2, 2, 1, 1, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
   } else {                                                             // bf16: S and P double-buffered, two CTAs per SM

@@ -557,8 +557,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int buf = local & 1;
       mbar_wait(tmem_full_bar(buf), ((uint32_t)local >> 1) & 1u);
       tc_fence_after();
+#ifdef LDS_DEBUG_KNOBS   // timing experiments only (results are wrong by construction); never compiled into the product library
       if (!(p.dbg & 2))
         epilogue_block<STAGED>(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, e, part, (p.dbg & 1) != 0);
+#else
+      epilogue_block<STAGED>(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, e, part, false);
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(buf), 0));
@@ -693,6 +697,40 @@ cudaError_t tc_make_map_bf16(const void* ptr, int rank, const uint64_t* dims, co
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// cached form (attention operand maps: the same scratch buffers and shapes recur every evaluation)
+cudaError_t tc_make_map_bf16_cached(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                    int swizzle_bytes, CUtensorMap* out) {
+  struct Key {
+    const void* ptr; int rank, swz; uint64_t d[3], st[2]; uint32_t bx[3];
+    bool operator==(const Key& o) const {
+      if (ptr != o.ptr || rank != o.rank || swz != o.swz) return false;
+      for (int i = 0; i < 3; ++i) if (d[i] != o.d[i] || bx[i] != o.bx[i]) return false;
+      return st[0] == o.st[0] && st[1] == o.st[1];
+    }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      size_t h = reinterpret_cast<size_t>(k.ptr) ^ ((size_t)k.rank << 1) ^ ((size_t)k.swz << 8);
+      for (int i = 0; i < 3; ++i) h = (h * 1000003u ^ (size_t)k.d[i]) * 1000003u ^ (size_t)k.bx[i];
+      return (h * 1000003u ^ (size_t)k.st[0]) * 1000003u ^ (size_t)k.st[1];
+    }
+  };
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  static std::mutex mu;
+  if (rank < 2 || rank > 3) return cudaErrorInvalidValue;
+  Key key{ptr, rank, swizzle_bytes, {0, 0, 0}, {0, 0}, {0, 0, 0}};
+  for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.st[i] = strides_bytes[i];
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return cudaSuccess; }
+  const cudaError_t e = tc_make_map_bf16(ptr, rank, dims, strides_bytes, box, swizzle_bytes, out);
+  if (e != cudaSuccess) return e;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return cudaSuccess;
+}
+
 cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (a.batches <= 0 || a.rows <= 0 || a.N <= 0) return cudaSuccess;
   const bool split = a.a_parts == 3 && a.w_parts == 3 && a.n_pairs == 6;
@@ -732,7 +770,11 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   p.kb_per_tap = a.cin / TBK; p.nkb = a.taps * p.kb_per_tap;
   p.N = a.N; p.bias = a.bias; p.R = a.R; p.r_ld = a.r_ld; p.r_div = a.r_div;
   p.C = a.C; p.c_ld = a.c_ld; p.out_kind = a.out_kind; p.epilogue = a.epilogue;
+#ifdef LDS_DEBUG_KNOBS
   { static const int dbg = getenv("LDS_TC_DEBUG") ? atoi(getenv("LDS_TC_DEBUG")) : 0; p.dbg = dbg; }
+#else
+  p.dbg = 0;
+#endif
   p.q_out = a.q_out; p.k_out = a.k_out; p.vt_out = a.vt_out;
   p.att_T = a.att_T; p.att_H = a.att_H; p.att_dpad = a.att_dpad; p.att_Tpad = a.att_Tpad;
   const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + 512 + stage_bytes;

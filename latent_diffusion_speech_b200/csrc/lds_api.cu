@@ -89,6 +89,20 @@ struct Prof {
 
 }  // namespace
 
+namespace lds {
+const Knobs& knobs() {
+  static const Knobs k = [] {
+    Knobs v;
+    auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    v.gn_mode = env_int("LDS_GN_MODE", 2);
+    v.att_pa128 = env_int("LDS_ATT_PA128", 2);
+    v.pdl = env_int("LDS_PDL", 1) != 0;
+    return v;
+  }();
+  return k;
+}
+}  // namespace lds
+
 struct lds_handle {
   lds_config cfg{};
   int device = 0;
@@ -116,7 +130,10 @@ struct lds_handle {
   std::vector<int> Tl;
   std::vector<float> coefs;
   float* arena = nullptr;
-  size_t arena_floats = 0;
+  size_t arena_floats = 0, arena_cap = 0;     // grow-only: a smaller (B, T) re-plan reuses the allocation
+  float* temb_arena = nullptr;                // time-conditioning tables, independent of (B, T)
+  size_t temb_cap = 0;
+  std::vector<float> temb_key;                // the sinusoid rows the table was computed from
   float *temb = nullptr, *temb_single = nullptr, *sin_dev = nullptr, *e1 = nullptr, *e2 = nullptr;
   float *cond_part = nullptr, *gn_part = nullptr, *spk_rows = nullptr;
   std::vector<float*> skips;
@@ -125,7 +142,7 @@ struct lds_handle {
   float *x = nullptr, *xb = nullptr, *xp = nullptr, *eps = nullptr, *mbuf[3] = {nullptr, nullptr, nullptr};
   float *io_a = nullptr, *io_b = nullptr;   // channels-last staging for lds_denoise
   __nv_bfloat16* barena = nullptr;          // bf16 operand buffers (tensor-core modes)
-  size_t barena_elems = 0;
+  size_t barena_elems = 0, barena_cap = 0;
   __nv_bfloat16 *norm_b = nullptr, *raw_b = nullptr, *tmp2_b = nullptr, *xn_b = nullptr, *att_b = nullptr, *ffh_b = nullptr,
                 *th_b = nullptr, *cast_b = nullptr, *q_b = nullptr, *k_b = nullptr, *vt_b = nullptr;
   const float* cond_bound = nullptr;
@@ -326,7 +343,7 @@ int run_gn_planes(lds_handle* h, cudaStream_t s, const float* x1, int c1, const 
                   float eps, const float* ss, int silu, __nv_bfloat16* yb, __nv_bfloat16* rawb) {
   const double elems = (double)h->B * T * (c1 + c2);
   // LDS_GN_MODE: 2 (default) cluster single-pass kernel; 1 one-CTA-per-(utterance, group) single pass; 0 stats + apply
-  static const int gn_mode = getenv("LDS_GN_MODE") ? atoi(getenv("LDS_GN_MODE")) : 2;
+  const int gn_mode = knobs().gn_mode;
   if (gn_mode == 2) {
     const cudaError_t e = launch_gn_cluster(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, eps, n.g, n.b, ss, silu, nullptr, yb, h->parts, rawb, s);
     if (e != cudaErrorNotSupported)
@@ -625,13 +642,17 @@ int lds_create(const lds_config* cfg, int device, lds_handle** out) {
   if (cfg->precision != LDS_PREC_FP32 && cfg->precision != LDS_PREC_BF16 && cfg->precision != LDS_PREC_FP32_FFMA)
     return fail(LDS_ERR_INVALID, "unknown precision");
   if (cfg->norm_groups < 1 || cfg->norm_groups > 32) return fail(LDS_ERR_INVALID, "norm_groups must be in [1,32]");
+  if (cfg->n_heads < 1) return fail(LDS_ERR_INVALID, "n_heads must be positive");
+  if (cfg->n_layers < 1 || cfg->n_layers > 8) return fail(LDS_ERR_INVALID, "n_layers must be in [1,8]");
+  if (cfg->out_dims < 1 || cfg->n_hidden < 1 || cfg->input_channel < 1) return fail(LDS_ERR_INVALID, "out_dims, n_hidden and input_channel must be positive");
   for (int i = 0; i < cfg->n_blocks; ++i) {
     const int c = cfg->block_out_channels[i];
-    if (c % 64 || c % cfg->norm_groups || c % cfg->n_heads) return fail(LDS_ERR_INVALID, "block_out_channels[%d]=%d must be a multiple of 64, norm_groups and n_heads", i, c);
-    if (i < cfg->n_blocks - 1 || true) {
-      const int d = c / cfg->n_heads;
-      if (d != 32 && d != 48 && d != 64) return fail(LDS_ERR_UNSUPPORTED, "head dim %d (channels %d / heads %d) not in {32,48,64}", d, c, cfg->n_heads);
-    }
+    if (c < 64 || c % 64 || c % cfg->norm_groups || c % cfg->n_heads) return fail(LDS_ERR_INVALID, "block_out_channels[%d]=%d must be a positive multiple of 64, norm_groups and n_heads", i, c);
+    // kernel limits, checked here so that no launch can fail mid-sampling: LayerNorm rows of at most 512 channels
+    // (launch_layernorm), GroupNorm over a virtual concat of at most 1024 channels (launch_gn_apply, the stats + apply fallback)
+    if (c > 512) return fail(LDS_ERR_UNSUPPORTED, "block_out_channels[%d]=%d exceeds the 512-channel limit of the LayerNorm / GroupNorm kernels", i, c);
+    const int d = c / cfg->n_heads;
+    if (d != 32 && d != 48 && d != 64) return fail(LDS_ERR_UNSUPPORTED, "head dim %d (channels %d / heads %d) not in {32,48,64}", d, c, cfg->n_heads);
   }
   if (cfg->out_dims % 16 || cfg->n_hidden % 16 || cfg->input_channel % 16)
     return fail(LDS_ERR_INVALID, "out_dims, n_hidden and input_channel must be multiples of 16");
@@ -650,6 +671,7 @@ int lds_create(const lds_config* cfg, int device, lds_handle** out) {
   e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return fail(LDS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
   if (prop.major != 10) return fail(LDS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  (void)lds::knobs();     // the run-time switches are read here, once per process
   lds_handle* h = new lds_handle();
   h->cfg = *cfg;
   h->device = device;
@@ -664,6 +686,7 @@ void lds_destroy(lds_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->arena) cudaFree(h->arena);
+  if (h->temb_arena) cudaFree(h->temb_arena);
   if (h->warena) cudaFree(h->warena);
   if (h->wharena) cudaFree(h->wharena);
   if (h->barena) cudaFree(h->barena);
@@ -946,8 +969,6 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
   }
   if ((int64_t)B * T > (1ll << 30)) return fail(LDS_ERR_INVALID, "B*T too large");
   LDS_CK(h, cudaSetDevice(h->device));
-  LDS_CK(h, cudaDeviceSynchronize());
-  if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
   h->planned = false;
   const lds_config& c = h->cfg;
   const int nb = c.n_blocks, L = c.n_layers;
@@ -977,11 +998,6 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
   }
   (void)max_c;
   const int rows_t = std::max(1, n_nfe);
-  want(&h->temb, (size_t)rows_t * h->temb_total);
-  want(&h->temb_single, (size_t)h->temb_total);
-  want(&h->sin_dev, (size_t)rows_t * ch[0]);
-  want(&h->e1, (size_t)rows_t * h->temb_dim);
-  want(&h->e2, (size_t)rows_t * h->temb_dim);
   want(&h->cond_part, M0 * ch[0]);
   want(&h->spk_rows, (size_t)B * c.n_hidden);
   want(&h->gn_part, (size_t)B * ((T + GN_ROWS - 1) / GN_ROWS) * c.norm_groups * 3);
@@ -1010,9 +1026,38 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
   for (int i = 0; i < 3; ++i) want(&h->mbuf[i], nx);
   want(&h->io_a, nx); want(&h->io_b, nx);
   h->arena_floats = off;
-  LDS_CK(h, cudaMalloc(&h->arena, off * sizeof(float)));
+  // The arenas only grow.  Work already enqueued on the caller's streams may still use the old allocation, so the device is
+  // synchronised before a free — and only then: re-planning for a batch that fits (e.g. the shorter segments of
+  // infer_from_long_audio, tools/infer_tools.py:84-117) neither synchronises nor allocates.
+  bool synced = false;
+  auto sync_once = [&]() -> cudaError_t {
+    if (synced) return cudaSuccess;
+    synced = true;
+    return cudaDeviceSynchronize();
+  };
+  if (off > h->arena_cap) {
+    LDS_CK(h, sync_once());
+    if (h->arena) { cudaFree(h->arena); h->arena = nullptr; h->arena_cap = 0; }
+    LDS_CK(h, cudaMalloc(&h->arena, off * sizeof(float)));
+    h->arena_cap = off;
+  }
   for (auto& s : slots) *s.first = h->arena + s.second;
-  if (h->barena) { cudaFree(h->barena); h->barena = nullptr; }
+  {  // time-conditioning tables: [rows_t, temb_total] + one row for lds_denoise + the MLP scratch
+    size_t toff = 0;
+    auto ttake = [&](size_t n) { size_t o = toff; toff += (n + 63) / 64 * 64; return o; };
+    const size_t o_temb = ttake((size_t)rows_t * h->temb_total), o_single = ttake((size_t)h->temb_total),
+                 o_sin = ttake((size_t)rows_t * ch[0]), o_e1 = ttake((size_t)rows_t * h->temb_dim), o_e2 = ttake((size_t)rows_t * h->temb_dim);
+    if (toff > h->temb_cap) {
+      LDS_CK(h, sync_once());
+      if (h->temb_arena) { cudaFree(h->temb_arena); h->temb_arena = nullptr; h->temb_cap = 0; }
+      LDS_CK(h, cudaMalloc(&h->temb_arena, toff * sizeof(float)));
+      h->temb_cap = toff;
+      h->temb_key.clear();
+    }
+    float* tb = h->temb_arena;
+    if (h->temb != tb + o_temb || h->sin_dev != tb + o_sin) h->temb_key.clear();   // layout moved: recompute
+    h->temb = tb + o_temb; h->temb_single = tb + o_single; h->sin_dev = tb + o_sin; h->e1 = tb + o_e1; h->e2 = tb + o_e2;
+  }
   h->barena_elems = 0;
   if (h->parts) {
     const size_t P = (size_t)h->parts;
@@ -1042,14 +1087,26 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
     wantb(&h->k_b, att_max * P);
     wantb(&h->vt_b, vt_max * P);
     h->barena_elems = boff;
-    LDS_CK(h, cudaMalloc(&h->barena, boff * sizeof(__nv_bfloat16)));
+    if (boff > h->barena_cap) {
+      LDS_CK(h, sync_once());
+      if (h->barena) { cudaFree(h->barena); h->barena = nullptr; h->barena_cap = 0; }
+      LDS_CK(h, cudaMalloc(&h->barena, boff * sizeof(__nv_bfloat16)));
+      h->barena_cap = boff;
+    }
     for (auto& b : bslots) *b.first = h->barena + b.second;
   }
 
-  // ---- per-step time conditioning (batch invariant) ----
+  // ---- per-step time conditioning (batch invariant; depends on the timestep rows only, so a re-plan for another (B, T)
+  //      with the same sampler program reuses the table) ----
   if (n_nfe > 0) {
-    LDS_TRY(run_temb(h, 0, t_sinusoid, n_nfe, h->temb));
-    LDS_CK(h, cudaStreamSynchronize(0));
+    const size_t nsin = (size_t)n_nfe * ch[0];
+    const bool same = h->temb_key.size() == nsin && memcmp(h->temb_key.data(), t_sinusoid, nsin * sizeof(float)) == 0;
+    if (!same) {
+      LDS_CK(h, sync_once());   // the table may still be read by enqueued work of the previous program
+      LDS_TRY(run_temb(h, 0, t_sinusoid, n_nfe, h->temb));
+      LDS_CK(h, cudaStreamSynchronize(0));
+      h->temb_key.assign(t_sinusoid, t_sinusoid + nsin);
+    }
   }
   h->planned = true;
   return LDS_OK;
@@ -1128,6 +1185,21 @@ int lds_sample_begin(lds_handle* h, const float* cond_BTH, const float* x_init_B
   h->m_cur = 0;
   return launched(h, s, PC_LAYOUT, 0, 8.0 * h->B * h->T * h->cfg.out_dims,
                   launch_transpose_bct_to_btc(x_init_BMT, h->x, h->B, h->cfg.out_dims, h->T, 1.f, s), "transpose");
+}
+
+int lds_sample_begin_shallow(lds_handle* h, const float* cond_BTH, const float* gt_spec_BTM, const float* noise_BMT, float sqrt_acp,
+                             float sqrt_1m_acp, void* stream) {
+  if (!h || !h->planned || h->n_nfe <= 0) return fail(LDS_ERR_INVALID, "lds_sample_begin_shallow: no sampler program planned");
+  if (!cond_BTH || !gt_spec_BTM || !noise_BMT) return fail(LDS_ERR_INVALID, "lds_sample_begin_shallow: null tensor");
+  if (h->sticky != cudaSuccess) return fail(LDS_ERR_CUDA, "handle is in a failed state: %s", cudaGetErrorString(h->sticky));
+  cudaStream_t s = (cudaStream_t)stream;
+  LDS_CK(h, cudaSetDevice(h->device));
+  if (h->prof.enabled) { prof_reset(h); LDS_TRY(prof_mark(h, s)); }
+  LDS_TRY(bind_cond(h, s, cond_BTH));
+  h->m_cur = 0;
+  return launched(h, s, PC_SOLVER, 0, 12.0 * h->B * h->T * h->cfg.out_dims,
+                  launch_q_sample(h->x, gt_spec_BTM, noise_BMT, h->cfg.acoustic_scale, sqrt_acp, sqrt_1m_acp, h->B, h->T,
+                                  h->cfg.out_dims, s), "q_sample");
 }
 
 int lds_sample_steps(lds_handle* h, int k0, int k1, const float* step_noise, void* stream) {
@@ -1228,7 +1300,7 @@ int lds_sample(lds_handle* h, const float* cond_BTH, const float* x_init_BMT, co
 }
 
 int64_t lds_workspace_bytes(const lds_handle* h) {
-  return h ? (int64_t)((h->arena_floats + h->warena_floats) * sizeof(float) + (h->barena_elems + h->wharena_elems) * 2) : 0;
+  return h ? (int64_t)((h->arena_floats + h->temb_cap + h->warena_floats) * sizeof(float) + (h->barena_elems + h->wharena_elems) * 2) : 0;
 }
 int64_t lds_kernel_launches(const lds_handle* h) { return h ? h->launches : 0; }
 
@@ -1332,6 +1404,79 @@ int lds_op_qkv_attention_tc(const void* x_planes, const void* w_qkv, int B, int 
   a.q = g.q_out; a.k = g.k_out; a.vt = g.vt_out; a.out = (__nv_bfloat16*)out_planes;
   a.B = B; a.T = T; a.T_pad = t_pad; a.H = H; a.d = C / H; a.dpad = dpad; a.parts = parts;
   return op_status(lds::launch_attention_tc(a, s), "lds_op_qkv_attention_tc(attention)");
+}
+
+
+// ---- solver / layout kernels (solver.cu), one entry point per kernel ----
+#define LDS_OP_NN(...)                                                               \
+  do {                                                                               \
+    const void* ptrs__[] = {__VA_ARGS__};                                            \
+    for (const void* q__ : ptrs__)                                                   \
+      if (!q__) return fail(LDS_ERR_INVALID, "%s: null tensor", __func__);           \
+  } while (0)
+
+int lds_op_x0_pred(const float* x, const float* eps, float sigma, float alpha, float* m, int64_t n, void* stream) {
+  LDS_OP_NN(x, eps, m);
+  return op_status(lds::launch_x0_pred(x, eps, sigma, alpha, m, n, (cudaStream_t)stream), __func__);
+}
+int lds_op_dpm_update(float* x, const float* m0, const float* m1, float cx, float cm, float hcm, float ir0, int order, int64_t n,
+                      void* stream) {
+  LDS_OP_NN(x, m0);
+  if (order != 1 && order != 2) return fail(LDS_ERR_INVALID, "lds_op_dpm_update: order must be 1 or 2");
+  if (order == 2 && !m1) return fail(LDS_ERR_INVALID, "lds_op_dpm_update: order 2 needs m1");
+  return op_status(lds::launch_dpm_update(x, m0, m1, cx, cm, hcm, ir0, order, n, (cudaStream_t)stream), __func__);
+}
+int lds_op_unipc_predict(const float* x, const float* m0, const float* m1, float cx, float cmE, float aB, float rk, float rho_p,
+                         int order, float* xb, float* xp, int64_t n, void* stream) {
+  LDS_OP_NN(x, m0, xb, xp);
+  if (order != 1 && order != 2) return fail(LDS_ERR_INVALID, "lds_op_unipc_predict: order must be 1 or 2");
+  if (order == 2 && !m1) return fail(LDS_ERR_INVALID, "lds_op_unipc_predict: order 2 needs m1");
+  return op_status(lds::launch_unipc_predict(x, m0, m1, cx, cmE, aB, rk, rho_p, order, xb, xp, n, (cudaStream_t)stream), __func__);
+}
+int lds_op_unipc_correct(const float* xb, const float* m0, const float* m1, const float* mt, float aB, float rk, float rho_c0,
+                         float rho_c1, int order, float* x, int64_t n, void* stream) {
+  LDS_OP_NN(xb, m0, mt, x);
+  if (order != 1 && order != 2) return fail(LDS_ERR_INVALID, "lds_op_unipc_correct: order must be 1 or 2");
+  if (order == 2 && !m1) return fail(LDS_ERR_INVALID, "lds_op_unipc_correct: order 2 needs m1");
+  return op_status(lds::launch_unipc_correct(xb, m0, m1, mt, aB, rk, rho_c0, rho_c1, order, x, n, (cudaStream_t)stream), __func__);
+}
+int lds_op_ddpm_step(float* x_BTM, const float* eps_BTM, const float* noise_BMT, float c_recip, float c_recipm1, float pm1, float pm2,
+                     float sig, int B, int T, int M, void* stream) {
+  LDS_OP_NN(x_BTM, eps_BTM, noise_BMT);
+  if (B < 1 || T < 1 || M < 1) return fail(LDS_ERR_INVALID, "lds_op_ddpm_step: bad shape");
+  return op_status(lds::launch_ddpm_step(x_BTM, eps_BTM, noise_BMT, c_recip, c_recipm1, pm1, pm2, sig, B, T, M, (cudaStream_t)stream), __func__);
+}
+int lds_op_ddim_step(float* x, const float* eps, float sqrt_at, float coef, float sqrt_aprev, int64_t n, void* stream) {
+  LDS_OP_NN(x, eps);
+  return op_status(lds::launch_ddim_step(x, eps, sqrt_at, coef, sqrt_aprev, n, (cudaStream_t)stream), __func__);
+}
+int lds_op_pndm_update(const float* x, const float* e, const float* h1, const float* h2, const float* h3, float d, float k1, float k2,
+                       int mode, float* out, int64_t n, void* stream) {
+  LDS_OP_NN(x, e, out);
+  if (mode < 0 || mode > 4 || (mode >= 1 && !h1) || (mode >= 3 && !h2) || (mode >= 4 && !h3))
+    return fail(LDS_ERR_INVALID, "lds_op_pndm_update: mode %d needs its history tensors", mode);
+  return op_status(lds::launch_pndm_update(x, e, h1 ? h1 : e, h2 ? h2 : e, h3 ? h3 : e, d, k1, k2, mode, out, n, (cudaStream_t)stream), __func__);
+}
+int lds_op_q_sample(float* x_BTM, const float* gt_BTM, const float* noise_BMT, float acoustic_scale, float sqrt_acp, float sqrt_1m_acp,
+                    int B, int T, int M, void* stream) {
+  LDS_OP_NN(x_BTM, gt_BTM, noise_BMT);
+  if (B < 1 || T < 1 || M < 1) return fail(LDS_ERR_INVALID, "lds_op_q_sample: bad shape");
+  return op_status(lds::launch_q_sample(x_BTM, gt_BTM, noise_BMT, acoustic_scale, sqrt_acp, sqrt_1m_acp, B, T, M, (cudaStream_t)stream), __func__);
+}
+int lds_op_cast_gather(const float* in, void* out_bf16, int B, int t_in, int t_out, int C, int parts, int mode, float scale, void* stream) {
+  LDS_OP_NN(in, out_bf16);
+  if (B < 1 || t_in < 1 || t_out < 1) return fail(LDS_ERR_INVALID, "lds_op_cast_gather: bad shape");
+  return op_status(lds::launch_cast_gather(in, (__nv_bfloat16*)out_bf16, B, t_in, t_out, C, parts, mode, scale, (cudaStream_t)stream), __func__);
+}
+int lds_op_transpose(const float* in, float* out, int B, int C, int T, float scale, int to_channels_last, void* stream) {
+  LDS_OP_NN(in, out);
+  if (B < 1 || C < 1 || T < 1) return fail(LDS_ERR_INVALID, "lds_op_transpose: bad shape");
+  return op_status(to_channels_last ? lds::launch_transpose_bct_to_btc(in, out, B, C, T, scale, (cudaStream_t)stream)
+                                    : lds::launch_transpose_btc_to_bct(in, out, B, C, T, scale, (cudaStream_t)stream), __func__);
+}
+int lds_op_div_copy(const float* in, float* out, int64_t n, float divisor, void* stream) {
+  LDS_OP_NN(in, out);
+  return op_status(lds::launch_div_copy(in, out, n, divisor, (cudaStream_t)stream), __func__);
 }
 
 }  // extern "C"

@@ -13,11 +13,20 @@ namespace lds {
 // global memory (blocks until the previous kernel has completed and flushed), and are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization: launch latency and the next kernel's prologue (barrier init, TMEM
 // allocation, tensor-map fetch) then hide behind the tail wave of the previous kernel.  LDS_PDL=0 turns the attribute off.
+//
+// Run-time switches (A/B measurements only; none selects a CPU path or changes results): read ONCE per process, on the
+// first call of knobs() — lds_create calls it — from the environment of the process that loads the library.
+struct Knobs {
+  int gn_mode = 2;      // LDS_GN_MODE   2 persistent cluster GroupNorm, 1 one CTA per slab, 0 stats + apply
+  int att_pa128 = 2;    // LDS_ATT_PA128 attention pass A over 128-key steps: 2 everywhere, 1 not for bf16 d > 32, 0 off
+  bool pdl = true;      // LDS_PDL       programmatic dependent launch attribute on the hot kernels
+};
+const Knobs& knobs();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
-bool pdl_enabled();
+inline bool pdl_enabled() { return knobs().pdl; }
 // Kernel attributes (opt-in shared memory) are per device: true exactly once per (call site, device of the calling thread).
 inline bool first_use_on_this_device(unsigned long long& seen) {
   int d = 0;
@@ -102,8 +111,6 @@ struct AttnTcArgs {
   int B = 0, T = 0, T_pad = 0, H = 0, d = 0, dpad = 0, parts = 1;
 };
 cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s);
-// CTA-pair (cta_group::2) variant for head dim <= 32 in split mode (attention_pair.cu); chosen by launch_attention_tc.
-cudaError_t launch_attention_pair(const AttnTcArgs& a, cudaStream_t s);
 inline void tc_set_split_pairs(TcGemmArgs& a) {   // lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
   static const int pa[6] = {2, 0, 1, 1, 0, 0}, pw[6] = {0, 2, 1, 0, 1, 0};
   a.a_parts = a.w_parts = 3; a.n_pairs = 6;
@@ -172,6 +179,10 @@ cudaError_t launch_unipc_correct(const float* xb, const float* m0, const float* 
 // DDPM ancestral step; noise is in the reference layout [B, M, T] and is transposed on the fly.
 cudaError_t launch_ddpm_step(float* x, const float* eps, const float* noise_BMT, float c_recip, float c_recipm1,
                              float pm1, float pm2, float sig, int B, int T, int M, cudaStream_t s);
+
+// Shallow-diffusion start: x[B,T,M] = sqrt_acp*(gt[B,T,M]*acoustic_scale) + sqrt_1m_acp*noise[B,M,T]   (diffusion.py:169-171,208-212)
+cudaError_t launch_q_sample(float* x, const float* gt_BTM, const float* noise_BMT, float acoustic_scale, float sqrt_acp,
+                            float sqrt_1m_acp, int B, int T, int M, cudaStream_t s);
 
 // DDIM step: x = sqrt_aprev * (x / sqrt_at + coef * eps)                                   (diffusion.py:131)
 cudaError_t launch_ddim_step(float* x, const float* eps, float sqrt_at, float coef, float sqrt_aprev, int64_t n, cudaStream_t s);

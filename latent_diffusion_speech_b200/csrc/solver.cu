@@ -179,6 +179,28 @@ __global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict_
   }
 }
 
+// Shallow-diffusion start (diffusion.py:208-212,169-171): x[b,t,m] <- sa*(gt[b,t,m]*ascale) + sb*noise[b,m,t], i.e.
+// q_sample(norm_spec(gt_spec).transpose(1,2)[:,None], t=k_step-1, noise) written straight in the channels-last state layout;
+// same tiling as the DDPM step (transposed noise read through shared memory).
+__global__ void q_sample_kernel(float* __restrict__ x, const float* __restrict__ gt, const float* __restrict__ noise,
+                                float ascale, float sa, float sb, int T, int M) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const float* nz = noise + (size_t)b * M * T;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int m = m0 + j, t = t0 + threadIdx.x;
+    if (m < M && t < T) tile[j][threadIdx.x] = nz[(size_t)m * T + t];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, m = m0 + threadIdx.x;
+    if (t < T && m < M) {
+      const size_t idx = ((size_t)b * T + t) * M + m;
+      x[idx] = add(mul(sa, mul(gt[idx], ascale)), mul(sb, tile[threadIdx.x][j]));
+    }
+  }
+}
+
 __global__ void div_copy_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t n, float d) {
   LDS_VEC4_LOOP(n) {
     const float4 a = in[i];
@@ -251,11 +273,6 @@ inline int grid_for(int64_t nvec) {
 
 }  // namespace
 
-bool pdl_enabled() {
-  static const bool on = !(getenv("LDS_PDL") && atoi(getenv("LDS_PDL")) == 0);
-  return on;
-}
-
 #define V4(p) reinterpret_cast<const float4*>(p)
 #define V4W(p) reinterpret_cast<float4*>(p)
 
@@ -288,6 +305,12 @@ cudaError_t launch_ddpm_step(float* x, const float* eps, const float* noise_BMT,
                              float pm1, float pm2, float sig, int B, int T, int M, cudaStream_t s) {
   dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
   ddpm_step_kernel<<<grid, block, 0, s>>>(x, eps, noise_BMT, c_recip, c_recipm1, pm1, pm2, sig, T, M);
+  return cudaGetLastError();
+}
+cudaError_t launch_q_sample(float* x, const float* gt_BTM, const float* noise_BMT, float acoustic_scale, float sqrt_acp,
+                            float sqrt_1m_acp, int B, int T, int M, cudaStream_t s) {
+  dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
+  q_sample_kernel<<<grid, block, 0, s>>>(x, gt_BTM, noise_BMT, acoustic_scale, sqrt_acp, sqrt_1m_acp, T, M);
   return cudaGetLastError();
 }
 cudaError_t launch_ddim_step(float* x, const float* eps, float sqrt_at, float coef, float sqrt_aprev, int64_t n, cudaStream_t s) {

@@ -97,6 +97,23 @@ class GaussianDiffusion(nn.Module):
         self._program_cache[key] = prog
         return prog
 
+    def _q_sample_scalars(self, t_total: int):
+        """(sqrt_alphas_cumprod[t], sqrt_one_minus_alphas_cumprod[t]) at t = k_step - 1 as Python floats (exact fp32 values)."""
+        key = ("q_sample", int(t_total))
+        hit = self._program_cache.get(key)
+        if hit is None:
+            hit = (float(self.sqrt_alphas_cumprod[t_total - 1]), float(self.sqrt_one_minus_alphas_cumprod[t_total - 1]))
+            self._program_cache[key] = hit
+        return hit
+
+    def invalidate_programs(self) -> None:
+        """The cached sampler programs derive from the schedule buffers, which are part of the checkpoint."""
+        self._program_cache.clear()
+
+    def _apply(self, fn, *a, **k):
+        self._program_cache.clear()
+        return super()._apply(fn, *a, **k)
+
     def prepare(self, eng, b: int, t_frames: int, method, infer_speedup: int, t_total: int):
         """Installs the sampler program and workspace for a [b, t_frames] batch (no-op when unchanged)."""
         kind, t_sin, rows = self.sampler_program(method, infer_speedup, t_total)
@@ -116,21 +133,22 @@ class GaussianDiffusion(nn.Module):
             raise RuntimeError("GaussianDiffusion is not attached to a Unit2Mel engine")
         b, t_frames, device = condition.shape[0], condition.shape[1], condition.device
         shape = (b, 1, self.out_dims, t_frames)
-        if gt_spec is None or k_step is None:
-            t_total = self.k_step
-            x = torch.randn(shape, device=device) if noise is None else noise.to(device)
-        else:
-            t_total = int(k_step)
-            x0 = self.norm_spec(gt_spec).transpose(1, 2)[:, None, :, :]
-            nz = torch.randn_like(x0) if noise is None else noise.to(device)
-            x = self.sqrt_alphas_cumprod[t_total - 1] * x0 + self.sqrt_one_minus_alphas_cumprod[t_total - 1] * nz
+        shallow = not (gt_spec is None or k_step is None)
+        t_total = int(k_step) if shallow else self.k_step
+        # the only host-side tensor work left on this path is the noise draw (the library has no RNG by contract)
+        nz = torch.randn(shape, device=device) if noise is None else noise.to(device)
         eng = self._engine_provider(device)
         kind, t_sin = self.prepare(eng, b, t_frames, method, infer_speedup, t_total)
         bar = None
         if use_tqdm:
             from tqdm import tqdm
             bar = tqdm(desc="sample time step", total=int(t_sin.shape[0]))
-        eng.sample_begin(condition, x.reshape(b, self.out_dims, t_frames))
+        if shallow:
+            # diffusion.py:208-212: x = q_sample(norm_spec(gt_spec)^T, t = k_step - 1, noise) — one fused kernel in the library
+            sa, sb = self._q_sample_scalars(t_total)
+            eng.sample_begin_shallow(condition, gt_spec, nz.reshape(b, self.out_dims, t_frames), sa, sb)
+        else:
+            eng.sample_begin(condition, nz.reshape(b, self.out_dims, t_frames))
         n = eng.num_steps
         if kind == st.SAMPLER_DDPM:
             chunk = max(1, int(self.ddpm_noise_chunk))

@@ -42,15 +42,31 @@ def gather_mels(mel_shard: torch.Tensor, n_items: int, group: Optional[dist.Proc
 
 
 def sharded_infer(model, units: torch.Tensor, spk_id: Optional[torch.Tensor], *, noise: Optional[torch.Tensor] = None,
-                  gather: bool = True, group: Optional[dist.ProcessGroup] = None, **forward_kwargs) -> torch.Tensor:
+                  gt_spec: Optional[torch.Tensor] = None, step_noise=None, gather: bool = True,
+                  group: Optional[dist.ProcessGroup] = None, out_dims: Optional[int] = None, **forward_kwargs) -> torch.Tensor:
     """Runs ``model(units[lo:hi], ...)`` for this rank's slice of the GLOBAL batch and gathers the mels.
 
-    ``units`` / ``spk_id`` / ``noise`` are the global tensors (each rank slices its own part, nothing is
-    scattered); per-utterance noise makes the result independent of the number of ranks."""
+    Every per-utterance input is given for the global batch and sliced here (nothing is scattered): ``units``,
+    ``spk_id``, ``noise`` ([B,1,M,T]), ``gt_spec`` ([B,T,M], shallow diffusion) and ``step_noise`` (callable
+    ``(j0, j1) -> [j1-j0, B, 1, M, T]``, DDPM).  Per-utterance noise makes the result independent of the number of ranks.
+    A rank whose shard is empty (fewer utterances than ranks) skips the model call and contributes zero rows
+    (``out_dims`` = mel bins of those rows; default ``model.decoder.out_dims``)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = units.shape[0]
+    for name, t in (("spk_id", spk_id), ("noise", noise), ("gt_spec", gt_spec)):
+        if t is not None and t.shape[0] != n:
+            raise ValueError(f"{name} has {t.shape[0]} rows, expected the global batch size {n}")
     lo, hi = shard_bounds(n, world, rank)
-    mel = model(units[lo:hi], None, spk_id=None if spk_id is None else spk_id[lo:hi], infer=True,
-                noise=None if noise is None else noise[lo:hi], **forward_kwargs)
+    if hi > lo:
+        local_step_noise = None
+        if step_noise is not None:
+            local_step_noise = lambda j0, j1: step_noise(j0, j1)[:, lo:hi]
+        mel = model(units[lo:hi], None, spk_id=None if spk_id is None else spk_id[lo:hi], infer=True,
+                    noise=None if noise is None else noise[lo:hi], gt_spec=None if gt_spec is None else gt_spec[lo:hi],
+                    step_noise=local_step_noise, **forward_kwargs)
+    else:
+        if out_dims is None:
+            out_dims = model.decoder.out_dims
+        mel = torch.zeros((0, units.shape[1], out_dims), dtype=torch.float32, device=units.device)
     return gather_mels(mel, n, group) if gather else mel

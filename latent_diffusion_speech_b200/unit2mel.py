@@ -71,6 +71,8 @@ class Unit2Mel(nn.Module):
         if self._engine is not None:
             self._engine.close()
         self._engine = None
+        if getattr(self, "decoder", None) is not None:
+            self.decoder.invalidate_programs()  # sampler programs are functions of the (checkpointed) schedule buffers
 
     def _apply(self, fn, *a, **k):
         self.invalidate_engine()

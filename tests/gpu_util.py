@@ -161,3 +161,98 @@ def op_qkv_attention_tc(x, wq, wk, wv, B, T, heads, parts):
     check(lib().lds_op_qkv_attention_tc(ptr(xp), ptr(wp), B, T, Cc, heads, dpad, parts, ptr(q), ptr(k), ptr(vt), ptr(out), stream()),
           "lds_op_qkv_attention_tc")
     return out.float().view(B * T, parts, Cc).double().sum(1)
+
+
+# ---- solver / layout kernels (csrc/solver.cu) ----
+def _f(v):
+    return float(v)
+
+
+def op_x0_pred(x, eps, sigma, alpha):
+    m = torch.empty_like(x)
+    check(lib().lds_op_x0_pred(ptr(x), ptr(eps), _f(sigma), _f(alpha), ptr(m), x.numel(), stream()), "lds_op_x0_pred")
+    return m
+
+
+def op_dpm_update(x, m0, m1, cx, cm, hcm, ir0, order):
+    x = x.clone()
+    check(lib().lds_op_dpm_update(ptr(x), ptr(m0), ptr(m1), _f(cx), _f(cm), _f(hcm), _f(ir0), order, x.numel(), stream()),
+          "lds_op_dpm_update")
+    return x
+
+
+def op_unipc_predict(x, m0, m1, cx, cmE, aB, rk, rho_p, order):
+    xb, xp = torch.empty_like(x), torch.empty_like(x)
+    check(lib().lds_op_unipc_predict(ptr(x), ptr(m0), ptr(m1), _f(cx), _f(cmE), _f(aB), _f(rk), _f(rho_p), order, ptr(xb), ptr(xp),
+                                     x.numel(), stream()), "lds_op_unipc_predict")
+    return xb, xp
+
+
+def op_unipc_correct(xb, m0, m1, mt, aB, rk, rho_c0, rho_c1, order):
+    x = torch.empty_like(xb)
+    check(lib().lds_op_unipc_correct(ptr(xb), ptr(m0), ptr(m1), ptr(mt), _f(aB), _f(rk), _f(rho_c0), _f(rho_c1), order, ptr(x),
+                                     xb.numel(), stream()), "lds_op_unipc_correct")
+    return x
+
+
+def op_ddpm_step(x_btm, eps_btm, noise_bmt, cr, crm1, pm1, pm2, sig):
+    B, T, M = x_btm.shape
+    x = x_btm.clone()
+    check(lib().lds_op_ddpm_step(ptr(x), ptr(eps_btm), ptr(noise_bmt), _f(cr), _f(crm1), _f(pm1), _f(pm2), _f(sig), B, T, M, stream()),
+          "lds_op_ddpm_step")
+    return x
+
+
+def op_ddim_step(x, eps, sqrt_at, coef, sqrt_aprev):
+    x = x.clone()
+    check(lib().lds_op_ddim_step(ptr(x), ptr(eps), _f(sqrt_at), _f(coef), _f(sqrt_aprev), x.numel(), stream()), "lds_op_ddim_step")
+    return x
+
+
+def op_pndm_update(x, e, h1, h2, h3, d, k1, k2, mode):
+    out = torch.empty_like(x)
+    check(lib().lds_op_pndm_update(ptr(x), ptr(e), ptr(h1), ptr(h2), ptr(h3), _f(d), _f(k1), _f(k2), mode, ptr(out), x.numel(), stream()),
+          "lds_op_pndm_update")
+    return out
+
+
+def op_q_sample(gt_btm, noise_bmt, ascale, sa, sb):
+    B, T, M = gt_btm.shape
+    x = torch.empty_like(gt_btm)
+    check(lib().lds_op_q_sample(ptr(x), ptr(gt_btm), ptr(noise_bmt), _f(ascale), _f(sa), _f(sb), B, T, M, stream()), "lds_op_q_sample")
+    return x
+
+
+def op_cast_gather(x_btc, t_out, parts, mode, scale=0.0):
+    B, t_in, Cc = x_btc.shape
+    width = parts * Cc * (3 if mode == 2 else 1)
+    out = torch.empty(B, t_out, width, device=x_btc.device, dtype=torch.bfloat16)
+    check(lib().lds_op_cast_gather(ptr(x_btc), ptr(out), B, t_in, t_out, Cc, parts, mode, float(scale), stream()), "lds_op_cast_gather")
+    return out
+
+
+def op_transpose(x, to_channels_last, scale=1.0):
+    if to_channels_last:
+        B, Cc, T = x.shape
+        out = torch.empty(B, T, Cc, device=x.device, dtype=torch.float32)
+    else:
+        B, T, Cc = x.shape
+        out = torch.empty(B, Cc, T, device=x.device, dtype=torch.float32)
+    check(lib().lds_op_transpose(ptr(x), ptr(out), B, Cc, T, float(scale), int(to_channels_last), stream()), "lds_op_transpose")
+    return out
+
+
+def op_div_copy(x, d):
+    out = torch.empty_like(x)
+    check(lib().lds_op_div_copy(ptr(x), ptr(out), x.numel(), float(d), stream()), "lds_op_div_copy")
+    return out
+
+
+def split_planes_ref(x, parts):
+    """fp32 [..., C] -> bf16 [..., parts*C] by the definition of the operand planes: hi = bf16(x), mid = bf16(x - hi), ..."""
+    planes, r = [], x.float()
+    for _ in range(parts):
+        p = r.to(torch.bfloat16)
+        planes.append(p)
+        r = r - p.float()
+    return torch.cat(planes, dim=-1)

@@ -20,13 +20,21 @@ def test_shard_bounds_cover_batch():
 
 
 class _FakeModel:
-    """Stands in for Unit2Mel.forward: a per-utterance function of (units, spk_id, noise)."""
+    """Stands in for Unit2Mel.forward: a per-utterance function of (units, spk_id, noise, gt_spec, step_noise)."""
 
-    def __call__(self, units, volume, spk_id=None, infer=True, noise=None, **kw):
-        return units[..., :4] * 2.0 + spk_id.float()[:, :, None] + noise[:, 0, :4, :].transpose(1, 2)
+    def __call__(self, units, volume, spk_id=None, infer=True, noise=None, gt_spec=None, step_noise=None, **kw):
+        out = units[..., :4] * 2.0 + spk_id.float()[:, :, None] + noise[:, 0, :4, :].transpose(1, 2)
+        if gt_spec is not None:
+            assert gt_spec.shape[0] == units.shape[0]
+            out = out + gt_spec[..., :4]
+        if step_noise is not None:
+            z = step_noise(0, 3)                        # [3, B_local, 1, M, T]
+            assert z.shape[1] == units.shape[0]
+            out = out + z.sum(0)[:, 0, :4, :].transpose(1, 2)
+        return out
 
 
-def _worker(rank, world, port, n_items, ret):
+def _worker(rank, world, port, n_items, shallow, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -34,8 +42,11 @@ def _worker(rank, world, port, n_items, ret):
         units = torch.randn(n_items, 6, 16, generator=g)
         spk = torch.randint(1, 9, (n_items, 1), generator=g)
         noise = torch.randn(n_items, 1, 8, 6, generator=g)
-        out = sharded_infer(_FakeModel(), units, spk, noise=noise)
-        want = _FakeModel()(units, None, spk_id=spk, noise=noise)
+        gt = torch.randn(n_items, 6, 8, generator=g) if shallow else None
+        steps = torch.randn(3, n_items, 1, 8, 6, generator=g)
+        sn = (lambda j0, j1: steps[j0:j1]) if shallow else None
+        out = sharded_infer(_FakeModel(), units, spk, noise=noise, gt_spec=gt, step_noise=sn, out_dims=4)
+        want = _FakeModel()(units, None, spk_id=spk, noise=noise, gt_spec=gt, step_noise=sn)
         ret[rank] = bool(torch.equal(out, want))
         lo, hi = shard_bounds(n_items, world, rank)
         part = gather_mels(want[lo:hi], n_items)
@@ -44,12 +55,19 @@ def _worker(rank, world, port, n_items, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_items", [4, 5])
-def test_sharded_infer_equals_unsharded_world2(n_items):
+# n_items = 1 < world: rank 1 has an empty shard (must not call the model, must still take part in the gather)
+@pytest.mark.parametrize("n_items,shallow", [(4, False), (5, False), (5, True), (1, True)])
+def test_sharded_infer_equals_unsharded_world2(n_items, shallow):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, port, n_items, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, n_items, shallow, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_sharded_infer_rejects_mismatched_global_inputs():
+    units = torch.randn(4, 6, 16)
+    with pytest.raises(ValueError):
+        sharded_infer(_FakeModel(), units, torch.ones(4, 1, dtype=torch.long), noise=torch.randn(4, 1, 8, 6), gt_spec=torch.randn(3, 6, 8))

@@ -229,15 +229,3 @@ def test_tc_qkv_attention(B, T, C, parts):
     e = G.errs(got, want)
     G.report(test="tc_qkv_attention", B=B, T=T, C=C, parts=parts, **e)
     assert e["max_abs"] <= (3e-5 if parts == 3 else 3e-2), e
-
-
-def test_pair_attention_experiment_subprocess():
-    """attention_pair.cu (cta_group::2 attention, LDS_ATT_PAIR=1; off by default because it measured slower) stays
-    parity-green: re-run the d = 32 attention cases in a subprocess with the switch on."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, LDS_ATT_PAIR="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k",
-                        "test_tc_qkv_attention and 256-3"], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
