@@ -11,12 +11,21 @@ replicated, no collective in the step loop) and the mels are all-gathered over N
 
 Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM; `e2e` = the same metric
 through the public API with pinned-host inputs (H2D of units/spk_id and D2H of the mel inside the timed region).
-`--impl reference` times the reference algorithm on the host CPU cores (the oracle port of the reference's
-PyTorch sampler — the reference is pure Python and cannot travel to the GPU box) on a bounded sample.
+`--impl reference` times the reference's own CPU sampler on the host cores on a bounded sample of the same workload: the
+UNMODIFIED `diffusion.unit2mel.Unit2Mel` staged under `baseline/_ref/` by `oracle/build_ref.py` (`kind: "reference"`), or —
+only when that directory is absent — the oracle port of it (`kind: "port"`).
+
+Besides the headline the default N-GPU run also reports (same JSON line):
+  `strong`             BASELINE configs[2] as BASELINE names it: global batch 512 x T=864, bf16, UniPC 10 NFE, split 512/N over the
+                       ranks through `distributed.sharded_infer`, per-utterance seeded inputs and noise, SHA-256 of utterances 0 and
+                       511 of the gathered mel (must be identical at every N)
+  `gpu_eager_baseline` (N=1) the reference PyTorch eager sampler on the same B200 (fp32 with TF32 off; autocast bf16), B=64 x T=864
+  `tf32_tflops_measured` (N=1) torch.matmul 8192^3 with TF32 on (the fp32-mode tensor peak SURVEY.md section 6 asks for)
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -46,8 +55,9 @@ WORKLOADS = {
     "pndm20_b64_t864_fp32": (64, 864, "pndm", 50, None, "fp32"),
 }
 HEADLINE = "dpm20_b64_t864_fp32"
-CPU_SAMPLE = dict(B=1, T=864)      # bounded CPU sample of the same workload (one utterance of the batch)
+CPU_SAMPLE_B = 4                   # utterances of the batch in the bounded CPU sample (same T, sampler and NFE as the workload)
 FRAME_RATE = 44100 / 512
+STRONG = dict(B=512, T=864, method="unipc", speedup=100, precision="bf16")    # BASELINE configs[2]
 
 
 def flops_per_utt_nfe(T: int) -> float:
@@ -108,50 +118,253 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def cpu_oracle_run(B: int, T: int, method: str, speedup: int, threads: int):
-    """One pass of the reference algorithm (oracle port) on the host CPU; returns seconds."""
-    import torch
-    from oracle import unit2mel_oracle as O
-    torch.set_num_threads(threads)
-    torch.manual_seed(1234)
-    from latent_diffusion_speech_b200.unit2mel import Unit2Mel
-    sd = {k: v.detach() for k, v in Unit2Mel(1280, 323, 128, 2, [256, 384, 512, 512], 8, 256, 1.0).state_dict().items()}
-    units, spk, noise, _, _ = O.synthetic_inputs(B, T)
+def workload_config(name: str, world: int) -> dict:
+    """The `config` object of the JSON line — identical for both arms (the reference arm times a bounded sample of it)."""
+    B, T, method, speedup, k_step, precision = WORKLOADS[name]
+    t_total = k_step if k_step is not None else 1000
+    nfe = t_total // speedup + (1 if method == "pndm" else 0)
+    return {"workload": name, "sampler": method, "nfe": nfe, "T": T, "batch_per_gpu": B, "global_batch": B * world,
+            "precision_mode": precision, "l2_policy": "inputs_exceed_l2 (units 283 MB/step, activations >1 GB)",
+            "parallelism": f"batch-shard x{world}, final NCCL all_gather" if world > 1 else "single GPU"}
 
-    def once():
-        t0 = time.perf_counter()
+
+class HostReference:
+    """The reference sampler on a device of PyTorch's choosing: the UNMODIFIED reference `Unit2Mel` staged under baseline/_ref
+    (kind "reference"), else the oracle port (kind "port").  Checker / baseline only — never on the product path."""
+
+    def __init__(self, device="cpu"):
+        import torch
+        from oracle import ref_import
+        self.torch, self.device = torch, torch.device(device)
+        self.model = ref_import.build_reference_model(1234)
+        if self.model is not None:
+            self.kind, self._ri, self.root = "reference", ref_import, ref_import.REFERENCE_ROOT
+            self.model = self.model.to(self.device)
+        else:
+            from oracle import unit2mel_oracle as O
+            from latent_diffusion_speech_b200.unit2mel import Unit2Mel
+            self.kind, self._O = "port", O
+            torch.manual_seed(1234)
+            self.sd = {k: v.detach().to(self.device) for k, v in Unit2Mel(1280, 323, 128, 2, [256, 384, 512, 512], 8, 256, 1.0).state_dict().items()}
+
+    def inputs(self, B, T, k_step=None):
+        torch = self.torch
+        g = torch.Generator().manual_seed(7)
+        units = torch.randn(B, T, 1280, generator=g).to(self.device)
+        spk = torch.randint(1, 324, (B, 1), generator=g).to(self.device)
+        gt = (torch.rand(B, T, 128, generator=g) * 14 - 12).to(self.device) if k_step is not None else None
+        return units, spk, gt
+
+    def run(self, units, spk, gt, method, speedup, k_step):
+        torch = self.torch
+        if self.kind == "reference":
+            return self._ri.reference_infer(self.model, units, spk, method, speedup, gt_spec=gt, k_step=k_step)
+        B, T = units.shape[:2]
+        noise = torch.randn(B, 1, 128, T, device=self.device)
+        n_steps = (k_step or 1000) if (method is None or speedup == 1) else 0
+        steps = [torch.randn(B, 1, 128, T, device=self.device) for _ in range(n_steps)]
         with torch.no_grad():
-            O.unit2mel_infer(sd, O.DEFAULT_CFG, units, spk, noise, method, speedup)
-        return time.perf_counter() - t0
-    return once
+            return self._O.unit2mel_infer(self.sd, self._O.DEFAULT_CFG, units, spk, noise, method, speedup, gt_spec=gt, k_step=k_step,
+                                          step_noises=steps)
+
+    def timer(self, B, T, method, speedup, k_step):
+        units, spk, gt = self.inputs(B, T, k_step)
+
+        def once():
+            t0 = time.perf_counter()
+            self.run(units, spk, gt, method, speedup, k_step)
+            if self.device.type == "cuda":
+                self.torch.cuda.synchronize()
+            return time.perf_counter() - t0
+        return once
+
+
+def cpu_sample_batch(name: str) -> int:
+    """Utterances in one bounded CPU step: 4 of the batch for the 20/10-NFE 10 s workloads (about 7 s on 16 cores), one for the
+    1000-step and the 30 s ones."""
+    B, T, method, speedup, k_step, _ = WORKLOADS[name]
+    heavy = (method is None or speedup == 1) or T > 1000
+    return 1 if heavy else min(CPU_SAMPLE_B, B)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU sampler (oracle port) on all host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU sampler on all host cores; each step = a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    B, T, method, speedup, _, _ = WORKLOADS[args.workload]
+    B, T, method, speedup, k_step, _ = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    once = cpu_oracle_run(CPU_SAMPLE["B"], T, method, speedup, cores)
-    for _ in range(min(args.warmup, 1)):       # one CPU warm-up is enough to page the weights in
+    torch.set_num_threads(cores)
+    ref = HostReference("cpu")
+    sb = cpu_sample_batch(args.workload)
+    once = ref.timer(sb, T, method, speedup, k_step)
+    for _ in range(args.warmup):
         once()
     times = [once() for _ in range(args.steps)]
     sec = sum(times) / len(times)
-    val = CPU_SAMPLE["B"] * T / sec
-    sample = f"B={CPU_SAMPLE['B']} utterance of the batch x T={T}, {method} {1000 // speedup} NFE, fp32, torch CPU {cores} threads"
+    val = sb * T / sec
+    cfg = workload_config(args.workload, int(os.environ.get("WORLD_SIZE", "1")))
+    what = (f"unmodified reference diffusion.unit2mel.Unit2Mel ({os.path.relpath(ref.root, ROOT)})" if ref.kind == "reference"
+            else "oracle port of the reference sampler")
+    sample = (f"{sb} of the {B} utterances x T={T}, {method or 'ddpm'} {cfg['nfe']} NFE, fp32, {what}, torch CPU {cores} threads, "
+              f"{args.warmup} warm-up + {args.steps} timed passes")
     line = {
         "impl": "reference", "metric": "mel_frames_per_sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "sampler": method, "nfe": 1000 // speedup, "T": T, "batch_per_gpu": B,
-                   "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": ref.kind, "sample": sample},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "rtf": sec / (CPU_SAMPLE["B"] * T / FRAME_RATE),
+        "rtf": sec / (sb * T / FRAME_RATE),
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(name: str) -> dict:
+    """Bounded CPU sample inside the GPU arm (rank 0, N=1): BASELINE configs[0] exactly (B=1, T=432, DPM-Solver 20 NFE; median of
+    3 after 1 warm-up) and one bounded sample of the benched workload itself."""
+    import torch
+    B, T, method, speedup, k_step, _ = WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = HostReference("cpu")
+    c1 = ref.timer(1, 432, "dpm-solver", 50, None)
+    c1()
+    sec1 = sorted(c1() for _ in range(3))[1]
+    sb = cpu_sample_batch(name)
+    once = ref.timer(sb, T, method, speedup, k_step)
+    once()
+    sec = once()
+    what = (f"unmodified reference Unit2Mel ({os.path.relpath(ref.root, ROOT)})" if ref.kind == "reference"
+            else "oracle port of the reference sampler")
+    return {"value": sb * T / sec, "unit": "frames/s", "cores": cores, "kind": ref.kind,
+            "sample": f"{sb} x T={T}, {method or 'ddpm'} fp32, {what}; one timed pass after one warm-up",
+            "config1_b1_t432_dpm20": {"value": 432 / sec1, "unit": "frames/s", "seconds": sec1, "rtf": sec1 / (432 / FRAME_RATE),
+                                      "sample": "BASELINE configs[0] exactly: B=1 x T=432, DPM-Solver 20 NFE; median of 3 after 1 warm-up"}}
+
+
+def gpu_eager_leg(dev, B: int, T: int, method: str, speedup: int) -> dict:
+    """SURVEY.md §0.1 'the bar to beat': the reference sampler as PyTorch eager dispatches it on this B200 (cuDNN / cuBLAS / SDPA),
+    in IEEE fp32 (TF32 off — the only setting that meets the fp32 parity bar) and under autocast(bf16)."""
+    import torch
+    out = {"B": B, "T": T, "sampler": method, "nfe": 1000 // speedup}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        ref = HostReference(dev)
+        out["kind"] = ref.kind
+        units, spk, gt = ref.inputs(B, T)
+        for mode in ("fp32_ieee", "autocast_bf16", "fp32_tf32"):
+            on = mode == "fp32_tf32"
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = on
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "autocast_bf16" else contextlib.nullcontext()
+            try:
+                with ctx:
+                    ref.run(units, spk, gt, method, speedup, None)        # warm-up (cuDNN autotune, allocator)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(2):
+                        ref.run(units, spk, gt, method, speedup, None)
+                    e1.record()
+                    torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 2
+                out[mode] = {"frames_per_sec": B * T / (ms * 1e-3), "ms_per_step": ms}
+            except Exception as ex:   # e.g. the dtype clash the survey notes for non-autocast bf16
+                out[mode] = {"error": repr(ex)[:200]}
+        del ref
+    except Exception as ex:
+        out["error"] = repr(ex)[:300]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+    return out
+
+
+def tf32_peak(dev) -> dict:
+    """torch.matmul fp32 8192^3 with TF32 allowed: best of 10 (burst) and back to back for 2 s (sustained), like MEASURED_PEAKS.json."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(2000 / best))
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record(); torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n ** 3
+        return {"burst": fl / (best * 1e-3) / 1e12, "sustained": fl / (sus * 1e-3) / 1e12, "how": "torch.matmul fp32 8192^3, allow_tf32=True"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+
+
+def strong_leg(dev, world: int, rank: int, steps: int) -> dict:
+    """BASELINE configs[2]: global batch 512 x T=864, bf16 mode, UniPC 10 NFE, split 512/N across the ranks (strong scaling) through
+    distributed.sharded_infer; inputs and noise are seeded PER UTTERANCE (global index), so the gathered mel is bit-identical at
+    every N — the SHA-256 of utterances 0 and 511 in the line proves it across the driver's N = 1, 2, 4, 8 runs."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from latent_diffusion_speech_b200.distributed import shard_bounds, gather_mels
+    from latent_diffusion_speech_b200.unit2mel import Unit2Mel
+    Bg, T = STRONG["B"], STRONG["T"]
+    lo, hi = shard_bounds(Bg, world, rank)
+    torch.manual_seed(1234)
+    model = Unit2Mel(1280, 323, 128, 2, [256, 384, 512, 512], 8, 256, 1.0).eval().to(dev).set_precision(STRONG["precision"])
+    units = torch.empty(hi - lo, T, 1280, device=dev)
+    noise = torch.empty(hi - lo, 1, 128, T, device=dev)
+    spk = torch.empty(hi - lo, 1, dtype=torch.int64, device=dev)
+    g = torch.Generator(device=dev)
+    for b in range(lo, hi):                                  # global utterance index -> seed
+        g.manual_seed(100000 + b)
+        units[b - lo] = torch.randn(T, 1280, generator=g, device=dev)
+        noise[b - lo] = torch.randn(1, 128, T, generator=g, device=dev)
+        spk[b - lo, 0] = 1 + (b * 7919) % 323
+
+    def step():
+        mel = model(units, None, spk_id=spk, infer=True, infer_speedup=STRONG["speedup"], method=STRONG["method"], noise=noise)
+        return gather_mels(mel, Bg) if world > 1 else mel
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(2):
+            full = step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            full = step()
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    out = {"workload": "unipc10_b512_t864_bf16 (BASELINE configs[2])", "scaling": "strong", "global_batch": Bg, "batch_per_gpu": hi - lo,
+           "T": T, "nfe": 10, "dtype": "bf16", "ms_per_step": ms, "value": Bg * T / (ms * 1e-3), "unit": "frames/s", "steps": steps, "warmup": 2,
+           "model_tflops_per_s": Bg * 10 * flops_per_utt_nfe(T) / (ms * 1e-3) / 1e12}
+    if rank == 0:
+        sha = lambda t: hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()[:16]
+        out["sha256_utt0"], out["sha256_utt_last"] = sha(full[0]), sha(full[Bg - 1])
+    model.invalidate_engine()
+    del model, units, noise, full
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -159,7 +372,6 @@ def run_ours(args):
     import torch.distributed as dist
     from latent_diffusion_speech_b200.distributed import gather_mels
     from latent_diffusion_speech_b200.unit2mel import Unit2Mel
-    from oracle import unit2mel_oracle as O   # synthetic input generator + CPU baseline leg only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,8 +405,10 @@ def run_ours(args):
                     noise=noise)
         return gather_mels(mel, B * world) if world > 1 else mel
 
-    # result landing zone in pinned host memory: rank 0 reads the gathered global mel, the other ranks their own shard
-    mel_h = torch.empty((B * world if rank == 0 else B), T, 128, dtype=torch.float32).pin_memory()
+    # result landing zone in pinned host memory: every rank (= process) reads its OWN shard back over its own PCIe link, in
+    # parallel; the NVLink all-gather still runs, so the whole batch is also resident on every GPU (north star: "a final NCCL
+    # gather of mels"), but no single rank serialises a D2H of the global mel behind it (r01: 1.5 % of the N=8 step).
+    mel_h = torch.empty(B, T, 128, dtype=torch.float32).pin_memory()
 
     def step_e2e():
         u = units_h.to(dev, non_blocking=True)
@@ -202,8 +416,9 @@ def run_ours(args):
         gt = None if gt_h is None else gt_h.to(dev, non_blocking=True)
         # noise: torch.randn on the device, as the reference draws it
         mel = model(u, None, spk_id=s, gt_spec=gt, k_step=k_step, infer=True, infer_speedup=speedup, method=method)
-        full = gather_mels(mel, B * world) if world > 1 else mel
-        mel_h.copy_(full if rank == 0 else mel, non_blocking=True)
+        mel_h.copy_(mel, non_blocking=True)
+        if world > 1:
+            gather_mels(mel, B * world)
         torch.cuda.current_stream().synchronize()
         return mel_h
 
@@ -265,7 +480,9 @@ def run_ours(args):
             "bf16": "gemm_tc_kernel (tcgen05/TMEM/TMA implicit-GEMM conv k3 / 1x1 / linear, bf16 operands)",
             "fp32_ffma": "gemm_f32_kernel (implicit-GEMM conv k3 / 1x1 / linear, fp32 FFMA)"}[precision]
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")     # ncu dram bytes per gemm_tc launch (one capture per change)
+    tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")     # ncu dram bytes per gemm_tc launch (one capture per change)
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if os.path.exists(tp) and precision in ("fp32", "bf16") and (B, T) == (64, 864):
         tj = json.load(open(tp))
         traffic, traffic_src = tj[precision]["traffic_bytes_per_launch"], tj["source"]
@@ -288,36 +505,45 @@ def run_ours(args):
                       # algorithmic bytes / time against the measured copy bandwidth (HBM-bound classes)
                       "hbm_frac": None if gbs is None else gbs / hbm_peak}
 
+    # ---- context legs (outside the timed regions above) ----
+    workspace_bytes = eng.workspace_bytes
+    model.invalidate_engine()
+    del model, eng, units_d, noise
+    torch.cuda.empty_cache()
+    strong = None
+    if not args.no_strong:
+        try:
+            strong = strong_leg(dev, world, rank, max(2, min(args.steps, 5)))
+        except Exception as ex:      # reported, never fatal for the headline
+            strong = {"error": repr(ex)[:300]}
     line = None
     if rank == 0:
-        cpu_baseline = None
-        # bounded CPU sample of the same workload; the 1000-step and shallow workloads would take minutes per utterance
-        if world == 1 and not args.no_cpu_baseline and method is not None and k_step is None:
-            cores = os.cpu_count() or 1
-            once = cpu_oracle_run(CPU_SAMPLE["B"], T, method, speedup, cores)
-            once()                                             # warm-up pass (pages the weights in, sizes the allocator)
-            sec = sorted(once() for _ in range(3))[1]          # median of 3 (median of 3 after 1 warm-up)
-            cpu_baseline = {"value": CPU_SAMPLE["B"] * T / sec, "unit": "frames/s", "cores": cores, "kind": "port",
-                            "sample": f"B={CPU_SAMPLE['B']} x T={T}, {method} {nfe} NFE fp32, oracle port of the reference sampler, "
-                                      "median of 3 passes after 1 warm-up"}
+        cpu_baseline = gpu_eager = tf32 = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline = cpu_baseline_leg(args.workload)
+        if world == 1 and not args.no_gpu_eager and method is not None and k_step is None:
+            gpu_eager = gpu_eager_leg(dev, B, T, method, speedup)
+            tf32 = tf32_peak(dev)
         line = {
             "metric": "mel_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "sampler": method, "nfe": nfe, "T": T, "batch_per_gpu": B,
-                       "global_batch": B * world, "precision_mode": precision, "l2_policy": "inputs_exceed_l2 (units 283 MB/step, activations >1 GB)",
-                       "parallelism": f"batch-shard x{world}, final NCCL all_gather" if world > 1 else "single GPU"},
+            "config": workload_config(args.workload, world),
             "rtf": (ms_step * 1e-3) / (frames / FRAME_RATE),
             "e2e": {"value": e2e_val, "unit": "frames/s",
-                    "h2d_bytes_per_step": int(units_h.numel() * 4 + spk_h.numel() * 8 + (0 if gt_h is None else gt_h.numel() * 4)),
-                    "d2h_bytes_per_step": int(B * world * T * 128 * 4), "ms_per_step": ms_e2e / args.steps},
+                    "h2d_bytes_per_step": int(world * (units_h.numel() * 4 + spk_h.numel() * 8 + (0 if gt_h is None else gt_h.numel() * 4))),
+                    "d2h_bytes_per_step": int(B * world * T * 128 * 4), "ms_per_step": ms_e2e / args.steps,
+                    "note": "bytes are whole-job totals; each rank copies its own shard in (pinned host -> HBM) and out, in parallel"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "gpu_eager_baseline": gpu_eager,
+            "tf32_tflops_measured": tf32,
+            "strong": strong,
             "kernel_classes": classes,
             "model_tflops_per_s": B * world * nfe * flops_per_utt_nfe(T) / (ms_step * 1e-3) / 1e12,
-            "workspace_bytes": eng.workspace_bytes,
+            "workspace_bytes": workspace_bytes,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -334,6 +560,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:   # convenience: self-launch one rank per GPU
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

@@ -46,3 +46,42 @@ def import_reference():
         sys.path.insert(0, REFERENCE_ROOT)
     import importlib
     return importlib.import_module("diffusion.unit2mel")
+
+
+def staged_or_source_root():
+    """Where the unmodified reference can be imported from: /root/reference (authoring container) or the staged copy under
+    baseline/_ref (GPU box; see oracle/build_ref.py).  None when neither exists."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("LDS_REFERENCE_ROOT"), os.path.join(root, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isfile(os.path.join(cand, "diffusion", "unit2mel.py")):
+            return cand
+    return None
+
+
+def build_reference_model(weight_seed: int = 1234, model_args=(1280, 323, 128, 2, [256, 384, 512, 512], 8, 256, 1.0)):
+    """The reference's own ``Unit2Mel`` with its default random init under ``torch.manual_seed(weight_seed)`` (eval mode), or
+    None when the reference is not importable here."""
+    global REFERENCE_ROOT
+    root = staged_or_source_root()
+    if root is None:
+        return None
+    REFERENCE_ROOT = root
+    import torch
+    mod = import_reference()
+    torch.manual_seed(weight_seed)
+    model = mod.Unit2Mel(*model_args).eval()
+    model.is_tts = True          # the reference reads this attribute without ever setting it (unit2mel.py:74)
+    return model
+
+
+def reference_infer(model, units, spk_id, method, infer_speedup, gt_spec=None, k_step=None):
+    """One ``Unit2Mel.forward(infer=True)`` of the reference (unit2mel.py:73-89); shallow diffusion goes through the decoder,
+    as the reference's own forward never passes ``k_step``."""
+    import torch
+    with torch.no_grad():
+        if gt_spec is None or k_step is None:
+            if infer_speedup == 1:
+                method = None
+            return model(units, None, spk_id=spk_id, infer=True, infer_speedup=infer_speedup, method=method)
+        cond = model.unit_embed(units) + model.spk_embed(spk_id - 1)
+        return model.decoder(cond, gt_spec=gt_spec, infer=True, infer_speedup=infer_speedup, method=method, k_step=k_step)
