@@ -34,8 +34,7 @@ using namespace ptx;
 constexpr int AQ = 128, ATT_TC_THREADS = 320, NSOFT = 256;
 
 struct AttnTcParams {
-  int B, T, H, d, C, parts, nk, nv, nsb, npb;   // ring depths: K, V^T tiles (smem), S (TMEM) and P (smem) buffers
-  int pa_tiles;         // 64-key tiles per pass-A step: 1, or 2 (split mode: the two hi-plane tiles fill plane slots 0 and 1 of a K stage -> one N = 128 instruction)
+  int B, T, H, d, C, parts;
   float scale;
   __nv_bfloat16* out;   // planes [B*T][parts*C]
 };
@@ -82,7 +81,13 @@ struct MmaItem { int a_plane, b_plane0, n_planes, blk; };
 
 // DUAL (split mode, d <= 32): two S accumulator blocks instead of three and 256 TMEM columns, so that two CTAs fit on
 // one SM and the softmax of one overlaps the tensor-pipe work of the other.
-template <int DPAD, int AKV, int PARTS, bool DUAL>
+//
+// Ring depths are compile-time: NK / NV stages of the K / V^T rings (shared memory), NSB S buffers (TMEM), NPB P buffers (shared
+// memory).  PA = 2: a pass-A step covers two 64-key tiles (the two hi-plane tiles fill plane slots 0 and 1 of a K stage -> one
+// N = 128 instruction).  Everything the single MMA-issuing thread computes between two tcgen05.mma must be cheap: the ncu source
+// page of the round-1 kernel (runtime ring depths -> integer divisions, ~440 instructions per key tile) showed that thread
+// executing 96 % of its time while the tensor pipe was busy 67 % — the pipe was waiting for its issuer, not the other way round.
+template <int DPAD, int AKV, int PARTS, bool DUAL, int NK, int NV, int NSB, int NPB>
 __global__ void __launch_bounds__(ATT_TC_THREADS, (PARTS == 1 || DUAL) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapVT, const AttnTcParams p) {
@@ -97,10 +102,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int parts = PARTS;
-  const int NK = p.nk, NV = p.nv;
-  const int KSL = parts > p.pa_tiles ? parts : p.pa_tiles;     // K tiles (plane slots) per stage of the K ring
+  constexpr int PA = 2;                            // 64-key tiles per pass-A step
+  constexpr int KSL = parts > PA ? parts : PA;     // K tiles (plane slots) per stage of the K ring
   const uint32_t q_s = base, k_s = q_s + parts * QB, v_s = k_s + NK * KSL * KB, p_s = v_s + NV * parts * KBLK * VBK;
-  const int NSB = p.nsb, NPB = p.npb;
   const uint32_t bar0 = p_s + NPB * parts * KBLK * PBK;
   uint8_t* p_ptr = smem + (p_s - base);
   const uint32_t q_full = bar0;
@@ -116,14 +120,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
   float* red = reinterpret_cast<float*>(misc + 16);          // [2][128] exchange of row max / row sum between the halves
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;   // provably warp-uniform: the role branches below do not diverge
   pdl_trigger();
   // Persistent CTA: work items (utterance, head, query tile) blockIdx.x, blockIdx.x + gridDim.x, ...; every barrier
   // phase follows a running use counter, so the TMA producer and the MMA warp run ahead into the next item (its Q / K
   // loads and its pass A overlap the softmax tail, the O read-out and the stores of the current one).
   const int nq = (p.T + AQ - 1) / AQ, n_items = nq * p.H * p.B;
   const int nt = (p.T + AKV - 1) / AKV;
-  const int PA = p.pa_tiles, ntA = (nt + PA - 1) / PA;      // pass-A steps of PA key tiles
+  const int ntA = (nt + PA - 1) / PA;              // pass-A steps of PA key tiles
   const int HD = p.H * DPAD;
   constexpr int tmem_cols = (parts == 3 && !DUAL) ? 512 : 256;
   constexpr int o_col = (parts == 3 && !DUAL) ? 256 : 128;    // S buffers start at column 0, O blocks at o_col
@@ -154,16 +158,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t kc = 0, vc = 0, local = 0;        // K tiles / V^T tiles loaded so far, items started
+      int ks = 0, vs = 0;                        // next stage of the K / V^T ring
+      uint32_t kph = 0, vph = 0, local = 0;      // ring phases; items started
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
         const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
         mbar_wait(q_empty, (local & 1u) ^ 1u);                   // every Q K^T of the previous item has read Q
         mbar_expect_tx(q_full, parts * QB);
         for (int pl = 0; pl < parts; ++pl) tma_load_3d(q_s + pl * QB, &mapQ, q_full, pl * HD + h * DPAD, qt * AQ, b);
-        for (int it = 0; it < ntA + nt; ++it, ++kc) {
+        for (int it = 0; it < ntA + nt; ++it) {
           const int jt = it < ntA ? it : it - ntA;
-          const int ks = kc % NK;
-          mbar_wait(k_empty(ks), ((kc / NK) & 1u) ^ 1u);
+          mbar_wait(k_empty(ks), kph ^ 1u);
           if (it < ntA) {                                        // pass A needs the hi plane only: PA consecutive key tiles per stage
             mbar_expect_tx(k_full(ks), PA * KB);
             for (int u = 0; u < PA; ++u)                         // (a tile beyond T is all out-of-bounds: zero fill, full byte count)
@@ -174,56 +178,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
               tma_load_3d(k_s + (ks * KSL + pl) * KB, &mapK, k_full(ks), pl * HD + h * DPAD, jt * AKV, b);
           }
           if (it >= ntA) {
-            const int vs = vc % NV;
-            mbar_wait(v_empty(vs), ((vc / NV) & 1u) ^ 1u);
+            mbar_wait(v_empty(vs), vph ^ 1u);
             mbar_expect_tx(v_full(vs), parts * KBLK * VBK);
             for (int kb = 0; kb < KBLK; ++kb)
               for (int pl = 0; pl < parts; ++pl)
                 tma_load_2d(v_s + ((vs * KBLK + kb) * parts + pl) * VBK, &mapVT, v_full(vs), jt * AKV + kb * 64,
                             ((b * parts + pl) * p.H + h) * DPAD);
-            ++vc;
+            if (++vs == NV) { vs = 0; vph ^= 1u; }
           }
+          if (++ks == NK) { ks = 0; kph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // work lists (widest instruction first: it initialises every accumulator block it covers)
-      MmaItem qk[4], pv[3];
-      int n_qk, n_pv;
-      if (parts == 3) {
-        if (AKV == 64 && !DUAL) { qk[0] = {0, 0, 3, 0}; qk[1] = {1, 0, 2, 0}; qk[2] = {2, 0, 1, 0}; n_qk = 3; }
-        else { qk[0] = {0, 0, 2, 0}; qk[1] = {1, 0, 2, 0}; qk[2] = {0, 2, 1, 1}; qk[3] = {2, 0, 1, 0}; n_qk = 4; }
-        pv[0] = {0, 0, 3, 0}; pv[1] = {1, 0, 2, 0}; pv[2] = {2, 0, 1, 0}; n_pv = 3;
-      } else {
-        qk[0] = {0, 0, 1, 0}; n_qk = 1;
-        pv[0] = {0, 0, 1, 0}; n_pv = 1;
-      }
-      // descriptors are assembled once; the loops below only add address offsets (units of 16 bytes)
-      uint64_t qd0[4], kd0[4], pd0[3], vd0[3];
-      uint32_t qk_idesc[4], pv_idesc[3], qk_dst[4], pv_dst[3];
-      for (int e = 0; e < n_qk; ++e) {
-        qd0[e] = umma_desc_kmajor(q_s + qk[e].a_plane * QB, SWZ);
-        kd0[e] = umma_desc_kmajor(k_s + qk[e].b_plane0 * KB, SWZ);
-        qk_idesc[e] = umma_idesc_bf16(AQ, qk[e].n_planes * AKV);
-        qk_dst[e] = tmem0 + qk[e].blk * AKV;
-      }
-      for (int e = 0; e < n_pv; ++e) {
-        pd0[e] = umma_desc_kmajor(p_s + pv[e].a_plane * KBLK * PBK, 128);
-        vd0[e] = umma_desc_kmajor(v_s + pv[e].b_plane0 * VBK, 128);
-        pv_idesc[e] = umma_idesc_bf16(AQ, pv[e].n_planes * DPAD);
-        pv_dst[e] = tmem_o + pv[e].blk * DPAD;
-      }
-      const uint64_t k_stage_step = (uint64_t)((KSL * KB) >> 4), v_stage_step = (uint64_t)((parts * KBLK * VBK) >> 4),
-                     v_kb_step = (uint64_t)((parts * VBK) >> 4), p_buf_step = (uint64_t)((parts * KBLK * PBK) >> 4),
-                     p_kb_step = (uint64_t)(PBK >> 4);
-      const uint64_t q_hi = umma_desc_kmajor(q_s, SWZ), k_hi = umma_desc_kmajor(k_s, SWZ);
-      const uint32_t hi_idesc = umma_idesc_bf16(AQ, PA * AKV);
+    {   // the WHOLE warp runs this loop in lock step (all lanes poll the barriers); one elected lane issues each MMA / commit
+      // Work lists (widest instruction first: it initialises every accumulator block it covers).  They are compile-time
+      // constants, the loops over them unroll completely and every descriptor below lives in a (uniform) register.
+      constexpr bool WIDE_QK = parts == 3 && AKV == 64 && !DUAL;   // three S accumulator blocks: one N = 192 instruction
+      constexpr int n_qk = parts == 3 ? (WIDE_QK ? 3 : 4) : 1, n_pv = parts == 3 ? 3 : 1;
+      constexpr MmaItem qk_wide[4] = {{0, 0, 3, 0}, {1, 0, 2, 0}, {2, 0, 1, 0}, {0, 0, 0, 0}};
+      constexpr MmaItem qk_dual[4] = {{0, 0, 2, 0}, {1, 0, 2, 0}, {0, 2, 1, 1}, {2, 0, 1, 0}};
+      constexpr MmaItem qk_one[4] = {{0, 0, 1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+      constexpr MmaItem pv_split[3] = {{0, 0, 3, 0}, {1, 0, 2, 0}, {2, 0, 1, 0}};
+      constexpr MmaItem pv_one[3] = {{0, 0, 1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+      auto qk = [&](int e) -> MmaItem { return parts == 3 ? (WIDE_QK ? qk_wide[e] : qk_dual[e]) : qk_one[e]; };
+      auto pv = [&](int e) -> MmaItem { return parts == 3 ? pv_split[e] : pv_one[e]; };
+      const uint64_t q_desc0 = umma_desc_kmajor(q_s, SWZ), k_desc0 = umma_desc_kmajor(k_s, SWZ);
+      const uint64_t p_desc0 = umma_desc_kmajor(p_s, 128), v_desc0 = umma_desc_kmajor(v_s, 128);
+      constexpr uint64_t k_stage_step = (uint64_t)((KSL * KB) >> 4), v_stage_step = (uint64_t)((parts * KBLK * VBK) >> 4),
+                         v_kb_step = (uint64_t)((parts * VBK) >> 4), p_buf_step = (uint64_t)((parts * KBLK * PBK) >> 4),
+                         p_kb_step = (uint64_t)(PBK >> 4);
+      constexpr uint32_t hi_idesc = umma_idesc_bf16(AQ, PA * AKV);
       const int ksteps = (p.d + 15) / 16;        // head dims beyond d are zero padding (d = 48 in a 64-wide tile): skip their K slices
-      // S buffer of evaluation `it`: pass B rotates over the NSB buffers of the S region; pass A always has two buffers —
-      // with NSB == 1 the second one borrows the O region (idle until the first P V of the item) — so that the hi*hi
-      // product of tile j+1 runs while the softmax threads still reduce tile j.
-      uint32_t su0 = 0u, su1 = 0u, pu0 = 0u, pu1 = 0u, kc = 0u, vc = 0u, local = 0u;
+      // S buffer of an evaluation: pass B rotates over the NSB buffers of the S region; pass A (PA == 2) alternates between
+      // columns [0, 128) and the O region (idle until the first P V of the item), so that the hi*hi product of step j+1 runs
+      // while the softmax threads still reduce step j.
+      uint32_t su0 = 0u, su1 = 0u, pu0 = 0u, pu1 = 0u, local = 0u;   // uses of the S / P buffers so far
+      int ks = 0, vs = 0;                                            // oldest live stage of the K / V^T ring
+      uint32_t kph = 0u, vph = 0u;
       bool o_claimed = false;
       auto claim_o = [&]() {                     // the softmax threads have read the previous item's O
         if (!o_claimed) {
@@ -231,62 +223,77 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           o_claimed = true;
         }
       };
-      // `it` < ntA: pass-A step; else pass-B tile it - ntA.  Pass A with PA == 2 always uses [0, 128) and the O region.
-      auto issue_qk = [&](int it) {
-        const int ks = kc % NK;
-        const bool passA = it < ntA;
-        const int sb = passA ? (it & 1) : (it - ntA) % NSB;
-        const bool alt = passA && (NSB == 1 || PA == 2) && sb == 1;
-        const uint32_t soff = alt ? (uint32_t)o_col : (uint32_t)((passA && PA == 2) ? 0 : sb * s_stride);
-        if (alt) claim_o();
-        mbar_wait(k_full(ks), (kc / NK) & 1u);
-        ++kc;
+      auto k_advance = [&]() { if (++ks == NK) { ks = 0; kph ^= 1u; } };
+      // pass-A step `it`: hi*hi of PA key tiles (the row maximum is only needed to ~1 %: any m close to it gives the same softmax)
+      auto issue_qk_a = [&](int it) {
+        const int sb = it & 1;
+        if (sb) claim_o();
+        mbar_wait(k_full(ks), kph);
         mbar_wait(s_free(sb), ((sb ? su1 : su0) & 1u) ^ 1u);   // the softmax threads have read the previous use of this S buffer
-        // a 128-column pass-A step into [0, 128) also covers pass-B buffer 1 ([64, 128) when NSB == 2): its last use too
-        if (passA && PA == 2 && NSB == 2 && sb == 0) mbar_wait(s_free(1), (su1 & 1u) ^ 1u);
+        // the 128 columns [0, 128) also cover pass-B buffer 1 ([64, 128) when NSB == 2): wait for its last use too
+        if (NSB == 2 && sb == 0) mbar_wait(s_free(1), (su1 & 1u) ^ 1u);
         if (sb) ++su1; else ++su0;
         tc_fence_after();
-        const uint64_t koff = (uint64_t)ks * k_stage_step;
-        if (passA) {
-          // pass A only needs the row maximum to ~1 %: hi*hi alone (any m close to the maximum gives the same softmax)
+        const uint32_t dst = tmem0 + (sb ? (uint32_t)o_col : 0u);
+        const uint64_t kd = k_desc0 + (uint64_t)ks * k_stage_step;
 #pragma unroll
-          for (int k = 0; k < DPAD / 16; ++k)
-            if (k < ksteps) umma_bf16(tmem0 + soff, q_hi + (uint64_t)(2 * k), k_hi + koff + (uint64_t)(2 * k), hi_idesc, k == 0 ? 0u : 1u);
-        } else {
+        for (int k = 0; k < DPAD / 16; ++k)
+          if (k < ksteps) umma_bf16_elect(dst, q_desc0 + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), hi_idesc, k == 0 ? 0u : 1u);
+        umma_commit_elect(k_empty(ks));
+        umma_commit_elect(s_full(sb));
+        k_advance();
+      };
+      // pass-B tile `jb`: the six (one) plane products of Q K^T
+      auto issue_qk_b = [&](int jb, bool last) {
+        const int sb = NSB == 1 ? 0 : (jb & 1);
+        mbar_wait(k_full(ks), kph);
+        mbar_wait(s_free(sb), ((sb ? su1 : su0) & 1u) ^ 1u);
+        if (sb) ++su1; else ++su0;
+        tc_fence_after();
+        const uint32_t dst = tmem0 + (uint32_t)(sb * s_stride);
+        const uint64_t kd = k_desc0 + (uint64_t)ks * k_stage_step;
 #pragma unroll
-          for (int k = 0; k < DPAD / 16; ++k)
-            for (int e = 0; e < n_qk && k < ksteps; ++e)
-              umma_bf16(qk_dst[e] + soff, qd0[e] + (uint64_t)(2 * k), kd0[e] + koff + (uint64_t)(2 * k), qk_idesc[e],
+        for (int k = 0; k < DPAD / 16; ++k) {
+          if (k < ksteps) {
+#pragma unroll
+            for (int e = 0; e < n_qk; ++e)
+              umma_bf16_elect(dst + (uint32_t)(qk(e).blk * AKV), q_desc0 + (uint64_t)((qk(e).a_plane * QB) >> 4) + (uint64_t)(2 * k),
+                        kd + (uint64_t)((qk(e).b_plane0 * KB) >> 4) + (uint64_t)(2 * k), umma_idesc_bf16(AQ, qk(e).n_planes * AKV),
                         (k == 0 && e == 0) ? 0u : 1u);
+          }
         }
-        umma_commit(k_empty(ks));
-        umma_commit(s_full(sb));
-        if (it == ntA + nt - 1) umma_commit(q_empty);          // last Q K^T of the item: Q may be overwritten
+        umma_commit_elect(k_empty(ks));
+        umma_commit_elect(s_full(sb));
+        if (last) umma_commit_elect(q_empty);                          // last Q K^T of the item: Q may be overwritten
+        k_advance();
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
         o_claimed = false;
         mbar_wait(q_full, local & 1u);
-        for (int it = 0; it < ntA; ++it) issue_qk(it);           // pass A
-        issue_qk(ntA);                                           // pass B: Q K^T runs one tile ahead of P V
+        for (int it = 0; it < ntA; ++it) issue_qk_a(it);         // pass A
+        issue_qk_b(0, nt == 1);                                  // pass B: Q K^T runs one tile ahead of P V
         for (int jb = 0; jb < nt; ++jb) {
-          if (jb + 1 < nt) issue_qk(ntA + jb + 1);
-          const int vs = vc % NV, pb = jb % NPB;
-          mbar_wait(v_full(vs), (vc / NV) & 1u);
-          ++vc;
+          if (jb + 1 < nt) issue_qk_b(jb + 1, jb + 2 == nt);
+          const int pb = NPB == 1 ? 0 : (jb & 1);
+          mbar_wait(v_full(vs), vph);
           mbar_wait(p_full(pb), (pb ? pu1 : pu0) & 1u);
           if (pb) ++pu1; else ++pu0;
           if (jb == 0) claim_o();
           tc_fence_after();
-          const uint64_t poff = (uint64_t)pb * p_buf_step, voff = (uint64_t)vs * v_stage_step;
+          const uint64_t pd = p_desc0 + (uint64_t)pb * p_buf_step, vd = v_desc0 + (uint64_t)vs * v_stage_step;
 #pragma unroll
           for (int k = 0; k < AKV / 16; ++k) {
-            const uint64_t pk = poff + (uint64_t)(k >> 2) * p_kb_step + (uint64_t)(2 * (k & 3));
-            const uint64_t vk = voff + (uint64_t)(k >> 2) * v_kb_step + (uint64_t)(2 * (k & 3));
+            const uint64_t pk = pd + (uint64_t)(k >> 2) * p_kb_step + (uint64_t)(2 * (k & 3));
+            const uint64_t vk = vd + (uint64_t)(k >> 2) * v_kb_step + (uint64_t)(2 * (k & 3));
+#pragma unroll
             for (int e = 0; e < n_pv; ++e)
-              umma_bf16(pv_dst[e], pd0[e] + pk, vd0[e] + vk, pv_idesc[e], (jb == 0 && k == 0 && e == 0) ? 0u : 1u);
+              umma_bf16_elect(tmem_o + (uint32_t)(pv(e).blk * DPAD), pk + (uint64_t)((pv(e).a_plane * KBLK * PBK) >> 4),
+                        vk + (uint64_t)((pv(e).b_plane0 * VBK) >> 4), umma_idesc_bf16(AQ, pv(e).n_planes * DPAD),
+                        (jb == 0 && k == 0 && e == 0) ? 0u : 1u);
           }
-          umma_commit(v_empty(vs));
-          umma_commit(pv_done(pb));
+          umma_commit_elect(v_empty(vs));
+          umma_commit_elect(pv_done(pb));
+          if (++vs == NV) { vs = 0; vph ^= 1u; }
         }
       }
     }
@@ -445,23 +452,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   }
 }
 
-template <int DPAD, int AKV, int PARTS, bool DUAL = false>
-cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, cudaStream_t s) {
-  const int parts = a.parts;
-  // LDS_ATT_PA128: 0 off; 1 split mode and bf16 d <= 32; 2 (default) also bf16 d > 32 (its K ring then has two stages)
-  const int pa128 = knobs().att_pa128;
-  const bool wide_ok = PARTS == 3 || DPAD == 32 || pa128 == 2;
-  const int pa_tiles = (AKV == 64 && pa128 != 0 && wide_ok) ? 2 : 1;
-  if (PARTS == 1 && DPAD == 64) nk = pa_tiles == 2 ? 2 : 4;
-  const int ksl = parts > pa_tiles ? parts : pa_tiles;
-  const size_t smem = (size_t)parts * (AQ * DPAD * 2 + nv * DPAD * AKV * 2 + npb * AQ * AKV * 2) + (size_t)ksl * nk * AKV * DPAD * 2 + 1024 +
-                      72 + 8 * 16 + 16 + 16 + 2 * 128 * 4 + 64;
+template <int DPAD, int AKV, int PARTS, bool DUAL, int NK, int NV, int NSB, int NPB>
+cudaError_t launch_attn(const AttnTcArgs& a, cudaStream_t s) {
+  constexpr int PA = 2, KSL = PARTS > PA ? PARTS : PA;
+  auto kernel = attention_tc_kernel<DPAD, AKV, PARTS, DUAL, NK, NV, NSB, NPB>;
+  constexpr size_t smem = (size_t)PARTS * (AQ * DPAD * 2 + NV * DPAD * AKV * 2 + NPB * AQ * AKV * 2) + (size_t)KSL * NK * AKV * DPAD * 2 + 1024 +
+                          72 + 8 * 16 + 16 + 16 + 2 * 128 * 4 + 64;
+  static_assert(smem <= 227 * 1024, "attention tile configuration exceeds shared memory");
   cudaError_t e = cudaSuccess;
-  static unsigned long long configured = 0;      // per template instance: the shared-memory size of an instance is fixed
+  static unsigned long long configured = 0;      // per template instance
   if (first_use_on_this_device(configured)) {
-    e = cudaFuncSetAttribute(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
+  const int parts = PARTS;
   const uint64_t HD = (uint64_t)a.H * DPAD;
   CUtensorMap mQ, mK, mV;
   {
@@ -478,8 +482,7 @@ cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, c
     if ((e = tc_make_map_bf16_cached(a.vt, 2, dims, str, box, 128, &mV)) != cudaSuccess) return e;
   }
   AttnTcParams p;
-  p.B = a.B; p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts; p.nk = nk; p.nv = nv; p.nsb = nsb; p.npb = npb;
-  p.pa_tiles = pa_tiles;
+  p.B = a.B; p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts;
   p.scale = 1.0f / sqrtf((float)a.d);
   p.out = a.out;
   // persistent: one CTA per resident slot (two per SM in bf16 / DUAL mode), items strided over them
@@ -491,7 +494,7 @@ cudaError_t launch_attn(const AttnTcArgs& a, int nk, int nv, int nsb, int npb, c
   // (bf16, d <= 32: one item per CTA measured 3 % faster than the persistent grid — its items are too short to amortise anything)
   const bool persist = !(PARTS == 1 && DPAD == 32);
   dim3 grid(persist && n_items > slots ? slots : n_items);
-  return launch_pdl(attention_tc_kernel<DPAD, AKV, PARTS, DUAL>, grid, dim3(ATT_TC_THREADS), smem, s, 1, mQ, mK, mV, p);
+  return launch_pdl(kernel, grid, dim3(ATT_TC_THREADS), smem, s, 1, mQ, mK, mV, p);
 }
 
 }  // namespace
@@ -506,13 +509,13 @@ cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
     // (A CTA-pair variant, tests/micro/attention_pair.cu, is parity-green but NOT faster: a cta_group::2 instruction
     // occupies the tensor pipes of BOTH SMs for the same ~92 cycles, so the issue cost per query row and SM is unchanged —
     // tests/micro/bench_umma.cu, 0.73 vs 0.68 ms per T=864 attention at B=64.  It is not part of the library.)
-    if (a.dpad == 32) return launch_attn<32, 64, 3, true>(a, 2, 1, 1, 1, s);
+    if (a.dpad == 32) return launch_attn<32, 64, 3, true, 2, 1, 1, 1>(a, s);
     // (a second P buffer in exchange for a one-deep V^T ring measured 14 % slower: 0.47 vs 0.41 ms at T=432, B=64)
-    if (a.dpad == 64) return launch_attn<64, 64, 3>(a, 2, 2, 1, 1, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
+    if (a.dpad == 64) return launch_attn<64, 64, 3, false, 2, 2, 1, 1>(a, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
   } else {                                                             // bf16: S and P double-buffered, two CTAs per SM
     // K stages hold two 64-key tiles (pass A runs over 128-key steps): 4 (2) stages of 8 (16) KB
-    if (a.dpad == 32) return launch_attn<32, 64, 1>(a, 4, 3, 2, 2, s);    //  8 + 4*8 + 3*4 + 2*16 = 84, TMEM 2*64 (S) + 32 (O)
-    if (a.dpad == 64) return launch_attn<64, 64, 1>(a, 2, 3, 2, 2, s);    // 16 + 2*16 + 3*8 + 2*16 = 104
+    if (a.dpad == 32) return launch_attn<32, 64, 1, false, 4, 3, 2, 2>(a, s);    //  8 + 4*8 + 3*4 + 2*16 = 84, TMEM 2*64 (S) + 32 (O)
+    if (a.dpad == 64) return launch_attn<64, 64, 1, false, 2, 3, 2, 2>(a, s);    // 16 + 2*16 + 3*8 + 2*16 = 104
   }
   return cudaErrorNotSupported;
 }

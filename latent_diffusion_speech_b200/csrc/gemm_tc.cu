@@ -371,12 +371,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   auto tmem_full_bar = [&](int b) { return bar_base + 8u * (4 * MAX_SLOTS + b); };
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (4 * MAX_SLOTS + 2 + b); };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;   // provably warp-uniform role branches
   pdl_trigger();                                 // the next kernel may start launching behind our last wave
   // CTA pair: rank 0 (leader) issues every MMA for both SMs.  full barriers live in the leader and count the bytes
   // of both CTAs' loads; empty / tmem_full barriers exist in both CTAs and are signalled by the leader's multicast
   // commits; tmem_empty lives in the leader and collects one arrive per epilogue warp of both CTAs.
-  const uint32_t crank = cluster_ctarank();
+  const uint32_t crank = (uint32_t)__shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0);   // uniform for the compiler too
   const bool leader = crank == 0;
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
@@ -463,7 +463,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {   // the whole warp runs the issue loop in lock step; one elected lane issues each MMA / commit (tc_ptx.cuh)
       const uint32_t idesc = umma_idesc_bf16(2 * TBM, p.BN);
       int sa = 0, sw = 0;                        // oldest live slot of each ring
       uint32_t pha = 0, phw = 0;
@@ -481,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint64_t wd = umma_desc_kmajor(w_ring + w_slot * p.w_slot_bytes, 128);
 #pragma unroll
           for (int k = 0; k < TBK / 16; ++k) {   // +32 B (16 bf16) along K inside the swizzle atom per UMMA_K step
-            umma_bf16_pair(acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc, accumulate);
+            umma_bf16_pair_elect(acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc, accumulate);
             accumulate = 1;
           }
         };
@@ -492,32 +492,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(w_full(w_hi), phw);
           tc_fence_after();
           product(a_lo, w_hi);                   // lo * hi
-          umma_commit_pair(a_empty(a_lo), 3);
+          umma_commit_pair_elect(a_empty(a_lo), 3);
           next_a();
           const int a_mid = sa;
           mbar_wait(a_full(a_mid), pha);
           tc_fence_after();
           product(a_mid, w_hi);                  // mid * hi
-          umma_commit_pair(w_empty(w_hi), 3);
+          umma_commit_pair_elect(w_empty(w_hi), 3);
           next_w();
           const int w_mid = sw;
           mbar_wait(w_full(w_mid), phw);
           tc_fence_after();
           product(a_mid, w_mid);                 // mid * mid
-          umma_commit_pair(a_empty(a_mid), 3);
+          umma_commit_pair_elect(a_empty(a_mid), 3);
           next_a();
           const int a_hi = sa;
           mbar_wait(a_full(a_hi), pha);
           tc_fence_after();
           product(a_hi, w_mid);                  // hi * mid
-          umma_commit_pair(w_empty(w_mid), 3);
+          umma_commit_pair_elect(w_empty(w_mid), 3);
           next_w();
           const int w_lo = sw;
           mbar_wait(w_full(w_lo), phw);
           tc_fence_after();
           product(a_hi, w_lo);                   // hi * lo
-          umma_commit_pair(a_empty(a_hi), 3);
-          umma_commit_pair(w_empty(w_lo), 3);
+          umma_commit_pair_elect(a_empty(a_hi), 3);
+          umma_commit_pair_elect(w_empty(w_lo), 3);
           next_a();
           next_w();
         }
@@ -526,12 +526,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(w_full(sw), phw);
           tc_fence_after();
           product(sa, sw);                       // hi * hi
-          umma_commit_pair(a_empty(sa), 3);
-          umma_commit_pair(w_empty(sw), 3);
+          umma_commit_pair_elect(a_empty(sa), 3);
+          umma_commit_pair_elect(w_empty(sw), 3);
           next_a();
           next_w();
         }
-        umma_commit_pair(tmem_full_bar(buf), 3);
+        umma_commit_pair_elect(tmem_full_bar(buf), 3);
       }
     }
   } else {

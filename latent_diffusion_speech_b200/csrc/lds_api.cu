@@ -95,7 +95,6 @@ const Knobs& knobs() {
     Knobs v;
     auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
     v.gn_mode = env_int("LDS_GN_MODE", 2);
-    v.att_pa128 = env_int("LDS_ATT_PA128", 2);
     v.pdl = env_int("LDS_PDL", 1) != 0;
     return v;
   }();

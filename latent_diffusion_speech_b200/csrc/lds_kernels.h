@@ -18,7 +18,6 @@ namespace lds {
 // first call of knobs() — lds_create calls it — from the environment of the process that loads the library.
 struct Knobs {
   int gn_mode = 2;      // LDS_GN_MODE   2 persistent cluster GroupNorm, 1 one CTA per slab, 0 stats + apply
-  int att_pa128 = 2;    // LDS_ATT_PA128 attention pass A over 128-key steps: 2 everywhere, 1 not for bf16 d > 32, 0 off
   bool pdl = true;      // LDS_PDL       programmatic dependent launch attribute on the hot kernels
 };
 const Knobs& knobs();

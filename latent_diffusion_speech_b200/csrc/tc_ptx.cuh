@@ -103,6 +103,31 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// Warp-collective forms: called by ALL 32 lanes of a converged warp in warp-uniform control flow (warp index obtained with
+// warp_id_uniform(), operands derived from uniform values only); one elected lane issues.  The election sits inside the asm
+// statement, so the compiler sees a uniformly executed statement with uniform operands and emits a bare UTCHMMA / UTCBAR with
+// uniform-register operands — about 3 SASS instructions per MMA.  Issued from a divergent `if (lane == 0)` branch the same
+// instruction costs an ELECT / PLOP3 / BRA.U.ANY loop plus R2UR moves (~10 instructions), which made the single issuing thread
+// of the attention kernel the bottleneck of the whole kernel (profiles/r02_attention_issue_bound.md).
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar) : "memory");
+}
+
 // commit that arrives on the mbarrier at the same offset in every CTA of `mask` (cluster launch)
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
@@ -151,6 +176,25 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
+}
+
+// warp-collective forms of the pair instructions (see umma_bf16_elect)
+__device__ __forceinline__ void umma_bf16_pair_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(bar), "h"(mask) : "memory");
 }
 
 // Split form of tmem_ld32: issue the load, do independent work (e.g. global prefetches), then wait.  The wait takes the

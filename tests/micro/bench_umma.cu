@@ -22,8 +22,10 @@ __global__ void __launch_bounds__(128) k(long long* out, int iters, int ksteps) 
     const uint64_t ad = umma_desc_kmajor(base, SWZ), bd = umma_desc_kmajor(base + 32 * 1024, SWZ);
     const uint32_t idesc = umma_idesc_bf16(128, N);
     long long t0 = clock64();
+    // NACC independent accumulators (disjoint TMEM column ranges), used round-robin: separates the latency of a dependent
+    // accumulate chain from the issue rate of the tensor pipe
     for (int i = 0; i < iters; ++i)
-      for (int ks = 0; ks < ksteps; ++ks) umma_bf16(tm, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+      for (int ks = 0; ks < ksteps; ++ks) umma_bf16(tm + (uint32_t)(((i * ksteps + ks) % NACC) * N), ad + 2 * ks, bd + 2 * ks, idesc, 1u);
     umma_commit(bar);
     mbar_wait(bar, 0);
     long long t1 = clock64();
@@ -188,6 +190,21 @@ void run_x(const char* name, int grid) {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'a') {                     // bench_umma a : independent accumulators
+    const int grid = 148;
+    run<32, 128, 1>("M128 N32  1 accum", grid);
+    run<32, 128, 2>("M128 N32  2 accum", grid);
+    run<32, 128, 4>("M128 N32  4 accum", grid);
+    run<32, 128, 8>("M128 N32  8 accum", grid);
+    run<64, 128, 1>("M128 N64  1 accum", grid);
+    run<64, 128, 2>("M128 N64  2 accum", grid);
+    run<64, 128, 4>("M128 N64  4 accum", grid);
+    run<128, 128, 1>("M128 N128 1 accum", grid);
+    run<128, 128, 2>("M128 N128 2 accum", grid);
+    run<64, 64, 2>("M128 N64 SW64 2 accum", grid);
+    run<64, 64, 4>("M128 N64 SW64 4 accum", grid);
+    return 0;
+  }
   if (argc > 1 && argv[1][0] == 's') {                     // bench_umma s : K-major M = 64 probes only
     const int grid = 148;
     run_x<128, 256, 0>("M128 N256 B:K-major", grid);
