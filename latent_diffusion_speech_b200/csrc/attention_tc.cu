@@ -130,10 +130,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const int ntA = (nt + PA - 1) / PA;              // pass-A steps of PA key tiles
   const int HD = p.H * DPAD;
   constexpr int tmem_cols = (parts == 3 && !DUAL) ? 512 : 256;
-  constexpr int o_col = (parts == 3 && !DUAL) ? 256 : 128;    // S buffers start at column 0, O blocks at o_col
   constexpr int n_sblk = parts == 3 ? ((AKV == 64 && !DUAL) ? 3 : 2) : 1;
   constexpr int s_stride = n_sblk * AKV;           // TMEM columns per S buffer
   constexpr int n_oblk = parts == 3 ? 3 : 1;
+  // S buffers start at column 0, the O blocks (and the alternate 128-column pass-A buffer) at o_col
+  constexpr int o_col = NSB * s_stride <= 128 ? 128 : (NSB * s_stride <= 256 ? 256 : 384);
+  static_assert(o_col + (n_oblk * DPAD > 128 ? n_oblk * DPAD : 128) <= tmem_cols, "TMEM layout");
   const uint32_t q_empty = bar0 + 72 + 8 * 16, o_free = q_empty + 8;
 
   if (warp == 0 && lane == 0) {
@@ -509,6 +511,8 @@ cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
     // (A CTA-pair variant, tests/micro/attention_pair.cu, is parity-green but NOT faster: a cta_group::2 instruction
     // occupies the tensor pipes of BOTH SMs for the same ~92 cycles, so the issue cost per query row and SM is unchanged —
     // tests/micro/bench_umma.cu, 0.73 vs 0.68 ms per T=864 attention at B=64.  It is not part of the library.)
+    // (One CTA per SM with S (three blocks, one N = 192 instruction per k-step) and P double-buffered measured SLOWER at d = 32:
+    // 0.578 vs 0.511 ms per T=864 attention at B=64, GPU call 8 of round 2 — two co-resident CTAs hide the softmax latency better.)
     if (a.dpad == 32) return launch_attn<32, 64, 3, true, 2, 1, 1, 1>(a, s);
     // (a second P buffer in exchange for a one-deep V^T ring measured 14 % slower: 0.47 vs 0.41 ms at T=432, B=64)
     if (a.dpad == 64) return launch_attn<64, 64, 3, false, 2, 2, 1, 1>(a, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
