@@ -58,8 +58,10 @@ constexpr int EPI_PARTS = N_EPI_WARPS / 4;          // epilogue warps per TMEM l
 constexpr int A_SLOT_BYTES = TBM * TBK * 2;         // 16 KB: 128 rows x 128 B
 constexpr int MAX_SLOTS = 8;                        // per ring
 constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;    // two accumulator buffers
-constexpr int STAGE_BYTES = 32 * 32 * 4;              // per epilogue warp
-constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 512;    // rings + per-warp staging tiles (split mode)
+constexpr int STAGE_BYTES = 32 * 32 * 4;              // per epilogue warp (and per TMA epilogue buffer): one 32 x 32 fp32 block
+constexpr int BAR_BYTES = 1024;                       // mbarriers + TMEM slot
+constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - BAR_BYTES;    // rings + per-warp staging tiles / TMA epilogue buffers
+constexpr int MAX_EPI_BUFS = 4;                       // TMA epilogue buffers per epilogue warp
 
 struct TcParams {
   int rows, batches, tiles_per_batch, m_tiles, n_tiles, total_items;   // A: [batches][rows][parts*cin]; item = (M-tile group, N tile)
@@ -72,6 +74,7 @@ struct TcParams {
   const float* R; int r_ld, r_div;
   void* C; int c_ld; int out_kind;      // 0 fp32, 1 bf16, 2 split bf16 (3 planes of c_ld/3 columns), 3 attention operands
   int epilogue, dbg;
+  int tma_epi, nbuf;                    // fp32 output through TMA (residual tile TMA-loaded, result tile TMA-stored); buffers per epilogue warp
   __nv_bfloat16 *q_out, *k_out, *vt_out; int att_T, att_H, att_dpad, att_Tpad;
 };
 
@@ -352,9 +355,104 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, uint32_t trow,
   }
 }
 
+// ---- TMA epilogue (fp32 output, out_kind 0) ---------------------------------------------------------------------------
+// The per-thread ld.global / st.global epilogue above is LATENCY bound where the main loop is short: every warp walks its
+// 32-column chunks one after the other and each chunk waits for its own residual load (the C x C projections moved 14-22 B/clk
+// per SM against a ~40 B/clk path; profiles/r02_gemm_bounds_call8.md: 0.45-0.67 of their bound).  Here each epilogue warp owns
+// a small ring of 4 KB shared-memory tiles: the fp32 RESIDUAL block of a chunk is TMA-loaded into a tile ahead of time (the
+// loads of the next chunks / the next output tile fly while the main loop of that tile still runs), the thread that holds a
+// TMEM row adds bias + residual IN PLACE in the tile (the 128-byte TMA swizzle is the same XOR pattern the staged path used,
+// so both the row-per-thread accesses and the TMA engine see conflict-free / linear data), and one elected lane hands the tile
+// to a TMA STORE — no thread ever waits for a global load or issues a global store, ragged tile edges are clipped by the
+// tensor map (a 3-D map [columns, frames, utterances] like the A operand's, so a block never spills into the next utterance).
+struct TmaEpi {
+  uint32_t buf0, bar0;     // shared-memory addresses of this warp's tiles / mbarriers
+  uint32_t q, pq;          // chunks consumed / residual loads issued so far (ring position = count % nbuf)
+  int p_item, p_c;         // prefetch iterator: next (item, chunk) whose residual has not been requested yet
+};
+
+__device__ __forceinline__ void chunk_coords(const TcParams& p, int item, int c, int crank, int quarter, int& col, int& t, int& b) {
+  const int it = item / p.n_tiles, nt = item - it * p.n_tiles, mt = it * 2 + crank;
+  col = nt * p.BN + c * 32;
+  if (p.blk_tiling) {
+    const int gb = mt * 4 + quarter;
+    b = gb < p.total_blks ? gb / p.blks_per_batch : p.batches;          // ghost block: out of bounds (zero fill / nothing stored)
+    t = gb < p.total_blks ? (gb - b * p.blks_per_batch) * 32 : 0;
+  } else {
+    b = mt < p.m_tiles ? mt / p.tiles_per_batch : p.batches;
+    t = mt < p.m_tiles ? (mt - b * p.tiles_per_batch) * TBM + quarter * 32 : 0;
+  }
+}
+
+// lane 0 of an epilogue warp: request the residual block of the next chunk of this warp's sequence
+__device__ __forceinline__ void tma_epi_prefetch(const TcParams& p, const CUtensorMap* mapR, TmaEpi& st, int crank, int quarter, int part,
+                                                 int ncl) {
+  if (st.p_item >= p.total_items) return;
+  int col, t, b;
+  chunk_coords(p, st.p_item, st.p_c, crank, quarter, col, t, b);
+  const uint32_t k = st.pq % (uint32_t)p.nbuf;
+  mbar_expect_tx(st.bar0 + 8u * k, STAGE_BYTES);
+  tma_load_3d(st.buf0 + k * STAGE_BYTES, mapR, st.bar0 + 8u * k, col, t, b);
+  ++st.pq;
+  st.p_c += EPI_PARTS;
+  if (st.p_c >= (p.BN >> 5)) { st.p_c = part; st.p_item += ncl; }
+}
+
+__device__ __forceinline__ void epilogue_tma(const TcParams& p, const CUtensorMap* mapC, const CUtensorMap* mapR, TmaEpi& st, uint32_t trow,
+                                             int item, int crank, int quarter, int part, int lane, int nvalid, int ncl, uint8_t* smem_gen,
+                                             uint32_t smem_gen_addr) {
+  const int chunks = p.BN >> 5;
+#pragma unroll 1
+  for (int c = part; c < chunks; c += EPI_PARTS) {
+    const uint32_t k = st.q % (uint32_t)p.nbuf;
+    const uint32_t buf = st.buf0 + k * STAGE_BYTES;
+    int col, t, b;
+    chunk_coords(p, item, c, crank, quarter, col, t, b);
+    uint32_t raw[32];
+    tmem_ld32_issue(trow + c * 32, raw);
+    if (p.R) {
+      mbar_wait(st.bar0 + 8u * k, (st.q / (uint32_t)p.nbuf) & 1u);          // the residual block has landed in this tile
+    } else {
+      if (lane == 0) {                                                       // the store that last used this tile (nbuf chunks ago) has read it
+        if (p.nbuf == 2) bulk_wait_read<1>(); else if (p.nbuf == 3) bulk_wait_read<2>(); else bulk_wait_read<3>();
+      }
+      __syncwarp();
+    }
+    tmem_ld32_wait(raw);
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+    if (p.bias) add_bias32(v, p.bias + col);
+    if (p.epilogue == EPI_SILU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+    }
+    float4* row = reinterpret_cast<float4*>(smem_gen + (buf - smem_gen_addr) + lane * 128);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      const int jj = j ^ (lane & 7);                                         // TMA 128-byte swizzle of an 8-row x 128 B atom
+      if (p.R) { const float4 r = row[jj]; x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
+      row[jj] = x;
+    }
+    fence_async_smem();
+    __syncwarp();
+    ++st.q;
+    if (lane == 0) {
+      if (nvalid > 0) tma_store_3d(mapC, buf, col, t, b);
+      bulk_commit();
+      if (p.R) {
+        bulk_wait_read<1>();        // every store but the one just committed has read its tile: the tile of the previous chunk is free
+        tma_epi_prefetch(p, mapR, st, crank, quarter, part, ncl);
+      }
+    }
+  }
+}
+
 template <bool STAGED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapC,
+               const __grid_constant__ CUtensorMap mapR, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;              // 1024 B alignment required by the 128B swizzle atoms
@@ -363,7 +461,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t ring_bytes = p.na * A_SLOT_BYTES + p.nw * p.w_slot_bytes;
   const uint32_t bar_base = base + ring_bytes;    // a_full[8], a_empty[8], w_full[8], w_empty[8], tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ring_bytes + 8 * (4 * MAX_SLOTS + 4));
-  float* stage_base = reinterpret_cast<float*>(smem + ring_bytes + 512);   // barriers + TMEM slot occupy < 512 B
+  const uint32_t epi_bar_base = bar_base + 8u * (4 * MAX_SLOTS + 8);        // [N_EPI_WARPS][MAX_EPI_BUFS] residual-tile barriers
+  float* stage_base = reinterpret_cast<float*>(smem + ring_bytes + BAR_BYTES);   // 1024-byte aligned (slots are multiples of 1 KB)
+  const uint32_t stage_addr = base + ring_bytes + BAR_BYTES;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (MAX_SLOTS + s); };
   auto w_full = [&](int s) { return bar_base + 8u * (2 * MAX_SLOTS + s); };
@@ -388,6 +488,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_init(tmem_full_bar(b), 1);
       mbar_init(tmem_empty_bar(b), 2 * N_EPI_WARPS);
     }
+    for (int s = 0; s < N_EPI_WARPS * MAX_EPI_BUFS; ++s) mbar_init(epi_bar_base + 8u * s, 1);
+    if (p.tma_epi) { prefetch_tensormap(&mapC); if (p.R) prefetch_tensormap(&mapR); }
     mbar_fence_init();
   } else if (warp == 1) {
     tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS);
@@ -540,6 +642,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     EpiCtx e;
     e.stage = stage_base + (warp - 2) * (STAGE_BYTES / 4);
     e.lane = lane;
+    TmaEpi te;
+    te.buf0 = stage_addr + (uint32_t)((warp - 2) * p.nbuf) * STAGE_BYTES;
+    te.bar0 = epi_bar_base + 8u * (uint32_t)((warp - 2) * MAX_EPI_BUFS);
+    te.q = te.pq = 0u;
+    te.p_item = cid; te.p_c = part;
+    if (p.tma_epi && p.R && lane == 0)            // residual blocks of the first nbuf - 1 chunks
+      for (int i = 0; i + 1 < p.nbuf; ++i) tma_epi_prefetch(p, &mapR, te, (int)crank, quarter, part, ncl);
     int local = 0;
     for (int item = cid; item < p.total_items; item += ncl, ++local) {
       const int nt = item % p.n_tiles, mt = (item / p.n_tiles) * 2 + (int)crank;
@@ -557,16 +666,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int buf = local & 1;
       mbar_wait(tmem_full_bar(buf), ((uint32_t)local >> 1) & 1u);
       tc_fence_after();
+      const uint32_t trow = tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
 #ifdef LDS_DEBUG_KNOBS   // timing experiments only (results are wrong by construction); never compiled into the product library
       if (!(p.dbg & 2))
-        epilogue_block<STAGED>(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, e, part, (p.dbg & 1) != 0);
+        epilogue_block<STAGED>(p, trow, nt * p.BN, e, part, (p.dbg & 1) != 0);
 #else
-      epilogue_block<STAGED>(p, tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16), nt * p.BN, e, part, false);
+      if (p.tma_epi)
+        epilogue_tma(p, &mapC, &mapR, te, trow, item, (int)crank, quarter, part, lane, e.nvalid, ncl, reinterpret_cast<uint8_t*>(stage_base), stage_addr);
+      else
+        epilogue_block<STAGED>(p, trow, nt * p.BN, e, part, false);
 #endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(buf), 0));
     }
+    if (p.tma_epi && lane == 0) bulk_wait<0>();   // every TMA store of this warp has completed before the CTA may exit
   }
   tc_fence_before();
   __syncthreads();
@@ -645,6 +759,41 @@ cudaError_t get_map(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint
   return cudaSuccess;
 }
 
+// fp32 tensor [d2][d1][d0 valid columns, row stride ld], box = 32 columns x 32 rows x 1, 128B swizzle (TMA epilogue tiles)
+cudaError_t get_map_f32(const void* ptr, uint64_t d0, uint64_t ld, uint64_t d1, uint64_t d2, CUtensorMap* out) {
+  struct Key {
+    const void* ptr; uint64_t d0, ld, d1, d2;
+    bool operator==(const Key& o) const { return ptr == o.ptr && d0 == o.d0 && ld == o.ld && d1 == o.d1 && d2 == o.d2; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      size_t h = reinterpret_cast<size_t>(k.ptr);
+      for (uint64_t v : {k.d0, k.ld, k.d1, k.d2}) h = h * 1000003u ^ (size_t)v;
+      return h;
+    }
+  };
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  static std::mutex mu;
+  const Key key{ptr, d0, ld, d1, d2};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return cudaSuccess; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {ld * 4, ld * 4 * d1};
+  const cuuint32_t box[3] = {32, 32, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return cudaSuccess;
+}
+
 int sm_count() {
   static int n[64] = {0};
   int dev = 0;
@@ -652,6 +801,12 @@ int sm_count() {
   int& v = n[dev & 63];
   if (!v && (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1)) v = 148;
   return v;
+}
+
+// A/B switch of the TMA epilogue while it is being validated (LDS_TMA_EPI=0 -> per-thread ld.global / st.global epilogue)
+bool tma_epilogue_enabled() {
+  static const bool on = !(getenv("LDS_TMA_EPI") && atoi(getenv("LDS_TMA_EPI")) == 0);
+  return on;
 }
 
 // co-resident clusters of two persistent CTAs (GPC boundaries can strand an SM; asked from the occupancy calculator)
@@ -751,11 +906,17 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   TcParams p;
   p.BN = a.N % 256 == 0 ? 256 : ((a.N % 192 == 0 && a.epilogue != EPI_GEGLU) ? 192 : 128);   // GEGLU groups are 128 wide
   p.w_slot_bytes = (p.BN / 2) * TBK * 2;          // each CTA of the pair holds half of the W tile
-  p.na = 6;
-  const int stage_bytes = split ? N_EPI_WARPS * STAGE_BYTES : 0;
+  // fp32 outputs (with or without an fp32 residual) go through the TMA epilogue
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (!a.R || (reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
+  p.tma_epi = (a.out_kind == 0 && a.epilogue != EPI_GEGLU && (!a.R || a.r_div == 1) && a.c_ld % 4 == 0 && (!a.R || a.r_ld % 4 == 0) &&
+               aligned16 && tma_epilogue_enabled()) ? 1 : 0;
+  p.nbuf = split ? 2 : 3;
+  p.na = (split || !p.tma_epi) ? 6 : 4;
+  const int stage_bytes = p.tma_epi ? N_EPI_WARPS * p.nbuf * STAGE_BYTES : (split ? N_EPI_WARPS * STAGE_BYTES : 0);
   p.nw = (SMEM_BUDGET - stage_bytes - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
   if (p.nw > MAX_SLOTS) p.nw = MAX_SLOTS;
-  CUtensorMap mA, mW;
+  if (!split && p.tma_epi && p.nw > 4) p.nw = 4;
+  CUtensorMap mA, mW, mC, mR;
   p.blk_tiling = (a.batches > 1 && a.rows % 32 == 0 && a.rows % TBM != 0) ? 1 : 0;
   p.blks_per_batch = a.rows / 32; p.total_blks = p.blks_per_batch * a.batches;
   cudaError_t e = get_map(a.A, (uint64_t)a.a_parts * a.cin, (uint64_t)a.rows, (uint64_t)a.batches, p.blk_tiling ? 32 : TBM, &mA);
@@ -777,11 +938,23 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
 #endif
   p.q_out = a.q_out; p.k_out = a.k_out; p.vt_out = a.vt_out;
   p.att_T = a.att_T; p.att_H = a.att_H; p.att_dpad = a.att_dpad; p.att_Tpad = a.att_Tpad;
-  const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + 512 + stage_bytes;
+  const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + BAR_BYTES + stage_bytes;
+  if (p.tma_epi) {
+    e = get_map_f32(a.C, (uint64_t)a.N, (uint64_t)a.c_ld, (uint64_t)a.rows, (uint64_t)a.batches, &mC);
+    if (e != cudaSuccess) return e;
+    if (a.R) {
+      e = get_map_f32(a.R, (uint64_t)a.N, (uint64_t)a.r_ld, (uint64_t)a.rows, (uint64_t)a.batches, &mR);
+      if (e != cudaSuccess) return e;
+    } else {
+      mR = mC;
+    }
+  } else {
+    mC = mA; mR = mA;            // unused by the kernel
+  }
   const int max_cl = max_clusters2();
   const int ncl = p.total_items < max_cl ? p.total_items : max_cl;
-  return split ? launch_pdl(gemm_tc_kernel<true>, dim3(ncl * csize), dim3(TC_THREADS), smem, s, csize, mA, mW, p)
-               : launch_pdl(gemm_tc_kernel<false>, dim3(ncl * csize), dim3(TC_THREADS), smem, s, csize, mA, mW, p);
+  return split ? launch_pdl(gemm_tc_kernel<true>, dim3(ncl * csize), dim3(TC_THREADS), smem, s, csize, mA, mW, mC, mR, p)
+               : launch_pdl(gemm_tc_kernel<false>, dim3(ncl * csize), dim3(TC_THREADS), smem, s, csize, mA, mW, mC, mR, p);
 }
 
 }  // namespace lds
