@@ -23,12 +23,24 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a few ns unless a profiler (ncu / nsys) is attached
+
 #include "../../include/lds_b200.h"
 #include "lds_kernels.h"
 
 namespace {
 
 thread_local std::string g_last_error;
+
+// NVTX range per U-Net block / sampler step (the reference has no tracing at all): names follow the
+// reference's state_dict keys ("down_blocks.0.resnets.1", "mid_block.attentions.0", ...), so an nsys / ncu timeline reads like
+// the reference's module tree (unet_1d_condition.py:743-1036).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -433,6 +445,7 @@ int run_transformer_tc(lds_handle* h, cudaStream_t s, const XfW& w, const float*
 
 // k=3 stride-2 downsample (resnet.py:200) and nearest-upsample + k=3 conv (resnet.py:157-169) on the tensor-core path
 int run_downsample_tc(lds_handle* h, cudaStream_t s, const ConvW& w, const float* x, int t_in, int t_out, float* out) {
+  NvtxRange range("downsamplers.0.conv");
   LDS_TRY(launched(h, s, PC_LAYOUT, 0, 4.0 * h->B * t_in * w.cin + 2.0 * h->parts * 3.0 * h->B * t_out * w.cin,
                    launch_cast_gather(x, h->cast_b, h->B, t_in, t_out, w.cin, h->parts, 2, 0.f, s), "cast_im2col_s2"));
   TcGemmArgs g = tc_base(h, h->cast_b, 1, h->B * t_out, 3 * w.cin, 1, w.wh, w.b, w.cout);
@@ -440,6 +453,7 @@ int run_downsample_tc(lds_handle* h, cudaStream_t s, const ConvW& w, const float
   return run_gemm_tc(h, s, g);
 }
 int run_upsample_tc(lds_handle* h, cudaStream_t s, const ConvW& w, const float* x, int t_in, int t_up, float scale, float* out) {
+  NvtxRange range("upsamplers.0.conv");
   LDS_TRY(launched(h, s, PC_LAYOUT, 0, (4.0 + 2.0 * h->parts) * h->B * t_up * w.cin,
                    launch_cast_gather(x, h->cast_b, h->B, t_in, t_up, w.cin, h->parts, 1, scale, s), "cast_upsample"));
   TcGemmArgs g = tc_base(h, h->cast_b, h->B, t_up, w.cin, 3, w.wh, w.b, w.cout);
@@ -455,14 +469,17 @@ float* other_hid(lds_handle* h, const float* a, const float* b) {
 
 int run_resnet(lds_handle* h, cudaStream_t s, const ResnetW& r, const float* x1, const float* x2, int T,
                const float* temb_row, float* out) {
+  NvtxRange range(r.key.c_str() + (r.key.size() > 19 ? 19 : 0));      // key without "decoder.denoise_fn."
   return h->parts ? run_resnet_tc(h, s, r, x1, x2, T, temb_row, out) : run_resnet_ffma(h, s, r, x1, x2, T, temb_row, out);
 }
 int run_transformer(lds_handle* h, cudaStream_t s, const XfW& w, const float* x, int T, float* out) {
+  NvtxRange range(w.key.c_str() + (w.key.size() > 19 ? 19 : 0));
   return h->parts ? run_transformer_tc(h, s, w, x, T, out) : run_transformer_ffma(h, s, w, x, T, out);
 }
 
 // One denoiser evaluation on channels-last state x [B*T, out_dims]; eps out [B*T, out_dims].
 int run_unet(lds_handle* h, cudaStream_t s, const float* x, const float* temb_row, float* eps) {
+  NvtxRange range("denoise_fn");
   const lds_config& c = h->cfg;
   const int nb = c.n_blocks, L = c.n_layers, B = h->B;
   const int* ch = c.block_out_channels;
@@ -1212,6 +1229,9 @@ int lds_sample_steps(lds_handle* h, int k0, int k1, const float* step_noise, voi
   const double sb = 4.0 * n;
   const int S = h->n_nfe;   // DPM / UniPC: number of solver steps == number of evaluations
   for (int k = k0; k < k1; ++k) {
+    char step_name[32];
+    snprintf(step_name, sizeof(step_name), "sampler_step_%d", k);
+    NvtxRange step_range(step_name);
     const float* c = &h->coefs[(size_t)k * LDS_COEF_STRIDE];
     float* m0 = h->mbuf[h->m_cur % 3];
     float* m1 = h->mbuf[(h->m_cur + 2) % 3];
