@@ -5,7 +5,7 @@
                     (rows that were never written);
   * determinism   — 8 runs on the same inputs must be bit-identical (races in the mbarrier / TMEM hand-offs of the hand-rolled
                     pipelines show up as run-to-run differences)."""
-import ctypes as C
+import ctypes as ct
 
 import pytest
 import torch
@@ -50,7 +50,7 @@ def test_gemm_tc_fp32_output_guard_bands_and_determinism(parts, batches, rows, c
     for _ in range(8):
         buf, out = _guarded(M * N, torch.float32)
         G.check(G.lib().lds_op_gemm_tc(G.ptr(a), batches, rows, cin, parts, G.ptr(w), N, taps, G.ptr(bias), G.ptr(R), 0 if R is None else N, 1,
-                                       C.c_void_p(out.data_ptr()), N, 0, 0, G.stream()), "lds_op_gemm_tc")
+                                       ct.c_void_p(out.data_ptr()), N, 0, 0, G.stream()), "lds_op_gemm_tc")
         torch.cuda.synchronize()
         assert _bands_clean(buf, M * N), "write outside the output tensor"
         assert not torch.isnan(out).any(), "output rows left unwritten"
@@ -90,8 +90,8 @@ def test_attention_tc_guard_bands_and_determinism(parts, B, T, C):
         bv, vt = _guarded(n_vt, torch.bfloat16)
         bo, out = _guarded(n_out, torch.bfloat16)
         vt.zero_()                      # the key padding [T, T_pad) of V^T is never written by the projection and never read beyond T
-        G.check(G.lib().lds_op_qkv_attention_tc(G.ptr(xp), G.ptr(wp), B, T, C, heads, dpad, parts, C.c_void_p(q.data_ptr()),
-                                                C.c_void_p(k.data_ptr()), C.c_void_p(vt.data_ptr()), C.c_void_p(out.data_ptr()), G.stream()), "op")
+        G.check(G.lib().lds_op_qkv_attention_tc(G.ptr(xp), G.ptr(wp), B, T, C, heads, dpad, parts, ct.c_void_p(q.data_ptr()),
+                                                ct.c_void_p(k.data_ptr()), ct.c_void_p(vt.data_ptr()), ct.c_void_p(out.data_ptr()), G.stream()), "op")
         torch.cuda.synchronize()
         for buf, n in ((bq, n_qk), (bk, n_qk), (bv, n_vt), (bo, n_out)):
             assert _bands_clean(buf, n), "write outside an attention operand / output tensor"
