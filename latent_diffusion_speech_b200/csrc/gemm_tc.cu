@@ -803,12 +803,6 @@ int sm_count() {
   return v;
 }
 
-// A/B switch of the TMA epilogue while it is being validated (LDS_TMA_EPI=0 -> per-thread ld.global / st.global epilogue)
-bool tma_epilogue_enabled() {
-  static const bool on = !(getenv("LDS_TMA_EPI") && atoi(getenv("LDS_TMA_EPI")) == 0);
-  return on;
-}
-
 // co-resident clusters of two persistent CTAs (GPC boundaries can strand an SM; asked from the occupancy calculator)
 int max_clusters2() {
   static int n[64] = {0};
@@ -922,7 +916,7 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   // fp32 outputs (with or without an fp32 residual) go through the TMA epilogue
   const bool aligned16 = (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (!a.R || (reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
   p.tma_epi = (a.out_kind == 0 && a.epilogue != EPI_GEGLU && (!a.R || a.r_div == 1) && a.c_ld % 4 == 0 && (!a.R || a.r_ld % 4 == 0) &&
-               aligned16 && tma_epilogue_enabled()) ? 1 : 0;
+               aligned16 && knobs().tma_epi) ? 1 : 0;
   p.nbuf = split ? 2 : 3;
   p.na = (split || !p.tma_epi) ? 6 : 4;
   const int stage_bytes = p.tma_epi ? N_EPI_WARPS * p.nbuf * STAGE_BYTES : (split ? N_EPI_WARPS * STAGE_BYTES : 0);

@@ -108,6 +108,7 @@ const Knobs& knobs() {
     auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
     v.gn_mode = env_int("LDS_GN_MODE", 2);
     v.pdl = env_int("LDS_PDL", 1) != 0;
+    v.tma_epi = env_int("LDS_TMA_EPI", 1) != 0;
     return v;
   }();
   return k;
