@@ -309,6 +309,37 @@ def tf32_peak(dev) -> dict:
         torch.cuda.empty_cache()
 
 
+def vocoder_leg(dev, B: int = 16, T: int = 864) -> dict:
+    """HiFi-VAEGAN Generator decode of B x T latent frames to 44.1 kHz audio through the library
+    (csrc/vocoder.cu, fp32 FFMA) — the step that turns the headline's mel frames into waveforms; random-init weights of the
+    HiFi-GAN V1 layout (latent_diffusion_speech_b200/vocoder.py DEFAULT_H)."""
+    import torch
+    from latent_diffusion_speech_b200.vocoder import Vocoder
+    torch.manual_seed(1234)
+    voc = Vocoder("hifi-vaegan", None, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    mel = torch.randn(B, T, voc.dimension, generator=g, device=dev)
+    for _ in range(2):
+        voc.infer(mel)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(2):
+        wav = voc.infer(mel)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    eng = voc.generator._engine
+    out = {"workload": f"hifi-vaegan generator decode, B={B} x T={T} frames -> {wav.shape[-1]} samples each, fp32", "ms_per_step": ms,
+           "value": B * T / (ms * 1e-3), "unit": "frames/s", "rtf": (ms * 1e-3) / (B * T / FRAME_RATE),
+           "tflops": eng.last_flops / (ms * 1e-3) / 1e12, "flops_per_frame": eng.last_flops / (B * T),
+           "arithmetic": "fp32 FFMA (CUDA cores)", "finite": bool(torch.isfinite(wav).all())}
+    voc.generator._invalidate()
+    del voc, mel, wav
+    torch.cuda.empty_cache()
+    return out
+
+
 def strong_leg(dev, world: int, rank: int, steps: int) -> dict:
     """BASELINE configs[2]: global batch 512 x T=864, bf16 mode, UniPC 10 NFE, split 512/N across the ranks (strong scaling) through
     distributed.sharded_infer; inputs and noise are seeded PER UTTERANCE (global index), so the gathered mel is bit-identical at
@@ -524,6 +555,12 @@ def run_ours(args):
         if world == 1 and not args.no_gpu_eager and method is not None and k_step is None:
             gpu_eager = gpu_eager_leg(dev, B, T, method, speedup)
             tf32 = tf32_peak(dev)
+        vocoder = None
+        if world == 1 and not args.no_vocoder:
+            try:
+                vocoder = vocoder_leg(dev)
+            except Exception as ex:
+                vocoder = {"error": repr(ex)[:300]}
         line = {
             "metric": "mel_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -541,6 +578,7 @@ def run_ours(args):
             "gpu_eager_baseline": gpu_eager,
             "tf32_tflops_measured": tf32,
             "strong": strong,
+            "vocoder": vocoder,
             "kernel_classes": classes,
             "model_tflops_per_s": B * world * nfe * flops_per_utt_nfe(T) / (ms_step * 1e-3) / 1e12,
             "workspace_bytes": workspace_bytes,
@@ -562,6 +600,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-vocoder", action="store_true")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:   # convenience: self-launch one rank per GPU
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

@@ -243,6 +243,38 @@ LDS_API int lds_op_cast_gather(const float* in, void* out_bf16, int B, int t_in,
 LDS_API int lds_op_transpose(const float* in, float* out, int B, int C, int T, float scale, int to_channels_last, void* stream);
 LDS_API int lds_op_div_copy(const float* in, float* out, int64_t n, float divisor, void* stream);
 
+/* ---- HiFi-VAEGAN Generator decode: latent / mel frames -> waveform -------------------------------
+ * Replaces Vocoder.infer (diffusion/vocoder.py:31-32) -> Hifi_VAEGAN.forward (encoder/hifi_vaegan/hifi_vaegan.py:52-65) ->
+ * Generator.forward (encoder/hifi_vaegan/modules/models.py:248-256).  The configuration mirrors the generator's `h` dictionary
+ * (stored in the vocoder checkpoint, hifi_vaegan.py:6-8).  Weights are the Generator's state_dict AFTER remove_weight_norm
+ * (keys "conv_pre.weight", "ups.0.weight", "resblocks.3.convs1.1.bias", "conv_post.weight", ...; the Python host folds
+ * weight_g / weight_v pairs before loading).  fp32 throughout; same ownership / stream / error conventions as above,
+ * messages through lds_vocoder_last_error().  lds_vocode grows its workspace on demand (that call then synchronises). */
+#define LDS_VOC_MAX 8
+typedef struct {
+  int32_t inter_channels;                       /* h["inter_channels"] = Vocoder.dimension (128) */
+  int32_t upsample_initial_channel;             /* 512 */
+  int32_t n_ups;                                /* len(h["upsample_rates"]) */
+  int32_t upsample_rates[LDS_VOC_MAX];          /* product = hop size (512) */
+  int32_t upsample_kernel_sizes[LDS_VOC_MAX];
+  int32_t resblock_kind;                        /* 1: ResBlock1 (models.py:161-200), 2: ResBlock2 (:203-221) */
+  int32_t n_kernels;                            /* len(h["resblock_kernel_sizes"]) */
+  int32_t resblock_kernel_sizes[LDS_VOC_MAX];   /* in {3,5,7,11} */
+  int32_t resblock_dilations[LDS_VOC_MAX][3];   /* h["resblock_dilation_sizes"][j][:3] (ResBlock2 uses the first two) */
+} lds_vocoder_config;
+typedef struct lds_vocoder lds_vocoder;
+LDS_API const char* lds_vocoder_last_error(void);
+LDS_API int lds_vocoder_create(const lds_vocoder_config* cfg, int device, lds_vocoder** out);     /* Generator.__init__ (models.py:225-246) */
+LDS_API void lds_vocoder_destroy(lds_vocoder* v);
+LDS_API int lds_vocoder_load_weight(lds_vocoder* v, const char* key, const void* data, const int64_t* shape, int ndim, int dtype);
+LDS_API int lds_vocoder_finalize(lds_vocoder* v);              /* load_state_dict + remove_weight_norm (hifi_vaegan.py:56-61) */
+/* wav[B, T*hop] = tanh(conv_post(...Generator(mel[B,T,inter_channels]^T)))  (hifi_vaegan.py:52-65; the reference returns [B,1,T*hop]) */
+LDS_API int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL, void* stream);
+LDS_API int lds_vocoder_hop(const lds_vocoder* v);
+LDS_API int64_t lds_vocoder_launches(const lds_vocoder* v);
+LDS_API double lds_vocoder_last_flops(const lds_vocoder* v);   /* algorithmic FLOPs of the last lds_vocode call */
+LDS_API int64_t lds_vocoder_workspace_bytes(const lds_vocoder* v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,8 @@ EXPORTS = [
     "lds_op_split_cast", "lds_op_gemm_tc", "lds_op_qkv_attention_tc",
     "lds_op_x0_pred", "lds_op_dpm_update", "lds_op_unipc_predict", "lds_op_unipc_correct", "lds_op_ddpm_step", "lds_op_ddim_step",
     "lds_op_pndm_update", "lds_op_q_sample", "lds_op_cast_gather", "lds_op_transpose", "lds_op_div_copy",
+    "lds_vocoder_last_error", "lds_vocoder_create", "lds_vocoder_destroy", "lds_vocoder_load_weight", "lds_vocoder_finalize",
+    "lds_vocode", "lds_vocoder_hop", "lds_vocoder_launches", "lds_vocoder_last_flops", "lds_vocoder_workspace_bytes",
 ]
 
 
@@ -106,6 +108,16 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "lds_op_cast_gather": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]),
         "lds_op_transpose": (i32, [vp, vp, i32, i32, i32, f32, i32, vp]),
         "lds_op_div_copy": (i32, [vp, vp, i64, f32, vp]),
+        "lds_vocoder_last_error": (C.c_char_p, []),
+        "lds_vocoder_create": (i32, [vp, i32, C.POINTER(vp)]),
+        "lds_vocoder_destroy": (None, [vp]),
+        "lds_vocoder_load_weight": (i32, [vp, C.c_char_p, vp, i64p, i32, i32]),
+        "lds_vocoder_finalize": (i32, [vp]),
+        "lds_vocode": (i32, [vp, vp, i32, i32, vp, vp]),
+        "lds_vocoder_hop": (i32, [vp]),
+        "lds_vocoder_launches": (C.c_int64, [vp]),
+        "lds_vocoder_last_flops": (C.c_double, [vp]),
+        "lds_vocoder_workspace_bytes": (C.c_int64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)           # AttributeError if the symbol is not exported

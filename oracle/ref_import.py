@@ -85,3 +85,25 @@ def reference_infer(model, units, spk_id, method, infer_speedup, gt_spec=None, k
             return model(units, None, spk_id=spk_id, infer=True, infer_speedup=infer_speedup, method=method)
         cond = model.unit_embed(units) + model.spk_embed(spk_id - 1)
         return model.decoder(cond, gt_spec=gt_spec, infer=True, infer_speedup=infer_speedup, method=method, k_step=k_step)
+
+
+def import_reference_generator():
+    """The reference ``encoder.hifi_vaegan.modules.models`` module (Generator, ResBlock1/2).  ``vector_quantize_pytorch`` (only used
+    by the VAE encoder's quantiser) and ``msstftd`` (discriminator, pulls torchaudio) are import-only stubs."""
+    root = "/root/reference"
+    if not os.path.isfile(os.path.join(root, "encoder", "hifi_vaegan", "modules", "models.py")):
+        raise RuntimeError("reference tree not present at %s" % root)
+    if "vector_quantize_pytorch" not in sys.modules:
+        vq = types.ModuleType("vector_quantize_pytorch")
+        vq.VectorQuantize = object
+        sys.modules["vector_quantize_pytorch"] = vq
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import importlib
+    try:
+        return importlib.import_module("encoder.hifi_vaegan.modules.models")
+    except ImportError:
+        stub = types.ModuleType("encoder.hifi_vaegan.modules.msstftd")
+        stub.MultiScaleSTFTDiscriminator = object
+        sys.modules["encoder.hifi_vaegan.modules.msstftd"] = stub
+        return importlib.import_module("encoder.hifi_vaegan.modules.models")
