@@ -85,14 +85,16 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); 
 // bf16 mode only (the result is rounded to bf16, 2^-9 relative): erf by Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7
 // absolute, one MUFU.RCP + one MUFU.EX2 + 9 FMA-class instructions instead of the ~30 of erff — the GEGLU epilogue of the
 // bf16 GEMMs is bound by exactly this arithmetic (short main loops).  Split mode keeps erff.
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));             // bare MUFU.RCP / MUFU.EX2 (1-2 ulp): the result is rounded to bf16
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = poly * t * exp2f(-z * z * 1.4426950408889634f);    // 1 - erf(|x|/sqrt2)
+  const float e = poly * t * ex2_approx_ftz(-z * z * 1.4426950408889634f);    // 1 - erf(|x|/sqrt2)
   const float one_plus_erf = x >= 0.f ? 2.f - e : e;                    // 1 + erf(x/sqrt2)
   return 0.5f * x * one_plus_erf;
 }
