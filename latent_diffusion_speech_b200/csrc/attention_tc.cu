@@ -19,6 +19,7 @@
 // Warp roles (10 warps): warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..9 softmax / epilogue — two
 // warps per TMEM lane quarter, each thread owns one query row and half of the key columns of a tile.
 #include "lds_kernels.h"
+#include "planes.cuh"
 #include "tc_ptx.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -35,6 +36,7 @@ constexpr int AQ = 128, ATT_TC_THREADS = 320, NSOFT = 256;
 
 struct AttnTcParams {
   int B, T, H, d, C, parts;
+  int out_parts;        // operand planes of the output for the following GEMM: 1 bf16, 2 split-f16 (planes.cuh), 3 bf16 hi/mid/lo
   float scale;
   __nv_bfloat16* out;   // planes [B*T][parts*C]
 };
@@ -430,13 +432,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       mbar_arrive(o_free);                                               // the next item may overwrite O
       const int ncol = min(OC, p.d - half * OC);                        // d = 48: 16 valid columns in the upper half
       if (q < p.T && ncol > 0) {
-        __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q) * (size_t)(parts * p.C) + h * p.d + half * OC;
+        __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q) * (size_t)(p.out_parts * p.C) + h * p.d + half * OC;
+        const float oscale = p.out_parts == 2 ? inv * PLANE_SCALE : inv;
 #pragma unroll
-        for (int i = 0; i < OC; ++i) o[i] *= inv;
-        for (int pl = 0; pl < parts; ++pl) {
+        for (int i = 0; i < OC; ++i) o[i] *= oscale;
+        for (int pl = 0; pl < p.out_parts; ++pl) {
           uint32_t w[OC / 2];
 #pragma unroll
-          for (int i = 0; i < OC / 2; ++i) w[i] = split_pair(o[2 * i], o[2 * i + 1]);
+          for (int i = 0; i < OC / 2; ++i)
+            w[i] = p.out_parts == 2 ? (pl == 0 ? planes_split_pair_f16(o[2 * i], o[2 * i + 1]) : planes_pack_pair_f16(o[2 * i], o[2 * i + 1]))
+                                    : split_pair(o[2 * i], o[2 * i + 1]);
           uint4* dst = reinterpret_cast<uint4*>(orow + (size_t)pl * p.C);
 #pragma unroll
           for (int i = 0; i < OC / 8; ++i)
@@ -485,6 +490,7 @@ cudaError_t launch_attn(const AttnTcArgs& a, cudaStream_t s) {
   }
   AttnTcParams p;
   p.B = a.B; p.T = a.T; p.H = a.H; p.d = a.d; p.C = a.H * a.d; p.parts = parts;
+  p.out_parts = a.out_parts > 0 ? a.out_parts : parts;
   p.scale = 1.0f / sqrtf((float)a.d);
   p.out = a.out;
   // persistent: one CTA per resident slot (two per SM in bf16 / DUAL mode), items strided over them

@@ -48,6 +48,7 @@
 #include <unordered_map>
 
 #include "lds_kernels.h"
+#include "planes.cuh"
 #include "tc_ptx.cuh"
 
 namespace lds {
@@ -57,7 +58,7 @@ constexpr int TBM = 128, TBK = 64, N_EPI_WARPS = 8, TC_THREADS = 64 + 32 * N_EPI
 constexpr int EPI_PARTS = N_EPI_WARPS / 4;          // epilogue warps per TMEM lane quarter: they interleave the 32-column chunks
 constexpr int A_SLOT_BYTES = TBM * TBK * 2;         // 16 KB: 128 rows x 128 B
 constexpr int MAX_SLOTS = 8;                        // per ring
-constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;    // two accumulator buffers
+constexpr int TMEM_COLS = 512;                        // accumulator buffers: see TcParams::n_buf
 constexpr int STAGE_BYTES = 32 * 32 * 4;              // per epilogue warp (and per TMA epilogue buffer): one 32 x 32 fp32 block
 constexpr int BAR_BYTES = 1024;                       // mbarriers + TMEM slot
 constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - BAR_BYTES;    // rings + per-warp staging tiles / TMA epilogue buffers
@@ -74,6 +75,10 @@ struct TcParams {
   const float* R; int r_ld, r_div;
   void* C; int c_ld; int out_kind;      // 0 fp32, 1 bf16, 2 split bf16 (3 planes of c_ld/3 columns), 3 attention operands
   int epilogue, dbg;
+  float out_scale;                      // accumulator scale (split-f16: 1 / (scale_A * scale_W)); applied before bias / activation
+  int small_off;                        // split-f16: TMEM column offset of the "small" accumulator (h1*w2 + h2*w1) behind the main one; 0 = none
+  int n_buf, buf_stride;                // accumulator buffers in TMEM (2: epilogue of tile i overlaps the main loop of tile i+1) and their stride
+  int att_parts;                        // planes of the attention operands (out_kind 3)
   int tma_epi, nbuf;                    // fp32 output through TMA (residual tile TMA-loaded, result tile TMA-stored); buffers per epilogue warp
   __nv_bfloat16 *q_out, *k_out, *vt_out; int att_T, att_H, att_dpad, att_Tpad;
 };
@@ -120,14 +125,16 @@ __device__ __forceinline__ void store_row32(const TcParams& p, size_t row, int c
     for (int i = 0; i < 4; ++i)
       dst[i] = make_uint4(pack_pair_bf16(v[8 * i], v[8 * i + 1]), pack_pair_bf16(v[8 * i + 2], v[8 * i + 3]),
                           pack_pair_bf16(v[8 * i + 4], v[8 * i + 5]), pack_pair_bf16(v[8 * i + 6], v[8 * i + 7]));
-  } else {
+  } else {                                  // out_kind 2: split-f16 planes [h1 | h2] of the scaled value (planes.cuh)
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.c_ld + col;
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {
+    for (int i = 0; i < 32; ++i) v[i] *= PLANE_SCALE;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
       uint4* dst = reinterpret_cast<uint4*>(base + (size_t)pl * n_out);
       uint32_t w[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = pl == 2 ? pack_pair_bf16(v[2 * i], v[2 * i + 1]) : split_pair_bf16(v[2 * i], v[2 * i + 1]);
+      for (int i = 0; i < 16; ++i) w[i] = pl == 1 ? planes_pack_pair_f16(v[2 * i], v[2 * i + 1]) : planes_split_pair_f16(v[2 * i], v[2 * i + 1]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
     }
@@ -205,11 +212,20 @@ __device__ __forceinline__ void stage_store_bf16(const TcParams& p, const EpiCtx
     int parts, pstride;
     if (p.out_kind == 1) {
       base = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.c_ld + c8; parts = 1; pstride = 0;
-    } else if (p.out_kind == 2) {
-      base = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.c_ld + c8; parts = 3; pstride = n_out;
+    } else if (p.out_kind == 2) {         // split-f16 planes [h1 | h2] of the scaled value (planes.cuh)
+      __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.c_ld + c8;
+      a.x *= PLANE_SCALE; a.y *= PLANE_SCALE; a.z *= PLANE_SCALE; a.w *= PLANE_SCALE;
+      b.x *= PLANE_SCALE; b.y *= PLANE_SCALE; b.z *= PLANE_SCALE; b.w *= PLANE_SCALE;
+      uint4 w;
+      w.x = planes_split_pair_f16(a.x, a.y); w.y = planes_split_pair_f16(a.z, a.w);
+      w.z = planes_split_pair_f16(b.x, b.y); w.w = planes_split_pair_f16(b.z, b.w);
+      *reinterpret_cast<uint4*>(o2) = w;
+      w = make_uint4(planes_pack_pair_f16(a.x, a.y), planes_pack_pair_f16(a.z, a.w), planes_pack_pair_f16(b.x, b.y), planes_pack_pair_f16(b.z, b.w));
+      *reinterpret_cast<uint4*>(o2 + n_out) = w;
+      continue;
     } else {                              // q / k operands of the attention kernel: planes [row][parts][H*dpad]
       const int HD = p.att_H * p.att_dpad;
-      base = (q_region == 0 ? p.q_out : p.k_out) + row * (size_t)(p.parts * HD) + (c8 - q_region * HD); parts = p.parts; pstride = HD;
+      base = (q_region == 0 ? p.q_out : p.k_out) + row * (size_t)(p.att_parts * HD) + (c8 - q_region * HD); parts = p.att_parts; pstride = HD;
     }
     for (int pl = 0; pl < parts; ++pl) {
       uint4 w;
@@ -227,11 +243,11 @@ __device__ __forceinline__ void stage_store_bf16(const TcParams& p, const EpiCtx
 // q / k operands straight from the registers (direct path): planes [row][parts][H*dpad]
 __device__ __forceinline__ void store_qk32(const TcParams& p, size_t row, int col, int region, float* v) {
   const int HD = p.att_H * p.att_dpad;
-  __nv_bfloat16* base = (region == 0 ? p.q_out : p.k_out) + row * (size_t)(p.parts * HD) + (col - region * HD);
-  for (int pl = 0; pl < p.parts; ++pl) {
+  __nv_bfloat16* base = (region == 0 ? p.q_out : p.k_out) + row * (size_t)(p.att_parts * HD) + (col - region * HD);
+  for (int pl = 0; pl < p.att_parts; ++pl) {
     uint32_t w[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) w[i] = pl == p.parts - 1 ? pack_pair_bf16(v[2 * i], v[2 * i + 1]) : split_pair_bf16(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 16; ++i) w[i] = pl == p.att_parts - 1 ? pack_pair_bf16(v[2 * i], v[2 * i + 1]) : split_pair_bf16(v[2 * i], v[2 * i + 1]);
     uint4* dst = reinterpret_cast<uint4*>(base + (size_t)pl * HD);
 #pragma unroll
     for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
@@ -244,14 +260,28 @@ __device__ __forceinline__ void store_vt32(const TcParams& p, size_t row, int co
   const int HD = p.att_H * p.att_dpad, rem = col - 2 * HD;
   const int bb = (int)(row / p.att_T), tt = (int)(row - (size_t)bb * p.att_T);
   const int hh = rem / p.att_dpad, j0 = rem - hh * p.att_dpad;
-  for (int pl = 0; pl < p.parts; ++pl) {
-    __nv_bfloat16* dst = p.vt_out + ((size_t)((bb * p.parts + pl) * p.att_H + hh) * p.att_dpad + j0) * p.att_Tpad + tt;
+  for (int pl = 0; pl < p.att_parts; ++pl) {
+    __nv_bfloat16* dst = p.vt_out + ((size_t)((bb * p.att_parts + pl) * p.att_H + hh) * p.att_dpad + j0) * p.att_Tpad + tt;
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const uint32_t w = pl == p.parts - 1 ? pack_pair_bf16(v[i], v[i + 1]) : split_pair_bf16(v[i], v[i + 1]);
+      const uint32_t w = pl == p.att_parts - 1 ? pack_pair_bf16(v[i], v[i + 1]) : split_pair_bf16(v[i], v[i + 1]);
       dst[(size_t)i * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w & 0xffffu));
       dst[(size_t)(i + 1) * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w >> 16));
     }
+  }
+}
+
+// Accumulator read-out: 32 columns of the main accumulator; in split-f16 mode plus the same columns of the "small" accumulator
+// (h1*w2 + h2*w1, kept apart so that its tiny terms are not truncated against the large h1*w1 sums), times out_scale.
+__device__ __forceinline__ void acc_finish32(const TcParams& p, uint32_t taddr, float* v) {
+  if (p.small_off) {
+    float s[32];
+    tmem_ld32(taddr + p.small_off, s);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (v[i] + s[i]) * p.out_scale;
+  } else if (p.out_scale != 1.f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
   }
 }
 
@@ -275,7 +305,9 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, uint32_t trow,
       const int col_v = n0 + grp * 128 + c * 32, col_g = col_v + 64, oc = ((n0 + grp * 128) >> 1) + c * 32;
       float v[32], g[32];
       tmem_ld32(trow + grp * 128 + c * 32, v);
+      acc_finish32(p, trow + grp * 128 + c * 32, v);
       tmem_ld32(trow + grp * 128 + 64 + c * 32, g);
+      acc_finish32(p, trow + grp * 128 + 64 + c * 32, g);
       if (p.bias) { add_bias32(v, p.bias + col_v); add_bias32(g, p.bias + col_g); }
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] *= STAGED ? gelu_erf(g[i]) : gelu_fast(g[i]);
@@ -325,6 +357,7 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, uint32_t trow,
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+      acc_finish32(p, trow + c * 32, v);
       if (p.bias) add_bias32(v, p.bias + col);
       if (p.epilogue == EPI_SILU) {
 #pragma unroll
@@ -424,6 +457,7 @@ __device__ __forceinline__ void epilogue_tma(const TcParams& p, const CUtensorMa
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+    acc_finish32(p, trow + c * 32, v);
     if (p.bias) add_bias32(v, p.bias + col);
     if (p.epilogue == EPI_SILU) {
 #pragma unroll
@@ -503,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                    // everything above overlapped the previous kernel's tail; its data is needed from here on
 
-  const int n1 = p.parts == 3 ? p.nkb : 0;       // pass-1 K blocks (split mode only)
+  const bool split = p.parts == 2;               // split-f16: planes h1, h2 of both operands, three products per K block
 
   if (warp == 0) {
     if (lane == 0) {
@@ -548,92 +582,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         const int n0 = nt * p.BN;
         int tap = 0, cb = 0;
-        for (int kb = 0; kb < n1; ++kb) {
-          const int row = t0 - p.pad + tap, acol = cb * TBK, wcol = tap * p.parts * p.cin + cb * TBK;
-          load_a(2 * p.cin + acol, row, b);
-          load_w(wcol, n0);
-          load_a(p.cin + acol, row, b);
-          load_w(wcol + p.cin, n0);
-          load_a(acol, row, b);
-          load_w(wcol + 2 * p.cin, n0);
-          if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
-        }
-        tap = 0; cb = 0;
         for (int kb = 0; kb < p.nkb; ++kb) {
-          load_a(cb * TBK, t0 - p.pad + tap, b);
-          load_w(tap * p.parts * p.cin + cb * TBK, n0);
+          const int row = t0 - p.pad + tap, acol = cb * TBK, wcol = tap * p.parts * p.cin + cb * TBK;
+          if (split) {                           // need order of the MMA warp: A_h1, W_h2 | A_h2, W_h1
+            load_a(acol, row, b);
+            load_w(wcol + p.cin, n0);
+            load_a(p.cin + acol, row, b);
+            load_w(wcol, n0);
+          } else {
+            load_a(acol, row, b);
+            load_w(wcol, n0);
+          }
           if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
         }
       }
     }
   } else if (warp == 1) {
     if (leader) {   // the whole warp runs the issue loop in lock step; one elected lane issues each MMA / commit (tc_ptx.cuh)
-      const uint32_t idesc = umma_idesc_bf16(2 * TBM, p.BN);
+      const uint32_t idesc = split ? umma_idesc_f16(2 * TBM, p.BN) : umma_idesc_bf16(2 * TBM, p.BN);
       int sa = 0, sw = 0;                        // oldest live slot of each ring
       uint32_t pha = 0, phw = 0;
       int local = 0;
       auto next_a = [&]() { if (++sa == p.na) { sa = 0; pha ^= 1u; } };
       auto next_w = [&]() { if (++sw == p.nw) { sw = 0; phw ^= 1u; } };
       for (int item = cid; item < p.total_items; item += ncl, ++local) {
-        const int buf = local & 1;
-        mbar_wait(tmem_empty_bar(buf), (((uint32_t)local >> 1) & 1u) ^ 1u);   // both epilogues have drained this buffer
+        const int buf = p.n_buf == 2 ? (local & 1) : 0;
+        const uint32_t use = p.n_buf == 2 ? ((uint32_t)local >> 1) : (uint32_t)local;     // uses of this buffer so far
+        mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);   // both epilogues have drained this buffer
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * ACC_STRIDE;
-        uint32_t accumulate = 0;
-        auto product = [&](int a_slot, int w_slot) {
+        const uint32_t acc_main = tmem_base + buf * p.buf_stride, acc_small = acc_main + p.small_off;
+        uint32_t acc_m = 0, acc_s = 0;             // accumulate flags of the two accumulators
+        auto product = [&](int a_slot, int w_slot, uint32_t acc, uint32_t& accumulate) {
           const uint64_t ad = umma_desc_kmajor(a_ring + a_slot * A_SLOT_BYTES, 128);
           const uint64_t wd = umma_desc_kmajor(w_ring + w_slot * p.w_slot_bytes, 128);
 #pragma unroll
-          for (int k = 0; k < TBK / 16; ++k) {   // +32 B (16 bf16) along K inside the swizzle atom per UMMA_K step
+          for (int k = 0; k < TBK / 16; ++k) {   // +32 B (16 elements) along K inside the swizzle atom per UMMA_K step
             umma_bf16_pair_elect(acc, ad + (uint64_t)(2 * k), wd + (uint64_t)(2 * k), idesc, accumulate);
             accumulate = 1;
           }
         };
-        for (int kb = 0; kb < n1; ++kb) {
-          // slots (ring order): A: sa -> lo, sa+1 -> mid, sa+2 -> hi ; W: sw -> hi, sw+1 -> mid, sw+2 -> lo
-          const int a_lo = sa, w_hi = sw;
-          mbar_wait(a_full(a_lo), pha);
-          mbar_wait(w_full(w_hi), phw);
-          tc_fence_after();
-          product(a_lo, w_hi);                   // lo * hi
-          umma_commit_pair_elect(a_empty(a_lo), 3);
-          next_a();
-          const int a_mid = sa;
-          mbar_wait(a_full(a_mid), pha);
-          tc_fence_after();
-          product(a_mid, w_hi);                  // mid * hi
-          umma_commit_pair_elect(w_empty(w_hi), 3);
-          next_w();
-          const int w_mid = sw;
-          mbar_wait(w_full(w_mid), phw);
-          tc_fence_after();
-          product(a_mid, w_mid);                 // mid * mid
-          umma_commit_pair_elect(a_empty(a_mid), 3);
-          next_a();
-          const int a_hi = sa;
-          mbar_wait(a_full(a_hi), pha);
-          tc_fence_after();
-          product(a_hi, w_mid);                  // hi * mid
-          umma_commit_pair_elect(w_empty(w_mid), 3);
-          next_w();
-          const int w_lo = sw;
-          mbar_wait(w_full(w_lo), phw);
-          tc_fence_after();
-          product(a_hi, w_lo);                   // hi * lo
-          umma_commit_pair_elect(a_empty(a_hi), 3);
-          umma_commit_pair_elect(w_empty(w_lo), 3);
-          next_a();
-          next_w();
-        }
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(a_full(sa), pha);
-          mbar_wait(w_full(sw), phw);
-          tc_fence_after();
-          product(sa, sw);                       // hi * hi
-          umma_commit_pair_elect(a_empty(sa), 3);
-          umma_commit_pair_elect(w_empty(sw), 3);
-          next_a();
-          next_w();
+          if (split) {
+            // slots (ring order): A: sa -> h1, sa+1 -> h2 ; W: sw -> h2, sw+1 -> h1.  The two small products go to their own
+            // accumulator: their terms are 2^-11 of the main ones and would be truncated against the large h1*w1 partial sums
+            // by the tensor core's fp32 accumulate (the epilogue adds the two accumulators once, in fp32).
+            const int a_h1 = sa, w_h2 = sw;
+            mbar_wait(a_full(a_h1), pha);
+            mbar_wait(w_full(w_h2), phw);
+            tc_fence_after();
+            product(a_h1, w_h2, acc_small, acc_s);         // h1 * w2
+            umma_commit_pair_elect(w_empty(w_h2), 3);
+            next_a();
+            next_w();
+            const int a_h2 = sa, w_h1 = sw;
+            mbar_wait(a_full(a_h2), pha);
+            mbar_wait(w_full(w_h1), phw);
+            tc_fence_after();
+            product(a_h2, w_h1, acc_small, acc_s);         // h2 * w1
+            umma_commit_pair_elect(a_empty(a_h2), 3);
+            product(a_h1, w_h1, acc_main, acc_m);          // h1 * w1
+            umma_commit_pair_elect(a_empty(a_h1), 3);
+            umma_commit_pair_elect(w_empty(w_h1), 3);
+            next_a();
+            next_w();
+          } else {
+            mbar_wait(a_full(sa), pha);
+            mbar_wait(w_full(sw), phw);
+            tc_fence_after();
+            product(sa, sw, acc_main, acc_m);
+            umma_commit_pair_elect(a_empty(sa), 3);
+            umma_commit_pair_elect(w_empty(sw), 3);
+            next_a();
+            next_w();
+          }
         }
         umma_commit_pair_elect(tmem_full_bar(buf), 3);
       }
@@ -665,10 +686,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         e.nvalid = mt < p.m_tiles ? max(0, min(32, p.rows - t_blk)) : 0;
         e.grow0 = (size_t)(mt < p.m_tiles ? b : 0) * p.rows + t_blk;
       }
-      const int buf = local & 1;
-      mbar_wait(tmem_full_bar(buf), ((uint32_t)local >> 1) & 1u);
+      const int buf = p.n_buf == 2 ? (local & 1) : 0;
+      mbar_wait(tmem_full_bar(buf), (p.n_buf == 2 ? ((uint32_t)local >> 1) : (uint32_t)local) & 1u);
       tc_fence_after();
-      const uint32_t trow = tmem_base + buf * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t trow = tmem_base + buf * p.buf_stride + ((uint32_t)(quarter * 32) << 16);
 #ifdef LDS_DEBUG_KNOBS   // timing experiments only (results are wrong by construction); never compiled into the product library
       if (!(p.dbg & 2))
         epilogue_block<STAGED>(p, trow, nt * p.BN, e, part, (p.dbg & 1) != 0);
@@ -884,7 +905,7 @@ cudaError_t tc_make_map_bf16_cached(const void* ptr, int rank, const uint64_t* d
 
 cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (a.batches <= 0 || a.rows <= 0 || a.N <= 0) return cudaSuccess;
-  const bool split = a.a_parts == 3 && a.w_parts == 3 && a.n_pairs == 6;
+  const bool split = a.a_parts == 2 && a.w_parts == 2 && a.n_pairs == 3;      // split-f16 (fp32-accurate)
   const bool plain = a.a_parts == 1 && a.w_parts == 1 && a.n_pairs == 1;
   if (a.cin % 64 || a.N % 128 || (a.taps != 1 && a.taps != 3) || (!split && !plain) || (a.out_kind != 3 && a.c_ld % 8) ||
       (a.R && a.r_ld % 4) || a.r_div < 1)
@@ -945,6 +966,12 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
 #else
   p.dbg = 0;
 #endif
+  p.out_scale = a.out_scale; p.att_parts = a.att_parts;
+  // TMEM: main accumulator (BN columns) [+ small accumulator (BN columns) in split-f16 mode] per buffer; two buffers when they fit
+  p.small_off = split ? p.BN : 0;
+  p.buf_stride = split ? 2 * p.BN : p.BN;
+  p.n_buf = 2 * p.buf_stride <= TMEM_COLS ? 2 : 1;
+  if (p.n_buf == 2) p.buf_stride = TMEM_COLS / 2;
   p.q_out = a.q_out; p.k_out = a.k_out; p.vt_out = a.vt_out;
   p.att_T = a.att_T; p.att_H = a.att_H; p.att_dpad = a.att_dpad; p.att_Tpad = a.att_Tpad;
   const size_t smem = (size_t)p.na * A_SLOT_BYTES + (size_t)p.nw * p.w_slot_bytes + 1024 + BAR_BYTES + stage_bytes;

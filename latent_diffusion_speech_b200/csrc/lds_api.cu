@@ -27,6 +27,7 @@
 
 #include "../../include/lds_b200.h"
 #include "lds_kernels.h"
+#include "planes.cuh"
 
 namespace {
 
@@ -125,7 +126,9 @@ struct lds_handle {
   size_t warena_floats = 0;
   __nv_bfloat16* wharena = nullptr;   // bf16 operand planes of the GEMM weights (tensor-core modes)
   size_t wharena_elems = 0;
-  int parts = 0;                      // 0: FFMA fp32 kernels; 1: bf16 tcgen05; 3: split-bf16 tcgen05 (fp32-accurate)
+  int parts = 0;                      // GEMM operand planes: 0 FFMA fp32 kernels; 1 bf16 tcgen05; 2 split-f16 tcgen05 (fp32-accurate), planes.cuh
+  int att_parts = 0;                  // attention operand planes (Q, K, V^T): 1 bf16; 3 bf16 hi/mid/lo (fp32-accurate mode)
+  float wscale = 1.f;                 // split-f16: power-of-two scale of the packed GEMM weights (activations: PLANE_SCALE)
   int temb_dim = 0, temb_total = 0;
   const float *unit_w = nullptr, *unit_b = nullptr, *spk_table = nullptr;
   const __nv_bfloat16 *unit_wh = nullptr, *conv_in_wxh = nullptr, *conv_in_wch = nullptr;
@@ -337,12 +340,12 @@ TcGemmArgs tc_base(lds_handle* h, const __nv_bfloat16* A, int batches, int rows,
                    const float* bias, int N) {
   TcGemmArgs g;
   g.A = A; g.batches = batches; g.rows = rows; g.cin = cin; g.taps = taps; g.W = W; g.N = N; g.bias = bias;
-  if (h->parts == 3) tc_set_split_pairs(g);
+  if (h->parts == 2) { tc_set_split_pairs(g); g.out_scale = 1.f / (PLANE_SCALE * h->wscale); }
   return g;
 }
 void tc_out_f32(TcGemmArgs& g, float* C, int ld) { g.C = C; g.c_ld = ld; g.out_kind = 0; }
 void tc_out_planes(lds_handle* h, TcGemmArgs& g, __nv_bfloat16* C, int n_out) {
-  g.C = C; g.c_ld = h->parts * n_out; g.out_kind = h->parts == 3 ? 2 : 1;
+  g.C = C; g.c_ld = h->parts * n_out; g.out_kind = h->parts == 2 ? 2 : 1;
 }
 int run_gemm_tc(lds_handle* h, cudaStream_t s, const TcGemmArgs& g) {
   const double M = (double)g.batches * g.rows, K = (double)g.taps * g.cin;
@@ -408,12 +411,12 @@ int run_attention_tc(lds_handle* h, cudaStream_t s, const AttnW& a, const NormW&
   const int H = h->cfg.n_heads, d = C / H, dpad = d <= 32 ? 32 : 64, t_pad = (T + 7) / 8 * 8;
   TcGemmArgs q = tc_base(h, h->xn_b, 1, M, C, 1, a.qkv_h, nullptr, 3 * H * dpad);
   q.out_kind = 3; q.q_out = h->q_b; q.k_out = h->k_b; q.vt_out = h->vt_b;
-  q.att_T = T; q.att_H = H; q.att_dpad = dpad; q.att_Tpad = t_pad;
+  q.att_T = T; q.att_H = H; q.att_dpad = dpad; q.att_Tpad = t_pad; q.att_parts = h->att_parts;
   LDS_TRY(run_gemm_tc(h, s, q));
   AttnTcArgs at;
   at.q = h->q_b; at.k = h->k_b; at.vt = h->vt_b; at.out = h->att_b;
-  at.B = h->B; at.T = T; at.T_pad = t_pad; at.H = H; at.d = d; at.dpad = dpad; at.parts = h->parts;
-  LDS_TRY(launched(h, s, PC_ATTENTION, 4.0 * h->B * (double)T * T * C, 2.0 * h->parts * (3.0 * M * H * dpad + (double)M * C),
+  at.B = h->B; at.T = T; at.T_pad = t_pad; at.H = H; at.d = d; at.dpad = dpad; at.parts = h->att_parts; at.out_parts = h->parts;
+  LDS_TRY(launched(h, s, PC_ATTENTION, 4.0 * h->B * (double)T * T * C, 2.0 * (h->att_parts * 3.0 * M * H * dpad + h->parts * (double)M * C),
                    launch_attention_tc(at, s), "attention_tc"));
   TcGemmArgs o = tc_base(h, h->att_b, 1, M, C, 1, a.out_h, a.out_b, C);
   tc_out_f32(o, h->th, C);
@@ -615,15 +618,35 @@ inline float host_bf2f(uint16_t b) {
   memcpy(&f, &u, 4);
   return f;
 }
-// fp32 [rows][cin] -> bf16 planes [rows][parts][cin]
+// fp32 [rows][cin] -> 16-bit planes [rows][parts][cin] (planes.cuh): parts 1 / 3 bf16 planes; parts 2 split-f16 planes of
+// the scaled value (h1 = f16(w * scale), h2 = f16(w * scale - h1)), bit-identical to what the device conversion would give
 struct PlanePacker {
   std::vector<uint16_t> host;
+  float scale = 1.f;
+  static uint16_t f2h_sat(float f) {
+    if (f > 65504.f) f = 65504.f;
+    if (f < -65504.f) f = -65504.f;
+    const __half_raw r = __float2half_rn(f);
+    return r.x;
+  }
+  static float h2f(uint16_t b) {
+    __half_raw r;
+    r.x = b;
+    return __half2float(__half(r));
+  }
   size_t add(const float* src, size_t rows, int cin, int parts) {
     size_t off = (host.size() + 127) / 128 * 128;   // 256-byte alignment
     host.resize(off + rows * parts * cin);
     for (size_t r = 0; r < rows; ++r)
       for (int c = 0; c < cin; ++c) {
         float v = src[r * cin + c];
+        if (parts == 2) {
+          v *= scale;
+          const uint16_t h1 = f2h_sat(v);
+          host[off + (r * 2 + 0) * cin + c] = h1;
+          host[off + (r * 2 + 1) * cin + c] = f2h_sat(v - h2f(h1));
+          continue;
+        }
         for (int p = 0; p < parts; ++p) {
           const uint16_t b = host_f2bf(v);
           host[off + (r * parts + p) * cin + c] = b;
@@ -692,7 +715,8 @@ int lds_create(const lds_config* cfg, int device, lds_handle** out) {
   lds_handle* h = new lds_handle();
   h->cfg = *cfg;
   h->device = device;
-  h->parts = cfg->precision == LDS_PREC_FP32 ? 3 : (cfg->precision == LDS_PREC_BF16 ? 1 : 0);
+  h->parts = cfg->precision == LDS_PREC_FP32 ? 2 : (cfg->precision == LDS_PREC_BF16 ? 1 : 0);
+  h->att_parts = cfg->precision == LDS_PREC_FP32 ? 3 : h->parts;
   h->temb_dim = 4 * cfg->block_out_channels[0];
   *out = h;
   return LDS_OK;
@@ -752,6 +776,18 @@ int lds_finalize_weights(lds_handle* h) {
   Packer pk;
   PlanePacker pkh;
   const int parts = h->parts;
+  if (parts == 2) {
+    // one power-of-two scale for all packed weights: the largest magnitude lands in [8192, 16384) but never above 2^12 x |w|
+    // (fp16 keeps 30 binades of normal numbers, so layers whose weights differ by orders of magnitude still split to 22 bits)
+    float wmax = 0.f;
+    for (const auto& kv : h->raw)
+      if (kv.second.shape.size() >= 2)
+        for (float v : kv.second.v) wmax = std::max(wmax, std::fabs(v));
+    float sc = 4096.f;
+    while (sc > 1.f && wmax * sc >= 16384.f) sc *= 0.5f;
+    h->wscale = sc;
+    pkh.scale = sc;
+  }
   int rc = LDS_OK;
   std::vector<std::pair<const float**, size_t>> fix;   // pointer slots to patch once the arena exists
   std::vector<std::pair<const __nv_bfloat16**, size_t>> fixh;
@@ -1100,9 +1136,9 @@ int lds_plan(lds_handle* h, int B, int T, int sampler, int n_nfe, const float* t
       att_max = std::max(att_max, (size_t)B * h->Tl[i] * c.n_heads * dpad);
       vt_max = std::max(vt_max, (size_t)B * c.n_heads * dpad * ((h->Tl[i] + 7) / 8 * 8));
     }
-    wantb(&h->q_b, att_max * P);
-    wantb(&h->k_b, att_max * P);
-    wantb(&h->vt_b, vt_max * P);
+    wantb(&h->q_b, att_max * (size_t)h->att_parts);
+    wantb(&h->k_b, att_max * (size_t)h->att_parts);
+    wantb(&h->vt_b, vt_max * (size_t)h->att_parts);
     h->barena_elems = boff;
     if (boff > h->barena_cap) {
       LDS_CK(h, sync_once());
@@ -1397,32 +1433,34 @@ int lds_op_split_cast(const float* in, void* out_bf16, int64_t rows, int C, int 
 int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, int parts, const void* w_bf16, int N, int taps,
                    const float* bias, const float* R, int r_ld, int r_div, void* C, int c_ld, int out_kind, int epilogue,
                    void* stream) {
-  if (!A_bf16 || !w_bf16 || !C || (parts != 1 && parts != 3)) return fail(LDS_ERR_INVALID, "lds_op_gemm_tc: bad argument");
+  if (!A_bf16 || !w_bf16 || !C || (parts != 1 && parts != 2)) return fail(LDS_ERR_INVALID, "lds_op_gemm_tc: bad argument (parts must be 1 or 2)");
   lds::TcGemmArgs g;
   g.A = (const __nv_bfloat16*)A_bf16; g.batches = batches; g.rows = rows; g.cin = cin;
   g.W = (const __nv_bfloat16*)w_bf16; g.N = N; g.taps = taps;
-  if (parts == 3) lds::tc_set_split_pairs(g);
+  if (parts == 2) { lds::tc_set_split_pairs(g); g.out_scale = 1.f / (lds::PLANE_SCALE * lds::PLANE_SCALE); }   // both operands from lds_op_split_cast
   g.bias = bias; g.R = R; g.r_ld = r_ld; g.r_div = r_div; g.C = C; g.c_ld = c_ld; g.out_kind = out_kind; g.epilogue = epilogue;
   return op_status(lds::launch_gemm_tc(g, (cudaStream_t)stream), "lds_op_gemm_tc");
 }
 
 int lds_op_qkv_attention_tc(const void* x_planes, const void* w_qkv, int B, int T, int C, int H, int dpad, int parts,
                             void* q_scratch, void* k_scratch, void* vt_scratch, void* out_planes, void* stream) {
-  if (!x_planes || !w_qkv || !q_scratch || !k_scratch || !vt_scratch || !out_planes || (parts != 1 && parts != 3) || H < 1 || C % H)
+  if (!x_planes || !w_qkv || !q_scratch || !k_scratch || !vt_scratch || !out_planes || (parts != 1 && parts != 2) || H < 1 || C % H)
     return fail(LDS_ERR_INVALID, "lds_op_qkv_attention_tc: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int t_pad = (T + 7) / 8 * 8;
   lds::TcGemmArgs g;
   g.A = (const __nv_bfloat16*)x_planes; g.batches = 1; g.rows = B * T; g.cin = C;
   g.W = (const __nv_bfloat16*)w_qkv; g.N = 3 * H * dpad; g.taps = 1;
-  if (parts == 3) lds::tc_set_split_pairs(g);
+  const int att_parts = parts == 2 ? 3 : 1;
+  if (parts == 2) { lds::tc_set_split_pairs(g); g.out_scale = 1.f / (lds::PLANE_SCALE * lds::PLANE_SCALE); }
+  g.att_parts = att_parts;
   g.out_kind = 3; g.q_out = (__nv_bfloat16*)q_scratch; g.k_out = (__nv_bfloat16*)k_scratch; g.vt_out = (__nv_bfloat16*)vt_scratch;
   g.att_T = T; g.att_H = H; g.att_dpad = dpad; g.att_Tpad = t_pad;
   int rc = op_status(lds::launch_gemm_tc(g, s), "lds_op_qkv_attention_tc(qkv gemm)");
   if (rc != LDS_OK) return rc;
   lds::AttnTcArgs a;
   a.q = g.q_out; a.k = g.k_out; a.vt = g.vt_out; a.out = (__nv_bfloat16*)out_planes;
-  a.B = B; a.T = T; a.T_pad = t_pad; a.H = H; a.d = C / H; a.dpad = dpad; a.parts = parts;
+  a.B = B; a.T = T; a.T_pad = t_pad; a.H = H; a.d = C / H; a.dpad = dpad; a.parts = att_parts; a.out_parts = parts;
   return op_status(lds::launch_attention_tc(a, s), "lds_op_qkv_attention_tc(attention)");
 }
 

@@ -84,9 +84,10 @@ struct GemmArgs {
 cudaError_t launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
 
 // tcgen05/TMEM/TMA implicit GEMM on bf16 operands (gemm_tc.cu).
-//  A: bf16 [batches][rows][a_parts*cin]; W: bf16 [N][taps*w_parts*cin]; logical product = sum over the listed
-//  (pair_a, pair_w) plane pairs of A_plane (*) W_plane^T.  Plain bf16: parts = 1, one pair (0,0).  Split-bf16
-//  (fp32-accurate): parts = 3 (hi, mid, lo planes) and the six significant pairs, smallest first.
+//  A: 16-bit planes [batches][rows][a_parts*cin]; W: [N][taps*w_parts*cin] (planes.cuh).  Plain bf16: parts = 1, one product.
+//  Split-f16 (fp32-accurate): parts = 2 (fp16 planes h1, h2 of the scaled operand) and the three products h1*w2, h2*w1 (into a
+//  "small" TMEM accumulator) and h1*w1 (into the main one); the epilogue adds the two and multiplies by out_scale =
+//  1 / (scale_A * scale_W) — three tensor-core products per logical product.
 //  taps==3: k=3, stride-1, pad-1 convolution along `rows` (TMA out-of-bounds fill = zero padding).
 //  out_kind: 0 fp32 [*, c_ld], 1 bf16 [*, c_ld], 2 three bf16 planes of c_ld/3 columns each,
 //            3 attention operands of a fused QKV projection with N = 3*H*dpad columns ([q | k | v], head dim padded
@@ -99,22 +100,24 @@ struct TcGemmArgs {
   const float* bias = nullptr;
   const float* R = nullptr; int r_ld = 0, r_div = 1;
   void* C = nullptr; int c_ld = 0, out_kind = 0, epilogue = EPI_NONE;
+  float out_scale = 1.f;                  // applied to the accumulator before bias / activation (split-f16: 1 / (scale_A * scale_W))
   __nv_bfloat16 *q_out = nullptr, *k_out = nullptr, *vt_out = nullptr; int att_T = 0, att_H = 0, att_dpad = 0, att_Tpad = 0;
+  int att_parts = 1;                      // planes of the attention operands written by out_kind 3 (bf16: 1 or 3)
 };
 cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
 
 // tcgen05 flash attention (attention_tc.cu) on the operands written by a QKV projection with out_kind 3.
-// out: bf16 planes [B*T][parts*H*d].
+// out: operand planes [B*T][out_parts*H*d] for the following GEMM (out_parts 1: bf16; 2: split-f16; 3: three bf16 planes).
 struct AttnTcArgs {
   const __nv_bfloat16 *q = nullptr, *k = nullptr, *vt = nullptr;
   __nv_bfloat16* out = nullptr;
-  int B = 0, T = 0, T_pad = 0, H = 0, d = 0, dpad = 0, parts = 1;
+  int B = 0, T = 0, T_pad = 0, H = 0, d = 0, dpad = 0, parts = 1, out_parts = 0;   // out_parts 0: same as parts
 };
 cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s);
-inline void tc_set_split_pairs(TcGemmArgs& a) {   // lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
-  static const int pa[6] = {2, 0, 1, 1, 0, 0}, pw[6] = {0, 2, 1, 0, 1, 0};
-  a.a_parts = a.w_parts = 3; a.n_pairs = 6;
-  for (int i = 0; i < 6; ++i) { a.pair_a[i] = pa[i]; a.pair_w[i] = pw[i]; }
+inline void tc_set_split_pairs(TcGemmArgs& a) {   // h1*w2, h2*w1, h1*w1
+  static const int pa[3] = {0, 1, 0}, pw[3] = {1, 0, 0};
+  a.a_parts = a.w_parts = 2; a.n_pairs = 3;
+  for (int i = 0; i < 3; ++i) { a.pair_a[i] = pa[i]; a.pair_w[i] = pw[i]; }
 }
 // fp32 [rows, C] -> bf16 [rows, parts*C]: parts=1 plain rounding; parts=3 hi/mid/lo planes (x == hi+mid+lo to 24 bits)
 cudaError_t launch_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, cudaStream_t s);

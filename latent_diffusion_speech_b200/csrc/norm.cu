@@ -323,17 +323,28 @@ __device__ __forceinline__ float silu_newton(float x) {
 }
 template <int PARTS>
 __device__ __forceinline__ void store_planes4_ct(uint2* dst, int plane_stride_u2, float v0, float v1, float v2, float v3) {
-#pragma unroll
-  for (int p = 0; p < PARTS; ++p) {
+  if constexpr (PARTS == 2) {                    // split-f16: two fp16 planes of the scaled value (planes.cuh)
+    v0 *= PLANE_SCALE; v1 *= PLANE_SCALE; v2 *= PLANE_SCALE; v3 *= PLANE_SCALE;
     uint2 w;
-    if (p == PARTS - 1) {
-      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(v1), "f"(v0));
-      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(v3), "f"(v2));
-    } else {
-      w.x = planes_split_pair(v0, v1);
-      w.y = planes_split_pair(v2, v3);
+    w.x = planes_split_pair_f16(v0, v1);
+    w.y = planes_split_pair_f16(v2, v3);
+    dst[0] = w;
+    w.x = planes_pack_pair_f16(v0, v1);
+    w.y = planes_pack_pair_f16(v2, v3);
+    dst[plane_stride_u2] = w;
+  } else {
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {
+      uint2 w;
+      if (p == PARTS - 1) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(v1), "f"(v0));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(v3), "f"(v2));
+      } else {
+        w.x = planes_split_pair(v0, v1);
+        w.y = planes_split_pair(v2, v3);
+      }
+      dst[p * plane_stride_u2] = w;
     }
-    dst[p * plane_stride_u2] = w;
   }
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
@@ -744,7 +755,7 @@ cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, 
                               int parts, __nv_bfloat16* rawb, cudaStream_t s) {
   const int C = c1 + c2;
   if (C % (4 * groups) || c1 % 4 || groups > 32 || B <= 0 || T <= 0) return cudaErrorInvalidValue;
-  if (yb ? (parts != 1 && parts != 3) : (y == nullptr)) return cudaErrorInvalidValue;
+  if (yb ? (parts < 1 || parts > 3) : (y == nullptr)) return cudaErrorInvalidValue;
   const int cg = C / groups, q = cg / 4;
   if (q > GNC_THREADS) return cudaErrorNotSupported;
   // cluster size: a function of (T, cg) only (batch-composition invariance); slices of <= 36 KB, two buffers per CTA
@@ -766,22 +777,26 @@ cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, 
   const bool raw = yb && rawb;
   if (!yb) return launch_gnc_flags<0>(silu != 0, ss != nullptr, false, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
   if (parts == 1) return launch_gnc_flags<1>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
+  if (parts == 2) return launch_gnc_flags<2>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
   return launch_gnc_flags<3>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
                              __nv_bfloat16* yb, int parts, cudaStream_t s) {
   if (C % 4 || C > 512) return cudaErrorInvalidValue;
-  if (yb && parts != 1 && parts != 3) return cudaErrorInvalidValue;
+  if (yb && (parts < 1 || parts > 3)) return cudaErrorInvalidValue;
   if (C == 256 || C == 384 || C == 512) {        // the denoiser's widths: specialised kernel
     const int pk = yb ? parts : 0;
     auto go = [&](auto kernel, int rows_per_warp) {
       const int rows_per_block = 8 * rows_per_warp;
       return launch_pdl(kernel, dim3((rows + rows_per_block - 1) / rows_per_block), dim3(256), 0, s, 1, x, gamma, beta, eps, rows, y, yb);
     };
-    if (C == 256) return pk == 0 ? go(layernorm_fast_kernel<2, 0, 4>, 4) : pk == 1 ? go(layernorm_fast_kernel<2, 1, 4>, 4) : go(layernorm_fast_kernel<2, 3, 4>, 4);
-    if (C == 384) return pk == 0 ? go(layernorm_fast_kernel<3, 0, 2>, 2) : pk == 1 ? go(layernorm_fast_kernel<3, 1, 2>, 2) : go(layernorm_fast_kernel<3, 3, 2>, 2);
-    return pk == 0 ? go(layernorm_fast_kernel<4, 0, 2>, 2) : pk == 1 ? go(layernorm_fast_kernel<4, 1, 2>, 2) : go(layernorm_fast_kernel<4, 3, 2>, 2);
+    if (C == 256) return pk == 0 ? go(layernorm_fast_kernel<2, 0, 4>, 4) : pk == 1 ? go(layernorm_fast_kernel<2, 1, 4>, 4)
+                                 : pk == 2 ? go(layernorm_fast_kernel<2, 2, 4>, 4) : go(layernorm_fast_kernel<2, 3, 4>, 4);
+    if (C == 384) return pk == 0 ? go(layernorm_fast_kernel<3, 0, 2>, 2) : pk == 1 ? go(layernorm_fast_kernel<3, 1, 2>, 2)
+                                 : pk == 2 ? go(layernorm_fast_kernel<3, 2, 2>, 2) : go(layernorm_fast_kernel<3, 3, 2>, 2);
+    return pk == 0 ? go(layernorm_fast_kernel<4, 0, 2>, 2) : pk == 1 ? go(layernorm_fast_kernel<4, 1, 2>, 2)
+                   : pk == 2 ? go(layernorm_fast_kernel<4, 2, 2>, 2) : go(layernorm_fast_kernel<4, 3, 2>, 2);
   }
   const int warps_per_block = 8, rows_per_block = warps_per_block * LN_ROWS;
   const int grid = (rows + rows_per_block - 1) / rows_per_block;

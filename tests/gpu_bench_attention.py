@@ -9,7 +9,7 @@ import gpu_util as G  # noqa: E402
 
 B = int(os.environ.get("AB", 8))
 for (T, C) in [(864, 256), (432, 384), (216, 512)]:
-    for parts in (3, 1):
+    for parts in (2, 1):
         heads, d = 8, C // 8
         dpad = 32 if d <= 32 else 64
         g = torch.Generator().manual_seed(0)
@@ -17,9 +17,10 @@ for (T, C) in [(864, 256), (432, 384), (216, 512)]:
         w = (torch.randn(3 * heads * dpad, C, generator=g) * C ** -0.5).cuda()
         wp, xp = G.pack_w_parts(w, 1, parts), G.op_split_cast(x, parts)
         t_pad = (T + 7) // 8 * 8
-        q = torch.zeros(B * T * parts * heads * dpad, device="cuda", dtype=torch.bfloat16)
+        ap = 3 if parts == 2 else 1
+        q = torch.zeros(B * T * ap * heads * dpad, device="cuda", dtype=torch.bfloat16)
         k = torch.zeros_like(q)
-        vt = torch.zeros(B * parts * heads * dpad * t_pad, device="cuda", dtype=torch.bfloat16)
+        vt = torch.zeros(B * ap * heads * dpad * t_pad, device="cuda", dtype=torch.bfloat16)
         out = torch.zeros(B * T, parts * C, device="cuda", dtype=torch.bfloat16)
 
         def run():

@@ -1,6 +1,6 @@
 """GPU experiment (not a test): gemm_tc throughput at the denoiser's GEMM shapes (SURVEY.md Appendix D, B=64, T=864),
 both precision modes, against cuBLAS bf16 on the same shape, next to each shape's own BOUNDS:
-  tensor_us : logical FLOPs x (6 plane products in split mode | 1) / measured sustained bf16 peak (MEASURED_PEAKS.json)
+  tensor_us : logical FLOPs x (3 plane products in split-f16 mode | 1) / measured sustained bf16 peak (MEASURED_PEAKS.json)
   hbm_us    : the launch's own bytes (A planes + W planes + output + fp32 residual) / measured copy bandwidth
   cublas_plus_epi_us : cuBLAS bf16 time of the bare matmul + (our output/residual bytes beyond a bf16 C) / copy bandwidth —
                        what a library GEMM followed by a perfect elementwise pass would take in bf16 mode
@@ -66,7 +66,7 @@ _pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 if os.path.exists(_pk):
     PEAKS.update({k: v for k, v in json.load(open(_pk)).items() if k in PEAKS})
 rows_out = []
-tot = {1: 0.0, 3: 0.0, "flops": 0.0}
+tot = {1: 0.0, 2: 0.0, "flops": 0.0}
 for name, (batches, rows, cin, N, taps, epi, calls) in SHAPES.items():
     M, K = batches * rows, taps * cin
     A, W = rnd(M, cin, seed=3), rnd(N, K, seed=4, scale=K ** -0.5)
@@ -76,13 +76,13 @@ for name, (batches, rows, cin, N, taps, epi, calls) in SHAPES.items():
     R = rnd(M, n_out, seed=6) if with_res else None
     fl = 2.0 * M * N * K
     res = dict(name=name, M=M, N=N, K=K, calls=calls, residual=with_res)
-    for parts in (1, 3):
+    for parts in (1, 2):
         a, w = G.op_split_cast(A, parts), G.pack_w_parts(W, taps, parts)
         out_kind = 0 if epi == 0 else (1 if parts == 1 else 2)
         t = timeit(lambda: G.op_gemm_tc(a, batches, rows, cin, parts, w, N, taps=taps, bias=bias, R=R, epilogue=epi, out_kind=out_kind))
         out_bytes = M * n_out * (4 if out_kind == 0 else 2 * parts)
         byts = M * cin * 2 * parts + N * K * 2 * parts + out_bytes + (M * n_out * 4 if with_res else 0)
-        tensor_us = fl * (6 if parts == 3 else 1) / (PEAKS["bf16_tflops_sustained"] * 1e12) * 1e6
+        tensor_us = fl * (3 if parts == 2 else 1) / (PEAKS["bf16_tflops_sustained"] * 1e12) * 1e6
         hbm_us = byts / (PEAKS["hbm_gbs"] * 1e9) * 1e6
         res[f"tc{parts}_us"] = round(t * 1e3, 2)
         res[f"tc{parts}_tflops"] = round(fl / t / 1e9, 1)
@@ -107,11 +107,11 @@ with open("gpurun_out/gemm_bounds.md", "w") as f:
     f.write("| shape | M | N | K | calls/NFE | split: measured us | tensor bound | HBM bound | frac of bound | bf16: measured us | tensor bound | HBM bound | "
             "frac of bound | cuBLAS bf16 us | cuBLAS + epilogue bytes us | ours / that |\n|" + "---|" * 16 + "\n")
     for r in rows_out:
-        f.write("| {name} | {M} | {N} | {K} | {calls} | {tc3_us} | {tc3_tensor_bound_us} | {tc3_hbm_bound_us} | {tc3_frac_of_bound} | {tc1_us} | "
+        f.write("| {name} | {M} | {N} | {K} | {calls} | {tc2_us} | {tc2_tensor_bound_us} | {tc2_hbm_bound_us} | {tc2_frac_of_bound} | {tc1_us} | "
                 "{tc1_tensor_bound_us} | {tc1_hbm_bound_us} | {tc1_frac_of_bound} | {cb} | {ce} | {rt} |\n".format(
                     cb=r.get("cublas_bf16_us", "-"), ce=r.get("cublas_plus_epi_us", "-"), rt=r.get("tc1_vs_cublas_plus_epi", "-"), **r))
-summary = dict(weighted_ms_bf16=tot[1], weighted_ms_split=tot[3], weighted_tflops_bf16=tot["flops"] / tot[1] / 1e9,
-               weighted_tflops_split=tot["flops"] / tot[3] / 1e9)
+summary = dict(weighted_ms_bf16=tot[1], weighted_ms_split=tot[2], weighted_tflops_bf16=tot["flops"] / tot[1] / 1e9,
+               weighted_tflops_split=tot["flops"] / tot[2] / 1e9)
 print(json.dumps(summary))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(dict(shapes=rows_out, summary=summary), open("gpurun_out/gemm_bench.json", "w"), indent=1)

@@ -115,8 +115,19 @@ def op_split_cast(x, parts):
     return out
 
 
+PLANE_SCALE = 16.0     # csrc/planes.cuh: split-f16 planes (parts = 2) hold fp16(x * 16) and fp16(x * 16 - h1)
+
+
+def planes_to_double(planes, parts, Cc):
+    """Operand planes [rows, parts*C] (stored in a bf16-typed tensor) -> the value they represent, fp64 [rows, C]."""
+    rows = planes.shape[0]
+    if parts == 2:
+        return planes.view(torch.float16).view(rows, 2, Cc).double().sum(1) / PLANE_SCALE
+    return planes.float().view(rows, parts, Cc).double().sum(1)
+
+
 def pack_w_parts(w, taps, parts):
-    """fp32 [N, taps*cin] (tap-major) -> bf16 [N, taps*parts*cin] (tap, plane, channel)."""
+    """fp32 [N, taps*cin] (tap-major) -> 16-bit planes [N, taps*parts*cin] (tap, plane, channel)."""
     N, K = w.shape
     cin = K // taps
     sp = op_split_cast(w.reshape(N * taps, cin).contiguous(), parts)       # [N*taps, parts*cin]
@@ -131,9 +142,9 @@ def op_gemm_tc(a_bf16, batches, rows, cin, parts, w_bf16, N, taps=1, bias=None, 
     elif out_kind == 1:
         out = torch.empty(batches * rows, n_out, device=a_bf16.device, dtype=torch.bfloat16)
         c_ld = n_out
-    else:
-        out = torch.empty(batches * rows, 3 * n_out, device=a_bf16.device, dtype=torch.bfloat16)
-        c_ld = 3 * n_out
+    else:                      # split-f16 planes [h1 | h2]
+        out = torch.empty(batches * rows, 2 * n_out, device=a_bf16.device, dtype=torch.bfloat16)
+        c_ld = 2 * n_out
     check(lib().lds_op_gemm_tc(ptr(a_bf16), batches, rows, cin, parts, ptr(w_bf16), N, taps, ptr(bias), ptr(R),
                                0 if R is None else R.shape[-1], r_div, ptr(out), c_ld, out_kind, epilogue, stream()),
           "lds_op_gemm_tc")
@@ -154,13 +165,14 @@ def op_qkv_attention_tc(x, wq, wk, wv, B, T, heads, parts):
     wp = pack_w_parts(torch.cat(rows, 0).contiguous(), 1, parts)
     xp = op_split_cast(x, parts)
     t_pad = (T + 7) // 8 * 8
-    q = torch.zeros(B * T * parts * heads * dpad, device=x.device, dtype=torch.bfloat16)
+    ap = 3 if parts == 2 else 1          # attention operands: three bf16 planes in the fp32-accurate mode
+    q = torch.zeros(B * T * ap * heads * dpad, device=x.device, dtype=torch.bfloat16)
     k = torch.zeros_like(q)
-    vt = torch.zeros(B * parts * heads * dpad * t_pad, device=x.device, dtype=torch.bfloat16)
+    vt = torch.zeros(B * ap * heads * dpad * t_pad, device=x.device, dtype=torch.bfloat16)
     out = torch.zeros(B * T, parts * Cc, device=x.device, dtype=torch.bfloat16)
     check(lib().lds_op_qkv_attention_tc(ptr(xp), ptr(wp), B, T, Cc, heads, dpad, parts, ptr(q), ptr(k), ptr(vt), ptr(out), stream()),
           "lds_op_qkv_attention_tc")
-    return out.float().view(B * T, parts, Cc).double().sum(1)
+    return planes_to_double(out, parts, Cc)
 
 
 # ---- solver / layout kernels (csrc/solver.cu) ----
@@ -249,7 +261,13 @@ def op_div_copy(x, d):
 
 
 def split_planes_ref(x, parts):
-    """fp32 [..., C] -> bf16 [..., parts*C] by the definition of the operand planes: hi = bf16(x), mid = bf16(x - hi), ..."""
+    """fp32 [..., C] -> 16-bit planes [..., parts*C] (as a bf16-typed tensor) by the definition of the operand planes:
+    parts 1 / 3: hi = bf16(x), mid = bf16(x - hi), ...; parts 2 (split-f16): h1 = f16(16 x), h2 = f16(16 x - h1)."""
+    if parts == 2:
+        xs = x.float() * PLANE_SCALE
+        h1 = xs.clamp(-65504.0, 65504.0).to(torch.float16)
+        h2 = (xs - h1.float()).to(torch.float16)
+        return torch.cat([h1, h2], dim=-1).view(torch.bfloat16)
     planes, r = [], x.float()
     for _ in range(parts):
         p = r.to(torch.bfloat16)

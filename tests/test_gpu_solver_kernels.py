@@ -142,7 +142,7 @@ def test_q_sample_bit_exact(shape, ascale):
     assert torch.equal(got, want[:, 0].transpose(1, 2).contiguous())
 
 
-@pytest.mark.parametrize("parts", [1, 3])
+@pytest.mark.parametrize("parts", [1, 2, 3])
 @pytest.mark.parametrize("B,t_in,C,t_out", [(2, 20, 256, 40), (3, 27, 384, 54), (2, 108, 512, 215), (1, 54, 512, 107)])
 def test_cast_gather_nearest_upsample_bit_exact(parts, B, t_in, C, t_out):
     x = _rand(B, t_in, C, seed=29, scale=7.0)
@@ -154,10 +154,10 @@ def test_cast_gather_nearest_upsample_bit_exact(parts, B, t_in, C, t_out):
         scale = float(torch.tensor(t_in, dtype=torch.float32) / torch.tensor(t_out, dtype=torch.float32))
     got = G.op_cast_gather(x, t_out, parts, 1, scale)
     want = G.split_planes_ref(up.transpose(1, 2).contiguous(), parts)
-    assert torch.equal(got, want)
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))        # bit patterns (parts = 2 holds fp16 bits)
 
 
-@pytest.mark.parametrize("parts", [1, 3])
+@pytest.mark.parametrize("parts", [1, 2, 3])
 @pytest.mark.parametrize("B,t_in,C", [(2, 40, 256), (3, 37, 384), (1, 431, 512)])
 def test_cast_gather_stride2_im2col_bit_exact(parts, B, t_in, C):
     x = _rand(B, t_in, C, seed=30, scale=7.0)
@@ -167,12 +167,12 @@ def test_cast_gather_stride2_im2col_bit_exact(parts, B, t_in, C):
     taps = torch.stack([xp[:, tap:tap + 2 * t_out:2] for tap in range(3)], dim=2)       # [B, t_out, 3, C]: frame 2*to - 1 + tap
     r = taps.reshape(B, t_out, 3 * C).float()
     want = G.split_planes_ref(r, parts)                                 # element (p, tap, c) at p*3C + tap*C + c
-    assert torch.equal(got, want)
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
     # and the k=3 / stride-2 / pad-1 convolution it feeds equals F.conv1d on the hi+mid+lo sum
-    if parts == 3:
+    if parts == 2:
         w = _rand(64, C, 3, seed=31, scale=(3 * C) ** -0.5)
         y_ref = F.conv1d(x.transpose(1, 2).double(), w.double(), stride=2, padding=1).transpose(1, 2)
-        cols = got.float().view(B, t_out, 3, 3 * C).double().sum(2)     # planes summed -> [B, t_out, 3C] (tap-major)
+        cols = G.planes_to_double(got.reshape(B * t_out, 2 * 3 * C), 2, 3 * C).view(B, t_out, 3 * C)   # planes -> values [B, t_out, 3C] (tap-major)
         y = cols @ w.permute(0, 2, 1).reshape(64, 3 * C).double().t()
         assert float((y - y_ref).abs().max()) < 1e-4
 

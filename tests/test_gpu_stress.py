@@ -32,7 +32,7 @@ def _bands_clean(buf, n):
     return bool(torch.isnan(buf[:GUARD]).all()) and bool(torch.isnan(buf[GUARD + n:]).all())
 
 
-@pytest.mark.parametrize("parts", [1, 3])
+@pytest.mark.parametrize("parts", [1, 2])
 @pytest.mark.parametrize("batches,rows,cin,N,taps,res", [
     (1, 300, 256, 256, 1, True),      # ragged M, TMA epilogue with residual
     (1, 55, 384, 384, 1, False),      # one partial tile + ghost tile
@@ -63,10 +63,10 @@ def test_gemm_tc_fp32_output_guard_bands_and_determinism(parts, batches, rows, c
         x = torch.cat([xp[:, t:t + rows] for t in range(3)], dim=-1)
     want = x.reshape(M, K) @ W.double().t() + bias.double() + (0 if R is None else R.double())
     e = G.errs(outs[0].view(M, N), want)
-    assert e["max_abs"] <= (5e-5 if parts == 3 else 6e-2) * max(1.0, e["scale"] / 4), e
+    assert e["max_abs"] <= (5e-5 if parts == 2 else 6e-2) * max(1.0, e["scale"] / 4), e
 
 
-@pytest.mark.parametrize("parts", [1, 3])
+@pytest.mark.parametrize("parts", [1, 2])
 @pytest.mark.parametrize("B,T,C", [(2, 40, 256), (3, 37, 384), (1, 300, 512)])
 def test_attention_tc_guard_bands_and_determinism(parts, B, T, C):
     heads, d = 8, C // 8
@@ -82,7 +82,8 @@ def test_attention_tc_guard_bands_and_determinism(parts, B, T, C):
     wp = G.pack_w_parts(torch.cat(rows, 0).contiguous(), 1, parts)
     xp = G.op_split_cast(x, parts)
     t_pad = (T + 7) // 8 * 8
-    n_qk, n_vt, n_out = B * T * parts * heads * dpad, B * parts * heads * dpad * t_pad, B * T * parts * C
+    ap = 3 if parts == 2 else 1
+    n_qk, n_vt, n_out = B * T * ap * heads * dpad, B * ap * heads * dpad * t_pad, B * T * parts * C
     outs = []
     for _ in range(8):
         bq, q = _guarded(n_qk, torch.bfloat16)
