@@ -131,10 +131,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const int nt = (p.T + AKV - 1) / AKV;
   const int ntA = (nt + PA - 1) / PA;              // pass-A steps of PA key tiles
   const int HD = p.H * DPAD;
-  constexpr int tmem_cols = (parts == 3 && !DUAL) ? 512 : 256;
-  constexpr int n_sblk = parts == 3 ? ((AKV == 64 && !DUAL) ? 3 : 2) : 1;
+  constexpr int tmem_cols = (parts >= 2 && !DUAL) ? 512 : 256;
+  // accumulator blocks: an instruction multiplies an A plane with up to `n_planes` B planes in consecutive shared-memory rows
+  // and writes one block per B plane; the softmax / epilogue threads add the blocks.
+  //   parts 2 (split-f16: h1, h2 of q, k, v^T and P): S = q1*[k1|k2] + q2*[k1]  ->  2 blocks, 2 instructions per k-step
+  //   parts 3 (three bf16 planes, round 1): 3 blocks (one N = 192 instruction) or 2 blocks in DUAL mode
+  constexpr int n_sblk = parts == 3 ? ((AKV == 64 && !DUAL) ? 3 : 2) : (parts == 2 ? 2 : 1);
   constexpr int s_stride = n_sblk * AKV;           // TMEM columns per S buffer
-  constexpr int n_oblk = parts == 3 ? 3 : 1;
+  constexpr int n_oblk = parts == 3 ? 3 : (parts == 2 ? 2 : 1);
+  // split-f16 scales: q, k, v^T planes hold 16 x value (written by the QKV projection), P planes 2048 x P (P <= 1)
+  constexpr float P_SCALE = parts == 2 ? 2048.f : 1.f;
+  constexpr float QK_SCALE = parts == 2 ? PLANE_SCALE * PLANE_SCALE : 1.f, PV_SCALE = parts == 2 ? P_SCALE * PLANE_SCALE : 1.f;
   // S buffers start at column 0, the O blocks (and the alternate 128-column pass-A buffer) at o_col
   constexpr int o_col = NSB * s_stride <= 128 ? 128 : (NSB * s_stride <= 256 ? 256 : 384);
   static_assert(o_col + (n_oblk * DPAD > 128 ? n_oblk * DPAD : 128) <= tmem_cols, "TMEM layout");
@@ -199,20 +206,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       // Work lists (widest instruction first: it initialises every accumulator block it covers).  They are compile-time
       // constants, the loops over them unroll completely and every descriptor below lives in a (uniform) register.
       constexpr bool WIDE_QK = parts == 3 && AKV == 64 && !DUAL;   // three S accumulator blocks: one N = 192 instruction
-      constexpr int n_qk = parts == 3 ? (WIDE_QK ? 3 : 4) : 1, n_pv = parts == 3 ? 3 : 1;
+      constexpr int n_qk = parts == 3 ? (WIDE_QK ? 3 : 4) : (parts == 2 ? 2 : 1), n_pv = parts == 3 ? 3 : (parts == 2 ? 2 : 1);
+      constexpr MmaItem qk_f16[4] = {{0, 0, 2, 0}, {1, 0, 1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};     // q1*[k1|k2], q2*[k1]
+      constexpr MmaItem pv_f16[3] = {{0, 0, 2, 0}, {1, 0, 1, 0}, {0, 0, 0, 0}};                    // p1*[v1|v2], p2*[v1]
       constexpr MmaItem qk_wide[4] = {{0, 0, 3, 0}, {1, 0, 2, 0}, {2, 0, 1, 0}, {0, 0, 0, 0}};
       constexpr MmaItem qk_dual[4] = {{0, 0, 2, 0}, {1, 0, 2, 0}, {0, 2, 1, 1}, {2, 0, 1, 0}};
       constexpr MmaItem qk_one[4] = {{0, 0, 1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
       constexpr MmaItem pv_split[3] = {{0, 0, 3, 0}, {1, 0, 2, 0}, {2, 0, 1, 0}};
       constexpr MmaItem pv_one[3] = {{0, 0, 1, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-      auto qk = [&](int e) -> MmaItem { return parts == 3 ? (WIDE_QK ? qk_wide[e] : qk_dual[e]) : qk_one[e]; };
-      auto pv = [&](int e) -> MmaItem { return parts == 3 ? pv_split[e] : pv_one[e]; };
+      auto qk = [&](int e) -> MmaItem { return parts == 3 ? (WIDE_QK ? qk_wide[e] : qk_dual[e]) : (parts == 2 ? qk_f16[e] : qk_one[e]); };
+      auto pv = [&](int e) -> MmaItem { return parts == 3 ? pv_split[e] : (parts == 2 ? pv_f16[e] : pv_one[e]); };
+      auto idesc = [&](int n) -> uint32_t { return parts == 2 ? umma_idesc_f16(AQ, n) : umma_idesc_bf16(AQ, n); };
       const uint64_t q_desc0 = umma_desc_kmajor(q_s, SWZ), k_desc0 = umma_desc_kmajor(k_s, SWZ);
       const uint64_t p_desc0 = umma_desc_kmajor(p_s, 128), v_desc0 = umma_desc_kmajor(v_s, 128);
       constexpr uint64_t k_stage_step = (uint64_t)((KSL * KB) >> 4), v_stage_step = (uint64_t)((parts * KBLK * VBK) >> 4),
                          v_kb_step = (uint64_t)((parts * VBK) >> 4), p_buf_step = (uint64_t)((parts * KBLK * PBK) >> 4),
                          p_kb_step = (uint64_t)(PBK >> 4);
-      constexpr uint32_t hi_idesc = umma_idesc_bf16(AQ, PA * AKV);
+      constexpr uint32_t hi_idesc = parts == 2 ? umma_idesc_f16(AQ, PA * AKV) : umma_idesc_bf16(AQ, PA * AKV);
       const int ksteps = (p.d + 15) / 16;        // head dims beyond d are zero padding (d = 48 in a 64-wide tile): skip their K slices
       // S buffer of an evaluation: pass B rotates over the NSB buffers of the S region; pass A (PA == 2) alternates between
       // columns [0, 128) and the O region (idle until the first P V of the item), so that the hi*hi product of step j+1 runs
@@ -262,7 +272,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 #pragma unroll
             for (int e = 0; e < n_qk; ++e)
               umma_bf16_elect(dst + (uint32_t)(qk(e).blk * AKV), q_desc0 + (uint64_t)((qk(e).a_plane * QB) >> 4) + (uint64_t)(2 * k),
-                        kd + (uint64_t)((qk(e).b_plane0 * KB) >> 4) + (uint64_t)(2 * k), umma_idesc_bf16(AQ, qk(e).n_planes * AKV),
+                        kd + (uint64_t)((qk(e).b_plane0 * KB) >> 4) + (uint64_t)(2 * k), idesc(qk(e).n_planes * AKV),
                         (k == 0 && e == 0) ? 0u : 1u);
           }
         }
@@ -292,7 +302,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 #pragma unroll
             for (int e = 0; e < n_pv; ++e)
               umma_bf16_elect(tmem_o + (uint32_t)(pv(e).blk * DPAD), pk + (uint64_t)((pv(e).a_plane * KBLK * PBK) >> 4),
-                        vk + (uint64_t)((pv(e).b_plane0 * VBK) >> 4), umma_idesc_bf16(AQ, pv(e).n_planes * DPAD),
+                        vk + (uint64_t)((pv(e).b_plane0 * VBK) >> 4), idesc(pv(e).n_planes * DPAD),
                         (jb == 0 && k == 0 && e == 0) ? 0u : 1u);
           }
           umma_commit_elect(v_empty(vs));
@@ -306,7 +316,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     const int row = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int c0 = half * (AKV / 2);                     // this thread's key columns inside a tile
-    const float sl2 = p.scale * 1.4426950408889634f;    // softmax scale * log2(e): exp(x*scale - m) = 2^(x*sl2 - m*sl2)
+    // softmax scale * log2(e) (/ the operand scales of the split-f16 planes): exp(x*scale - m) = 2^(x*sl2 - m*sl2)
+    const float sl2 = p.scale * 1.4426950408889634f / QK_SCALE;
     // sum of the accumulator blocks of 32 columns starting at column c of the S tile
     auto load_s32 = [&](int sb, int c, float* s) {
       const uint32_t sbase = tmem0 + lane_off + sb * s_stride + c;
@@ -378,12 +389,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; i += 2) { l0 += s[i]; l1 += s[i + 1]; }
           l += l0 + l1;
-          // split into bf16 planes in registers, so that only the stores sit behind the P-buffer hand-off
+          // split into operand planes in registers, so that only the stores sit behind the P-buffer hand-off
+          if constexpr (PARTS == 2) {                                    // split-f16: h1 = f16(P_SCALE * P), h2 = f16(rest)
 #pragma unroll
-          for (int pl = 0; pl < PARTS; ++pl) {
+            for (int i = 0; i < 32; ++i) s[i] *= P_SCALE;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              w[pl][ch * 16 + i] = (pl == PARTS - 1) ? pack_pair(s[2 * i], s[2 * i + 1]) : split_pair(s[2 * i], s[2 * i + 1]);
+            for (int i = 0; i < 16; ++i) w[0][ch * 16 + i] = planes_split_pair_f16(s[2 * i], s[2 * i + 1]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[1][ch * 16 + i] = planes_pack_pair_f16(s[2 * i], s[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int pl = 0; pl < PARTS; ++pl) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                w[pl][ch * 16 + i] = (pl == PARTS - 1) ? pack_pair(s[2 * i], s[2 * i + 1]) : split_pair(s[2 * i], s[2 * i + 1]);
+            }
           }
         }
         {                                                                // the P*V that last read this P buffer is done
@@ -433,7 +453,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const int ncol = min(OC, p.d - half * OC);                        // d = 48: 16 valid columns in the upper half
       if (q < p.T && ncol > 0) {
         __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q) * (size_t)(p.out_parts * p.C) + h * p.d + half * OC;
-        const float oscale = p.out_parts == 2 ? inv * PLANE_SCALE : inv;
+        const float oscale = (p.out_parts == 2 ? inv * PLANE_SCALE : inv) * (1.f / PV_SCALE);
 #pragma unroll
         for (int i = 0; i < OC; ++i) o[i] *= oscale;
         for (int pl = 0; pl < p.out_parts; ++pl) {
@@ -509,19 +529,20 @@ cudaError_t launch_attn(const AttnTcArgs& a, cudaStream_t s) {
 
 cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
-  if ((a.parts != 1 && a.parts != 3) || a.d > a.dpad || a.d % 8 || a.T_pad % 8 || a.T_pad < a.T) return cudaErrorInvalidValue;
+  if (a.parts < 1 || a.parts > 3 || a.d > a.dpad || a.d % 8 || a.T_pad % 8 || a.T_pad < a.T) return cudaErrorInvalidValue;
   // shared memory per CTA (KB): Q + nk*K + nv*V^T + P; a K stage holds max(parts, 2) 64-key tiles (pass A loads two
   // hi-plane tiles per stage), two CTAs per SM in bf16 and DUAL mode (bounded by 2 x 256 TMEM columns)
-  if (a.parts == 3) {
-    // d <= 32: two CTAs per SM: 24 (Q) + 2*12 (K) + 12 (V^T) + 48 (P) = 108 KB, TMEM 128 (S) + 96 (O) per CTA.
-    // (A CTA-pair variant, tests/micro/attention_pair.cu, is parity-green but NOT faster: a cta_group::2 instruction
-    // occupies the tensor pipes of BOTH SMs for the same ~92 cycles, so the issue cost per query row and SM is unchanged —
-    // tests/micro/bench_umma.cu, 0.73 vs 0.68 ms per T=864 attention at B=64.  It is not part of the library.)
-    // (One CTA per SM with S (three blocks, one N = 192 instruction per k-step) and P double-buffered measured SLOWER at d = 32:
-    // 0.578 vs 0.511 ms per T=864 attention at B=64, GPU call 8 of round 2 — two co-resident CTAs hide the softmax latency better.)
+  if (a.parts == 2) {
+    // split-f16 operands (h1, h2 of q, k, v^T; P split the same way): 2 S blocks (128 columns) + 2 O blocks (2*dpad columns).
+    // d <= 32: two CTAs per SM (DUAL): 16 (Q) + 2*8 (K) + 2*8 (V^T) + 32 (P) = 80 KB, TMEM 128 + 64.
+    // d > 32: 112 KB + barriers is 1.3 KB too much for two CTAs per SM -> one CTA per SM with S and P double-buffered:
+    //         32 (Q) + 2*16 (K) + 2*16 (V^T) + 2*32 (P) = 160 KB, TMEM 2*128 (S) + 128 (O)
+    if (a.dpad == 32) return launch_attn<32, 64, 2, true, 2, 2, 1, 1>(a, s);
+    if (a.dpad == 64) return launch_attn<64, 64, 2, false, 2, 2, 2, 2>(a, s);
+  } else if (a.parts == 3) {
+    // three bf16 planes, six plane products (round 1's fp32-accurate form; kept for A/B through lds_op_qkv_attention_tc)
     if (a.dpad == 32) return launch_attn<32, 64, 3, true, 2, 1, 1, 1>(a, s);
-    // (a second P buffer in exchange for a one-deep V^T ring measured 14 % slower: 0.47 vs 0.41 ms at T=432, B=64)
-    if (a.dpad == 64) return launch_attn<64, 64, 3, false, 2, 2, 1, 1>(a, s);    // 48 + 2*24 + 2*24 + 48 = 192, TMEM 192 (S) + 192 (O)
+    if (a.dpad == 64) return launch_attn<64, 64, 3, false, 2, 2, 1, 1>(a, s);
   } else {                                                             // bf16: S and P double-buffered, two CTAs per SM
     // K stages hold two 64-key tiles (pass A runs over 128-key steps): 4 (2) stages of 8 (16) KB
     if (a.dpad == 32) return launch_attn<32, 64, 1, false, 4, 3, 2, 2>(a, s);    //  8 + 4*8 + 3*4 + 2*16 = 84, TMEM 2*64 (S) + 32 (O)

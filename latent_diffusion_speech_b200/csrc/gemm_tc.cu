@@ -227,6 +227,17 @@ __device__ __forceinline__ void stage_store_bf16(const TcParams& p, const EpiCtx
       const int HD = p.att_H * p.att_dpad;
       base = (q_region == 0 ? p.q_out : p.k_out) + row * (size_t)(p.att_parts * HD) + (c8 - q_region * HD); parts = p.att_parts; pstride = HD;
     }
+    if (p.out_kind == 3 && parts == 2) {  // split-f16 attention operands: [h1 | h2] of the scaled value
+      a.x *= PLANE_SCALE; a.y *= PLANE_SCALE; a.z *= PLANE_SCALE; a.w *= PLANE_SCALE;
+      b.x *= PLANE_SCALE; b.y *= PLANE_SCALE; b.z *= PLANE_SCALE; b.w *= PLANE_SCALE;
+      uint4 w;
+      w.x = planes_split_pair_f16(a.x, a.y); w.y = planes_split_pair_f16(a.z, a.w);
+      w.z = planes_split_pair_f16(b.x, b.y); w.w = planes_split_pair_f16(b.z, b.w);
+      *reinterpret_cast<uint4*>(base) = w;
+      w = make_uint4(planes_pack_pair_f16(a.x, a.y), planes_pack_pair_f16(a.z, a.w), planes_pack_pair_f16(b.x, b.y), planes_pack_pair_f16(b.z, b.w));
+      *reinterpret_cast<uint4*>(base + pstride) = w;
+      continue;
+    }
     for (int pl = 0; pl < parts; ++pl) {
       uint4 w;
       if (pl == parts - 1) {
@@ -260,11 +271,16 @@ __device__ __forceinline__ void store_vt32(const TcParams& p, size_t row, int co
   const int HD = p.att_H * p.att_dpad, rem = col - 2 * HD;
   const int bb = (int)(row / p.att_T), tt = (int)(row - (size_t)bb * p.att_T);
   const int hh = rem / p.att_dpad, j0 = rem - hh * p.att_dpad;
+  if (p.att_parts == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= PLANE_SCALE;
+  }
   for (int pl = 0; pl < p.att_parts; ++pl) {
     __nv_bfloat16* dst = p.vt_out + ((size_t)((bb * p.att_parts + pl) * p.att_H + hh) * p.att_dpad + j0) * p.att_Tpad + tt;
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const uint32_t w = pl == p.att_parts - 1 ? pack_pair_bf16(v[i], v[i + 1]) : split_pair_bf16(v[i], v[i + 1]);
+      const uint32_t w = p.att_parts == 2 ? (pl == 0 ? planes_split_pair_f16(v[i], v[i + 1]) : planes_pack_pair_f16(v[i], v[i + 1]))
+                                          : (pl == p.att_parts - 1 ? pack_pair_bf16(v[i], v[i + 1]) : split_pair_bf16(v[i], v[i + 1]));
       dst[(size_t)i * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w & 0xffffu));
       dst[(size_t)(i + 1) * p.att_Tpad] = __ushort_as_bfloat16((unsigned short)(w >> 16));
     }
@@ -934,6 +950,11 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
     const bool flat = a.batches > 1 && a.rows % 32 == 0 && a.rows % TBM != 0;
     const int m_tiles = flat ? (blks + 3) / 4 : ((a.rows + TBM - 1) / TBM) * a.batches;
     if (p.BN == 256 && (a.N / 256) * ((m_tiles + 1) / 2) * 4 <= max_clusters2()) p.BN = 128;
+    // split-f16: main + small accumulator of a 256-column tile fill the 512 TMEM columns, so the epilogue of a tile cannot
+    // overlap the next tile's main loop; with 128-column tiles two buffers fit.  Short K loops (<= LDS_SPLIT_BN128_KB K blocks)
+    // take the narrow, double-buffered form, long ones the wide one.
+    static const int kb_thr = getenv("LDS_SPLIT_BN128_KB") ? atoi(getenv("LDS_SPLIT_BN128_KB")) : 8;      // tuning switch (to be fixed)
+    if (split && p.BN == 256 && a.taps * (a.cin / TBK) <= kb_thr) p.BN = 128;
   }
   p.w_slot_bytes = (p.BN / 2) * TBK * 2;          // each CTA of the pair holds half of the W tile
   // fp32 outputs (with or without an fp32 residual) go through the TMA epilogue

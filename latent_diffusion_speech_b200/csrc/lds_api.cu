@@ -127,7 +127,7 @@ struct lds_handle {
   __nv_bfloat16* wharena = nullptr;   // bf16 operand planes of the GEMM weights (tensor-core modes)
   size_t wharena_elems = 0;
   int parts = 0;                      // GEMM operand planes: 0 FFMA fp32 kernels; 1 bf16 tcgen05; 2 split-f16 tcgen05 (fp32-accurate), planes.cuh
-  int att_parts = 0;                  // attention operand planes (Q, K, V^T): 1 bf16; 3 bf16 hi/mid/lo (fp32-accurate mode)
+  int att_parts = 0;                  // attention operand planes (Q, K, V^T): 1 bf16; 2 split-f16 (fp32-accurate mode)
   float wscale = 1.f;                 // split-f16: power-of-two scale of the packed GEMM weights (activations: PLANE_SCALE)
   int temb_dim = 0, temb_total = 0;
   const float *unit_w = nullptr, *unit_b = nullptr, *spk_table = nullptr;
@@ -716,7 +716,7 @@ int lds_create(const lds_config* cfg, int device, lds_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   h->parts = cfg->precision == LDS_PREC_FP32 ? 2 : (cfg->precision == LDS_PREC_BF16 ? 1 : 0);
-  h->att_parts = cfg->precision == LDS_PREC_FP32 ? 3 : h->parts;
+  h->att_parts = h->parts;            // split-f16 attention operands in the fp32-accurate mode (three bf16 planes in round 1)
   h->temb_dim = 4 * cfg->block_out_channels[0];
   *out = h;
   return LDS_OK;
@@ -1451,7 +1451,7 @@ int lds_op_qkv_attention_tc(const void* x_planes, const void* w_qkv, int B, int 
   lds::TcGemmArgs g;
   g.A = (const __nv_bfloat16*)x_planes; g.batches = 1; g.rows = B * T; g.cin = C;
   g.W = (const __nv_bfloat16*)w_qkv; g.N = 3 * H * dpad; g.taps = 1;
-  const int att_parts = parts == 2 ? 3 : 1;
+  const int att_parts = parts;
   if (parts == 2) { lds::tc_set_split_pairs(g); g.out_scale = 1.f / (lds::PLANE_SCALE * lds::PLANE_SCALE); }
   g.att_parts = att_parts;
   g.out_kind = 3; g.q_out = (__nv_bfloat16*)q_scratch; g.k_out = (__nv_bfloat16*)k_scratch; g.vt_out = (__nv_bfloat16*)vt_scratch;

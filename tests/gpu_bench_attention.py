@@ -17,7 +17,7 @@ for (T, C) in [(864, 256), (432, 384), (216, 512)]:
         w = (torch.randn(3 * heads * dpad, C, generator=g) * C ** -0.5).cuda()
         wp, xp = G.pack_w_parts(w, 1, parts), G.op_split_cast(x, parts)
         t_pad = (T + 7) // 8 * 8
-        ap = 3 if parts == 2 else 1
+        ap = parts
         q = torch.zeros(B * T * ap * heads * dpad, device="cuda", dtype=torch.bfloat16)
         k = torch.zeros_like(q)
         vt = torch.zeros(B * ap * heads * dpad * t_pad, device="cuda", dtype=torch.bfloat16)

@@ -165,7 +165,7 @@ def op_qkv_attention_tc(x, wq, wk, wv, B, T, heads, parts):
     wp = pack_w_parts(torch.cat(rows, 0).contiguous(), 1, parts)
     xp = op_split_cast(x, parts)
     t_pad = (T + 7) // 8 * 8
-    ap = 3 if parts == 2 else 1          # attention operands: three bf16 planes in the fp32-accurate mode
+    ap = parts          # attention operands: three bf16 planes in the fp32-accurate mode
     q = torch.zeros(B * T * ap * heads * dpad, device=x.device, dtype=torch.bfloat16)
     k = torch.zeros_like(q)
     vt = torch.zeros(B * ap * heads * dpad * t_pad, device=x.device, dtype=torch.bfloat16)

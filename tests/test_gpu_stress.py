@@ -82,7 +82,7 @@ def test_attention_tc_guard_bands_and_determinism(parts, B, T, C):
     wp = G.pack_w_parts(torch.cat(rows, 0).contiguous(), 1, parts)
     xp = G.op_split_cast(x, parts)
     t_pad = (T + 7) // 8 * 8
-    ap = 3 if parts == 2 else 1
+    ap = parts
     n_qk, n_vt, n_out = B * T * ap * heads * dpad, B * ap * heads * dpad * t_pad, B * T * parts * C
     outs = []
     for _ in range(8):
