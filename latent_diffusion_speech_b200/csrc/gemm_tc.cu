@@ -703,6 +703,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         e.grow0 = (size_t)(mt < p.m_tiles ? b : 0) * p.rows + t_blk;
       }
       const int buf = p.n_buf == 2 ? (local & 1) : 0;
+      if (p.tma_epi == 2 && p.R && lane == 0) {  // while the main loop of this tile runs: pull its residual blocks into the L2, so
+        int col, t, b;                           // that the shared-memory loads of the chunks beyond the tile ring pay an L2 hit only
+        for (int c = part; c < (p.BN >> 5); c += EPI_PARTS) {
+          chunk_coords(p, item, c, (int)crank, quarter, col, t, b);
+          if (b < p.batches) tma_prefetch_l2_3d(&mapR, col, t, b);
+        }
+      }
       mbar_wait(tmem_full_bar(buf), (p.n_buf == 2 ? ((uint32_t)local >> 1) : (uint32_t)local) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + buf * p.buf_stride + ((uint32_t)(quarter * 32) << 16);
@@ -961,8 +968,10 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   const bool aligned16 = (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (!a.R || (reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
   p.tma_epi = (a.out_kind == 0 && a.epilogue != EPI_GEGLU && (!a.R || a.r_div == 1) && a.c_ld % 4 == 0 && (!a.R || a.r_ld % 4 == 0) &&
                aligned16 && knobs().tma_epi) ? 1 : 0;
-  p.nbuf = split ? 2 : 3;
-  p.na = (split || !p.tma_epi) ? 6 : 4;
+  static const int nbuf_split = getenv("LDS_EPI_NBUF") ? atoi(getenv("LDS_EPI_NBUF")) : 3;       // tuning switch (to be fixed)
+  p.nbuf = split ? nbuf_split : 3;
+  { static const bool l2pf = !(getenv("LDS_EPI_L2PF") && atoi(getenv("LDS_EPI_L2PF")) == 0); if (p.tma_epi && l2pf) p.tma_epi = 2; }   // tuning switch (to be fixed)
+  p.na = !p.tma_epi ? 6 : (split ? (p.nbuf >= 3 ? 4 : 6) : 4);
   const int stage_bytes = p.tma_epi ? N_EPI_WARPS * p.nbuf * STAGE_BYTES : (split ? N_EPI_WARPS * STAGE_BYTES : 0);
   p.nw = (SMEM_BUDGET - stage_bytes - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
   if (p.nw > MAX_SLOTS) p.nw = MAX_SLOTS;
