@@ -47,9 +47,11 @@ typedef enum {
   LDS_ERR_UNSUPPORTED = -4
 } lds_status;
 
-/* LDS_PREC_FP32      : fp32-accurate.  GEMM operands are split into three bf16 planes (hi+mid+lo == x to 24 bits) and the
- *                      six significant plane products are accumulated in fp32 in TMEM by tcgen05.mma; norms, softmax,
- *                      attention and the solver run in fp32.
+/* LDS_PREC_FP32      : fp32-accurate ("split-f16").  Every GEMM / attention operand is held as two fp16 planes of the value
+ *                      times a power of two (h1 = f16(s x), h2 = f16(s x - h1): 22 significant bits, csrc/planes.cuh) and every
+ *                      product is evaluated by tcgen05.mma as h1*w1 + (h1*w2 + h2*w1) with fp32 accumulation in TMEM — three
+ *                      tensor-core products per logical product; norms, softmax statistics and the solver run in fp32.
+ *                      Meets max-abs <= 1e-3 against the reference fp32 sampler (tests/test_gpu_parity*.py).
  * LDS_PREC_BF16      : bf16 GEMM operands (one tcgen05.mma per K slice), fp32 accumulation, fp32 norms / solver state.
  * LDS_PREC_FP32_FFMA : IEEE fp32 FFMA kernels on the CUDA cores (the first, reference-grade implementation). */
 typedef enum { LDS_PREC_FP32 = 0, LDS_PREC_BF16 = 1, LDS_PREC_FP32_FFMA = 2 } lds_precision;
@@ -192,19 +194,23 @@ LDS_API int lds_op_groupnorm_cluster(const float* x1, int c1, const float* x2, i
                              void* stream);
 LDS_API int lds_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
                      void* stream);
-/* Tensor-core (tcgen05/TMEM/TMA) form of lds_op_gemm on bf16 operands.
- *   lds_op_split_cast : fp32 [rows, C] -> bf16 [rows, parts*C]; parts=1 rounds, parts=3 writes hi/mid/lo planes
- *   lds_op_gemm_tc    : A bf16 [batches][rows][parts*cin], w bf16 [N][taps*parts*cin] (tap-major, then plane, then
- *                       channel); parts=1: plain bf16 product; parts=3: six-term split product (fp32-accurate).
- *                       taps=3: k=3/stride-1/pad-1 conv along rows.  out_kind 0 fp32, 1 bf16, 2 split planes. */
+/* Tensor-core (tcgen05/TMEM/TMA) form of lds_op_gemm on 16-bit operand planes (csrc/planes.cuh).
+ *   lds_op_split_cast : fp32 [rows, C] -> planes [rows, parts*C] (2 bytes per element): parts=1 rounds to bf16; parts=2 writes the
+ *                       SPLIT-F16 form h1 = f16(16 x), h2 = f16(16 x - h1) (fp32-accurate mode); parts=3 three bf16 planes hi/mid/lo
+ *   lds_op_gemm_tc    : A planes [batches][rows][parts*cin], w planes [N][taps*parts*cin] (tap-major, then plane, then channel),
+ *                       both produced by lds_op_split_cast; parts=1: one bf16 product; parts=2: the three products h1*w1 (main
+ *                       TMEM accumulator) and h1*w2 + h2*w1 (small accumulator), added and rescaled in the epilogue — fp32-accurate
+ *                       at three tensor-core products per logical product.  taps=3: k=3/stride-1/pad-1 conv along rows.
+ *                       out_kind 0 fp32, 1 bf16, 2 split-f16 planes [h1 | h2]. */
 LDS_API int lds_op_split_cast(const float* in, void* out_bf16, int64_t rows, int C, int parts, void* stream);
 LDS_API int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, int parts, const void* w_bf16, int N, int taps,
                    const float* bias, const float* R, int r_ld, int r_div, void* C, int c_ld, int out_kind,
                    int epilogue, void* stream);
-/* Fused QKV projection + tcgen05 flash attention (attention_processor.py:1012-1034) on bf16 planes:
- *   x planes [B*T][parts*C] -> q/k/v^T scratch (layouts in lds_kernels.h) -> out planes [B*T][parts*C].
- *   w_qkv: bf16 [3*H*dpad][parts*C], rows = [q | k | v] x heads x dpad (head dim zero-padded to dpad in {32,64}).
- *   scratch sizes (bf16 elements): q, k: B*T*parts*H*dpad; vt: B*parts*H*dpad*T_pad, T_pad = round_up(T, 8). */
+/* Fused QKV projection + tcgen05 flash attention (attention_processor.py:1012-1034) on operand planes:
+ *   x planes [B*T][parts*C] -> q/k/v^T scratch (layouts in lds_kernels.h) -> out planes [B*T][parts*C].  parts 1 (bf16) or 2 (split-f16:
+ *   Q, K, V^T and the probabilities P are each two fp16 planes, every product is evaluated as three plane products).
+ *   w_qkv: planes [3*H*dpad][parts*C], rows = [q | k | v] x heads x dpad (head dim zero-padded to dpad in {32,64}).
+ *   scratch sizes (16-bit elements): q, k: B*T*parts*H*dpad; vt: B*parts*H*dpad*T_pad, T_pad = round_up(T, 8). */
 LDS_API int lds_op_qkv_attention_tc(const void* x_planes, const void* w_qkv, int B, int T, int C, int H, int dpad, int parts,
                             void* q_scratch, void* k_scratch, void* vt_scratch, void* out_planes, void* stream);
 

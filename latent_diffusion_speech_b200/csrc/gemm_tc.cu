@@ -2,11 +2,14 @@
 //
 // One kernel serves both precision modes of the library:
 //   * LDS_PREC_BF16 : A and W are bf16, one tcgen05.mma (kind::f16, fp32 accumulate in TMEM) per K slice.
-//   * LDS_PREC_FP32 : "split-bf16" — every fp32 operand is stored as three bf16 planes (hi, mid, lo with
-//     hi+mid+lo == x to 24 bits) and the six significant plane products (lo*hi, hi*lo, mid*mid, mid*hi, hi*mid,
-//     hi*hi) are accumulated in fp32, which recovers fp32-level accuracy on the tensor pipe at 6 MMAs per K slice.
+//   * LDS_PREC_FP32 : "split-f16" (round 2) — every fp32 operand is stored as two fp16 planes of the scaled value (planes.cuh:
+//     h1 = f16(s x), h2 = f16(s x - h1), 22 significant bits) and the product is evaluated as h1*w1 + (h1*w2 + h2*w1): THREE MMAs
+//     per K slice instead of the six of round 1's three-bf16-plane split, and 4 instead of 6 operand bytes per element.  The
+//     operand error of the three-product sum is a third of an fp32 FFMA GEMM's own rounding error
+//     (profiles/r02_split_f16_operand_error.txt); what dominates the result error is the tensor core's truncating fp32
+//     accumulate, as before.
 //
-// Structure (B200, sm_100a), v4.  Measured on B200 (tests/micro/bench_umma.cu, tests/gpu_gemm_bench.py, ncu captures
+// Structure (B200, sm_100a).  Measured on B200 (tests/micro/bench_umma.cu, tests/gpu_gemm_bench.py, ncu captures
 // under profiles/): one tcgen05.mma M128 x K16 costs ~92 cycles for any N <= 128 but 96 / 128 cycles at N = 192 / 256,
 // so only N >= 192 instructions run the pipe at its rate; and the main loop is bound by the bytes the L2 can DELIVER
 // to one SM (~40 B/clk/SM; TMA multicast between two CTAs does not lower it, keeping a smaller share of W per SM does).
@@ -16,20 +19,20 @@
 //     MMA for both SMs.  BN = 256 / 192 / 128 chosen per GEMM so that N % BN == 0.  Pairs are persistent, items
 //     (M-tile pair, N tile) strided over the clusters with the N tiles of one row block adjacent (A rows stay hot in L2).
 //     An odd M tile count leaves one ghost tile (TMA zero fill, no stores).
-//   * K blocks of 64 bf16 (128-byte rows, 128B swizzle).  Operand tiles live in TWO shared-memory rings — A slots of
+//   * K blocks of 64 elements (128-byte rows, 128B swizzle).  Operand tiles live in TWO shared-memory rings — A slots of
 //     16 KB, W slots of BN/2 x 128 B — filled by each CTA's producer in the order the MMA warp needs them and released
-//     tile by tile, so that a plane tile is loaded once per K block and reused by every product that needs it:
-//       pass 1 (split mode), per K block: loads A_lo W_hi A_mid W_mid A_hi W_lo, products lo*hi, mid*hi, mid*mid,
-//                            hi*mid, hi*lo (6 tiles per 5 products instead of 10);
-//       pass 2, per K block: loads A_hi W_hi, product hi*hi (the only product in bf16 mode).
-//     The small products of the whole K range are accumulated before any hi*hi term: the tensor pipe's fp32
-//     accumulate truncates, so accumulation steps taken while the accumulator is still small cost nothing.
+//     tile by tile.  Split-f16 mode, per K block: loads A_h1 W_h2 A_h2 W_h1 (every plane tile once), products h1*w2 and
+//     h2*w1 into the SMALL accumulator, h1*w1 into the MAIN one.  The two accumulators are separate TMEM column ranges:
+//     the tensor core's fp32 accumulate truncates at every step, and the main accumulator should see as few steps as the
+//     bf16 mode's (four per K block); the small one holds terms 2^-11 of the main, its truncation is irrelevant.  The epilogue
+//     adds the two once, in fp32, and multiplies by 1 / (scale_A * scale_W).
 //   * Barriers: "full" barriers live in the leader and count the TMA bytes of BOTH CTAs (the peer's loads complete on
 //     the leader's barrier, cp.async.bulk.tensor.cta_group::2); "empty" and "accumulator full" barriers exist in both
 //     CTAs and are signalled by the leader's multicast tcgen05.commit; "accumulator empty" lives in the leader and
 //     collects one relaxed remote arrive per epilogue warp of both CTAs.
-//   * The accumulator (BN fp32 columns) is double-buffered in TMEM (2 x 256 of the 512 columns): the epilogue of
-//     tile i overlaps the main loop of tile i+1.
+//   * TMEM (512 columns): bf16 mode double-buffers its BN-column accumulator (the epilogue of tile i overlaps the main loop
+//     of tile i+1).  Split-f16 mode needs main + small = 2 BN columns per buffer: two buffers at BN = 128 (short K loops),
+//     one at BN = 256 / 192 (long K loops, where the exposed epilogue is a small share).
 //   warp 0      TMA producer  — cp.async.bulk.tensor (3-D map over [channels, frames, utterances] for A so that the
 //                               three taps of a k=3 convolution are three shifted loads of the same tensor and the
 //                               zero padding is TMA out-of-bounds fill; 2-D map for W), mbarrier tx counts
@@ -703,13 +706,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         e.grow0 = (size_t)(mt < p.m_tiles ? b : 0) * p.rows + t_blk;
       }
       const int buf = p.n_buf == 2 ? (local & 1) : 0;
-      if (p.tma_epi == 2 && p.R && lane == 0) {  // while the main loop of this tile runs: pull its residual blocks into the L2, so
-        int col, t, b;                           // that the shared-memory loads of the chunks beyond the tile ring pay an L2 hit only
-        for (int c = part; c < (p.BN >> 5); c += EPI_PARTS) {
-          chunk_coords(p, item, c, (int)crank, quarter, col, t, b);
-          if (b < p.batches) tma_prefetch_l2_3d(&mapR, col, t, b);
-        }
-      }
       mbar_wait(tmem_full_bar(buf), (p.n_buf == 2 ? ((uint32_t)local >> 1) : (uint32_t)local) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + buf * p.buf_stride + ((uint32_t)(quarter * 32) << 16);
@@ -958,20 +954,21 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
     const int m_tiles = flat ? (blks + 3) / 4 : ((a.rows + TBM - 1) / TBM) * a.batches;
     if (p.BN == 256 && (a.N / 256) * ((m_tiles + 1) / 2) * 4 <= max_clusters2()) p.BN = 128;
     // split-f16: main + small accumulator of a 256-column tile fill the 512 TMEM columns, so the epilogue of a tile cannot
-    // overlap the next tile's main loop; with 128-column tiles two buffers fit.  Short K loops (<= LDS_SPLIT_BN128_KB K blocks)
+    // overlap the next tile's main loop; with 128-column tiles two buffers fit.  Short K loops (<= 8 K blocks)
     // take the narrow, double-buffered form, long ones the wide one.
-    static const int kb_thr = getenv("LDS_SPLIT_BN128_KB") ? atoi(getenv("LDS_SPLIT_BN128_KB")) : 8;      // tuning switch (to be fixed)
-    if (split && p.BN == 256 && a.taps * (a.cin / TBK) <= kb_thr) p.BN = 128;
+    // take the narrow, double-buffered form, long ones the wide one (thresholds 0 / 4 / 8 / 16 K blocks measured 534.0 / 531.0 /
+    // 529.3 / 531.6 ms per headline step).
+    if (split && p.BN == 256 && a.taps * (a.cin / TBK) <= 8) p.BN = 128;
   }
   p.w_slot_bytes = (p.BN / 2) * TBK * 2;          // each CTA of the pair holds half of the W tile
   // fp32 outputs (with or without an fp32 residual) go through the TMA epilogue
   const bool aligned16 = (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (!a.R || (reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
   p.tma_epi = (a.out_kind == 0 && a.epilogue != EPI_GEGLU && (!a.R || a.r_div == 1) && a.c_ld % 4 == 0 && (!a.R || a.r_ld % 4 == 0) &&
                aligned16 && knobs().tma_epi) ? 1 : 0;
-  static const int nbuf_split = getenv("LDS_EPI_NBUF") ? atoi(getenv("LDS_EPI_NBUF")) : 3;       // tuning switch (to be fixed)
-  p.nbuf = split ? nbuf_split : 3;
-  { static const bool l2pf = !(getenv("LDS_EPI_L2PF") && atoi(getenv("LDS_EPI_L2PF")) == 0); if (p.tma_epi && l2pf) p.tma_epi = 2; }   // tuning switch (to be fixed)
-  p.na = !p.tma_epi ? 6 : (split ? (p.nbuf >= 3 ? 4 : 6) : 4);
+  // (three tiles per warp with shallower operand rings, and an L2 prefetch of the residual blocks at tile start, measured the
+  // same as two tiles: 115.1-116.0 k frames/s for all four combinations, GPU call 26 of round 2)
+  p.nbuf = split ? 2 : 3;
+  p.na = (split || !p.tma_epi) ? 6 : 4;
   const int stage_bytes = p.tma_epi ? N_EPI_WARPS * p.nbuf * STAGE_BYTES : (split ? N_EPI_WARPS * STAGE_BYTES : 0);
   p.nw = (SMEM_BUDGET - stage_bytes - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
   if (p.nw > MAX_SLOTS) p.nw = MAX_SLOTS;

@@ -60,7 +60,7 @@ class Unit2Mel(nn.Module):
         self._hp = dict(input_channel=input_channel, n_spk=n_spk, out_dims=out_dims, n_layers=n_layers,
                         block_out_channels=tuple(block_out_channels), n_heads=n_heads, n_hidden=n_hidden,
                         acoustic_scale=acoustic_scale)
-        self.precision = "fp32"       # "fp32": split-bf16 tcgen05 (fp32-accurate); "bf16": bf16 tcgen05; "fp32_ffma": CUDA-core fp32
+        self.precision = "fp32"       # "fp32": split-f16 tcgen05 (fp32-accurate); "bf16": bf16 tcgen05; "fp32_ffma": CUDA-core fp32
         self._engine: Optional[Engine] = None
         self.decoder._engine_provider = self._get_engine
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_engine())
