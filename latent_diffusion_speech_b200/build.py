@@ -35,17 +35,24 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug_knobs: bool = False) -> str:
+    """debug_knobs=True builds liblds_b200_dbg.so with -DLDS_DEBUG_KNOBS (timing experiments that skip stores / epilogues;
+    wrong results by construction — never the product library; load it with LDS_B200_LIB=...)."""
+    if debug_knobs:
+        return _build(os.path.join(HERE, "liblds_b200_dbg.so"), os.path.join(HERE, "build", "dbg"), ["-DLDS_DEBUG_KNOBS"], verbose)
     if not force and not _stale():
         return LIB_PATH
+    return _build(LIB_PATH, os.path.join(HERE, "build"), [], verbose)
+
+
+def _build(lib_path: str, objdir: str, extra: list, verbose: bool) -> str:
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -54,12 +61,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out.decode()))
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    link = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout.decode())
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, debug_knobs="--debug-knobs" in sys.argv))

@@ -689,7 +689,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     te.bar0 = epi_bar_base + 8u * (uint32_t)((warp - 2) * MAX_EPI_BUFS);
     te.q = te.pq = 0u;
     te.p_item = cid; te.p_c = part;
-    if (p.tma_epi && p.R && lane == 0)            // residual blocks of the first nbuf - 1 chunks
+    if (p.tma_epi && p.R && lane == 0 && !p.dbg)   // residual blocks of the first nbuf - 1 chunks
       for (int i = 0; i + 1 < p.nbuf; ++i) tma_epi_prefetch(p, &mapR, te, (int)crank, quarter, part, ncl);
     int local = 0;
     for (int item = cid; item < p.total_items; item += ncl, ++local) {
@@ -710,7 +710,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       const uint32_t trow = tmem_base + buf * p.buf_stride + ((uint32_t)(quarter * 32) << 16);
 #ifdef LDS_DEBUG_KNOBS   // timing experiments only (results are wrong by construction); never compiled into the product library
-      if (!(p.dbg & 2))
+      if (p.dbg & 2) {
+      } else if (p.tma_epi && !(p.dbg & 1))
+        epilogue_tma(p, &mapC, &mapR, te, trow, item, (int)crank, quarter, part, lane, e.nvalid, ncl, reinterpret_cast<uint8_t*>(stage_base), stage_addr);
+      else
         epilogue_block<STAGED>(p, trow, nt * p.BN, e, part, (p.dbg & 1) != 0);
 #else
       if (p.tma_epi)

@@ -103,7 +103,7 @@ for name, (batches, rows, cin, N, taps, epi, calls) in SHAPES.items():
     rows_out.append(res)
     print(json.dumps(res), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-with open("gpurun_out/gemm_bounds.md", "w") as f:
+with open("gpurun_out/gemm_bounds%s.md" % (sys.argv[1] if len(sys.argv) > 1 else ""), "w") as f:
     f.write("| shape | M | N | K | calls/NFE | split: measured us | tensor bound | HBM bound | frac of bound | bf16: measured us | tensor bound | HBM bound | "
             "frac of bound | cuBLAS bf16 us | cuBLAS + epilogue bytes us | ours / that |\n|" + "---|" * 16 + "\n")
     for r in rows_out:
@@ -114,4 +114,5 @@ summary = dict(weighted_ms_bf16=tot[1], weighted_ms_split=tot[2], weighted_tflop
                weighted_tflops_split=tot["flops"] / tot[2] / 1e9)
 print(json.dumps(summary))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(dict(shapes=rows_out, summary=summary), open("gpurun_out/gemm_bench.json", "w"), indent=1)
+TAG = sys.argv[1] if len(sys.argv) > 1 else ""
+json.dump(dict(shapes=rows_out, summary=summary), open(f"gpurun_out/gemm_bench{TAG}.json", "w"), indent=1)
