@@ -88,20 +88,22 @@ struct TcParams {
 
 using namespace ptx;
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
-// bf16 mode only (the result is rounded to bf16, 2^-9 relative): erf by Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7
-// absolute, one MUFU.RCP + one MUFU.EX2 + 9 FMA-class instructions instead of the ~30 of erff — the GEGLU epilogue of the
-// bf16 GEMMs is bound by exactly this arithmetic (short main loops).  Split mode keeps erff.
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erfc(z) ~ t P(t) exp(-z^2), t = 1 / (1 + 0.39 z), P of degree 5 in t (a minimax refit
+// of the Abramowitz-Stegun 7.1.26 form with one more term: approximation error 8.3e-9 absolute).  One MUFU.RCP + one MUFU.EX2 + 11
+// FMA-class instructions instead of the ~27 of erff (whose branch-free form costs nine FSELs per element) — the GEGLU epilogue is
+// bound by exactly this arithmetic.  Evaluated in fp32 the result is within 4e-7 absolute of the exact GELU (torch's own fp32
+// F.gelu: 1.2e-6), tests/test_gpu_kernels.py::test_tc_gemm_geglu_and_output_kinds; used in both precision modes.
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));             // bare MUFU.RCP / MUFU.EX2 (1-2 ulp): the result is rounded to bf16
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
+  const float t = rcp_approx(fmaf(0.39f, z, 1.f));
+  float poly = fmaf(-0.22753774338131172f, t, 0.8866668986234079f);
+  poly = fmaf(poly, t, -0.6354043903488646f);
+  poly = fmaf(poly, t, 0.6495627199979991f);
+  poly = fmaf(poly, t, 0.09138708187290995f);
+  poly = fmaf(poly, t, 0.23532543152903582f);
   const float e = poly * t * ex2_approx_ftz(-z * z * 1.4426950408889634f);    // 1 - erf(|x|/sqrt2)
   const float one_plus_erf = x >= 0.f ? 2.f - e : e;                    // 1 + erf(x/sqrt2)
   return 0.5f * x * one_plus_erf;
@@ -329,7 +331,7 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, uint32_t trow,
       acc_finish32(p, trow + grp * 128 + 64 + c * 32, g);
       if (p.bias) { add_bias32(v, p.bias + col_v); add_bias32(g, p.bias + col_g); }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= STAGED ? gelu_erf(g[i]) : gelu_fast(g[i]);
+      for (int i = 0; i < 32; ++i) v[i] *= gelu_fast(g[i]);
       if (!staged) {
         if (!skip_store && row_ok) {
           if (rrow) {
@@ -969,9 +971,22 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   p.tma_epi = (a.out_kind == 0 && a.epilogue != EPI_GEGLU && (!a.R || a.r_div == 1) && a.c_ld % 4 == 0 && (!a.R || a.r_ld % 4 == 0) &&
                aligned16 && knobs().tma_epi) ? 1 : 0;
   // (three tiles per warp with shallower operand rings, and an L2 prefetch of the residual blocks at tile start, measured the
-  // same as two tiles: 115.1-116.0 k frames/s for all four combinations, GPU call 26 of round 2)
+  // same as two tiles: 115.1-116.0 k frames/s for all four combinations, GPU call 26 of round 2.  Also measured and rejected,
+  // profiles/r02_gemm_experiments_call133.md: an L2 prefetch stream of the A operand 4 / 8 K blocks ahead of the ring loads
+  // (cp.async.bulk.prefetch.tensor) — 8-90 % SLOWER per shape: the main loop is bound by L2 -> SM throughput, not latency, and
+  // the prefetches compete for it; A ring of 4 instead of 6 slots: +2 %; the staged epilogue instead of TMA for long K: +5 %.)
   p.nbuf = split ? 2 : 3;
   p.na = (split || !p.tma_epi) ? 6 : 4;
+#ifdef LDS_DEBUG_KNOBS
+  {
+    static const int e_na = getenv("LDS_TC_NA") ? atoi(getenv("LDS_TC_NA")) : 0,
+                     e_nbuf = getenv("LDS_TC_NBUF") ? atoi(getenv("LDS_TC_NBUF")) : 0,
+                     e_maxkb = getenv("LDS_TC_TMAEPI_MAXKB") ? atoi(getenv("LDS_TC_TMAEPI_MAXKB")) : 1 << 30;
+    if (a.taps * (a.cin / TBK) > e_maxkb) p.tma_epi = 0;
+    if (e_nbuf) p.nbuf = e_nbuf;
+    if (e_na) p.na = e_na;
+  }
+#endif
   const int stage_bytes = p.tma_epi ? N_EPI_WARPS * p.nbuf * STAGE_BYTES : (split ? N_EPI_WARPS * STAGE_BYTES : 0);
   p.nw = (SMEM_BUDGET - stage_bytes - p.na * A_SLOT_BYTES) / p.w_slot_bytes;
   if (p.nw > MAX_SLOTS) p.nw = MAX_SLOTS;
