@@ -340,6 +340,75 @@ def vocoder_leg(dev, B: int = 16, T: int = 864) -> dict:
     return out
 
 
+def units_leg(dev, B: int = 8, L: int = 3000) -> dict:
+    """the units front-end at whisper-large-v3 size (32 layers x 1280 channels x 20 heads, random init) —
+    B x 30 s of 16 kHz audio -> log-mel (csrc/units.cu) -> AudioEncoder on the tcgen05 kernels -> units [B, 1500, 1280] -> nearest
+    alignment to the mel frame grid (2584 frames).  Context: the oracle port of the reference encoder as PyTorch eager dispatches it
+    on the same GPU (fp32 with TF32 off; autocast bf16)."""
+    import torch
+    from latent_diffusion_speech_b200 import units as UN
+    d = UN.LARGE_V3
+    torch.manual_seed(1234)
+    enc = UN.AudioEncoder(d.n_mels, d.n_audio_state, d.n_audio_head, d.n_audio_layer).eval().to(dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    tt = torch.arange(L * UN.HOP_LENGTH, device=dev, dtype=torch.float32) / 16000.0
+    f0 = 100.0 + 80.0 * torch.rand(B, 1, generator=g, device=dev)                 # synthetic "speech": harmonics under a slow envelope + noise
+    audio = sum((0.6 ** h) * torch.sin(2 * 3.14159265 * (h + 1) * f0 * tt) for h in range(6)) * (0.5 + 0.5 * torch.sin(2 * 3.14159265 * 1.3 * tt)) ** 2
+    audio = (0.3 * audio + 1e-3 * torch.randn(B, tt.numel(), generator=g, device=dev)).clamp(-1, 1).contiguous()
+    T = (L - 1) // 2 + 1
+    n_align = int(T * 320 / 16000 * FRAME_RATE)
+
+    def timed(fn, n=2, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, r
+
+    out = {"workload": f"whisper-large-v3 AudioEncoder (32 x 1280 x 20 heads, random init), B={B} x 30 s audio -> {T} units each -> "
+                       f"{n_align} aligned frames", "unit": "units/s (encoder frames, 50 per second of audio)"}
+    ms_mel, mel = timed(lambda: UN.log_mel_spectrogram(audio, n_mels=d.n_mels))
+    out["log_mel_ms"] = ms_mel
+    for prec in ("fp32", "bf16"):
+        enc.set_precision(prec)
+        ms, units = timed(lambda: enc(mel))
+        fl = enc._engine.last_flops
+        out[prec] = {"ms_per_step": ms, "value": B * T / (ms * 1e-3), "tflops": fl / (ms * 1e-3) / 1e12, "launches_per_step": None,
+                     "rtf": (ms * 1e-3) / (B * L * UN.HOP_LENGTH / 16000.0), "finite": bool(torch.isfinite(units).all()),
+                     "arithmetic": "split-f16 tcgen05 (fp32-accurate, 3 MMAs per product)" if prec == "fp32" else "bf16 tcgen05"}
+        n0 = enc._engine.kernel_launches
+        enc(mel)
+        out[prec]["launches_per_step"] = enc._engine.kernel_launches - n0
+    ms_al, _ = timed(lambda: UN.units_forced_alignment(units, n_frames=n_align))
+    out["align_ms"] = ms_al
+    out["flops_per_unit"] = fl / (B * T)
+    enc._invalidate()
+    from oracle import units_oracle as UO           # baseline leg only: the reference encoder restated, as PyTorch eager runs it
+    sd = {k: v.detach() for k, v in enc.state_dict().items()}
+    eager = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            ms, _ = timed(lambda: UO.audio_encoder(sd, d.n_audio_head, mel), n=1)
+            eager["fp32_ieee"] = {"ms_per_step": ms, "value": B * T / (ms * 1e-3)}
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ms, _ = timed(lambda: UO.audio_encoder(sd, d.n_audio_head, mel), n=1)
+            eager["autocast_bf16"] = {"ms_per_step": ms, "value": B * T / (ms * 1e-3)}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["gpu_eager_baseline"] = dict(eager, kind="port (oracle/units_oracle.py: the reference AudioEncoder restated; the reference "
+                                                 "module itself hard-codes .to('cuda') and needs no port on a GPU box, but is not staged)")
+    del enc, sd, mel, units, audio
+    torch.cuda.empty_cache()
+    return out
+
+
 def strong_leg(dev, world: int, rank: int, steps: int) -> dict:
     """BASELINE configs[2]: global batch 512 x T=864, bf16 mode, UniPC 10 NFE, split 512/N across the ranks (strong scaling) through
     distributed.sharded_infer; inputs and noise are seeded PER UTTERANCE (global index), so the gathered mel is bit-identical at
@@ -561,6 +630,12 @@ def run_ours(args):
                 vocoder = vocoder_leg(dev)
             except Exception as ex:
                 vocoder = {"error": repr(ex)[:300]}
+        units_fe = None
+        if world == 1 and not args.no_units:
+            try:
+                units_fe = units_leg(dev)
+            except Exception as ex:
+                units_fe = {"error": repr(ex)[:300]}
         line = {
             "metric": "mel_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -579,6 +654,7 @@ def run_ours(args):
             "tf32_tflops_measured": tf32,
             "strong": strong,
             "vocoder": vocoder,
+            "units_frontend": units_fe,
             "kernel_classes": classes,
             "model_tflops_per_s": B * world * nfe * flops_per_utt_nfe(T) / (ms_step * 1e-3) / 1e12,
             "workspace_bytes": workspace_bytes,
@@ -601,6 +677,7 @@ def main():
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-vocoder", action="store_true")
+    ap.add_argument("--no-units", action="store_true")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:   # convenience: self-launch one rank per GPU
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

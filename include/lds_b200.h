@@ -281,6 +281,45 @@ LDS_API int64_t lds_vocoder_launches(const lds_vocoder* v);
 LDS_API double lds_vocoder_last_flops(const lds_vocoder* v);   /* algorithmic FLOPs of the last lds_vocode call */
 LDS_API int64_t lds_vocoder_workspace_bytes(const lds_vocoder* v);
 
+/* ---- Units front-end: audio -> Whisper encoder units ---------------------------------------------
+ * The step before the sampler: Units_Encoder.encode -> WhisperLargeV3.__call__ (tools/tools.py:77-126) = log_mel_spectrogram
+ * (encoder/whisper/audio.py:60-80) + AudioEncoder.forward (encoder/whisper/model.py:112-131), then units_forced_alignment
+ * (tools/tools.py:193-223) onto the mel frame grid.  The configuration mirrors ModelDimensions' audio fields (model.py:11-21);
+ * weights are AudioEncoder's state_dict ("conv1.weight", "blocks.7.attn.query.bias", "blocks.7.mlp.2.weight", "ln_post.weight", ...;
+ * fp32, or the fp16 the whisper checkpoints are stored in).  precision: LDS_PREC_FP32 (split-f16 tensor-core GEMMs, fp32-accurate)
+ * or LDS_PREC_BF16.  Same ownership / stream / error conventions as above; messages through lds_units_last_error().
+ * lds_units_encode grows its workspace on demand (that call then synchronises). */
+typedef struct {
+  int32_t n_mels;        /* 128 for large-v3 (multiple of 64) */
+  int32_t n_state;       /* n_audio_state (1280) */
+  int32_t n_head;        /* n_audio_head (20); head dim n_state / n_head in {32, 48, 64} */
+  int32_t n_layer;       /* n_audio_layer (32) */
+  int32_t precision;     /* lds_precision: LDS_PREC_FP32 or LDS_PREC_BF16 */
+} lds_units_config;
+typedef struct lds_units lds_units;
+LDS_API const char* lds_units_last_error(void);
+LDS_API int lds_units_create(const lds_units_config* cfg, int device, lds_units** out);      /* AudioEncoder.__init__ (model.py:113-118) */
+LDS_API void lds_units_destroy(lds_units* u);
+LDS_API int lds_units_load_weight(lds_units* u, const char* key, const void* data, const int64_t* shape, int ndim, int dtype);
+LDS_API int lds_units_finalize(lds_units* u);                 /* model.load_state_dict (tools/tools.py:118) + repacking into operand planes */
+/* units[B, T, n_state] = AudioEncoder(mel[B, n_mels, L]), T = lds_units_out_frames(L) = (L - 1) / 2 + 1 (model.py:120-131).
+ * pos_TC: device [T, n_state] = sinusoids(T, n_state) (model.py:32-38; computed by the host, it depends on T only). */
+LDS_API int lds_units_encode(lds_units* u, const float* mel_BML, int B, int L, const float* pos_TC, float* out_BTC, void* stream);
+LDS_API int lds_units_out_frames(int L);
+LDS_API int64_t lds_units_launches(const lds_units* u);
+LDS_API double lds_units_last_flops(const lds_units* u);      /* algorithmic FLOPs of the last lds_units_encode call */
+LDS_API int64_t lds_units_workspace_bytes(const lds_units* u);
+/* mel[B, n_mels, L / 160] = log_mel_spectrogram(audio[B, L]) (audio.py:60-80): hann window 400, hop 160, centre / reflect padding,
+ * the last STFT frame dropped, |.|^2, filters[n_mels, 201] (audio.py:54-58), log10(max(., 1e-10)), max(., global max - 8), (. + 4) / 4.
+ * The DFT is evaluated directly with fp64 accumulation.  L > 200; scratch: one float on the device. */
+LDS_API int lds_units_log_mel(const float* audio_BL, int B, int L, const float* filters, int n_mels, float* mel_out, float* scratch,
+                      void* stream);
+/* out[b * out_per_batch + i, :] = table[b * in_per_batch + idx[i], :] (rows of C floats, C % 4 == 0; idx: device int64 [out_per_batch]).
+ * units_forced_alignment 'nearest' / 'left' (tools/tools.py:193-223; idx = the source frame of every output frame, in_per_batch = input
+ * frames) and EuclideanCodebook.dequantize / F.embedding (quantize/kmeans_codebook.py:29-31; n_batches = 1, in_per_batch = 0). */
+LDS_API int lds_units_gather_rows(const float* table, const int64_t* idx, int64_t n_batches, int64_t out_per_batch, int64_t in_per_batch,
+                          int C, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "liblds_b200.so")
-SOURCES = ["lds_api.cu", "gemm_f32.cu", "gemm_tc.cu", "attention_f32.cu", "attention_tc.cu", "norm.cu", "solver.cu", "vocoder.cu"]
+SOURCES = ["lds_api.cu", "gemm_f32.cu", "gemm_tc.cu", "attention_f32.cu", "attention_tc.cu", "norm.cu", "solver.cu", "vocoder.cu", "units.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

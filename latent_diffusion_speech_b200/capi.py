@@ -32,6 +32,9 @@ EXPORTS = [
     "lds_op_pndm_update", "lds_op_q_sample", "lds_op_cast_gather", "lds_op_transpose", "lds_op_div_copy",
     "lds_vocoder_last_error", "lds_vocoder_create", "lds_vocoder_destroy", "lds_vocoder_load_weight", "lds_vocoder_finalize",
     "lds_vocode", "lds_vocoder_hop", "lds_vocoder_launches", "lds_vocoder_last_flops", "lds_vocoder_workspace_bytes",
+    "lds_units_last_error", "lds_units_create", "lds_units_destroy", "lds_units_load_weight", "lds_units_finalize", "lds_units_encode",
+    "lds_units_out_frames", "lds_units_launches", "lds_units_last_flops", "lds_units_workspace_bytes", "lds_units_log_mel",
+    "lds_units_gather_rows",
 ]
 
 
@@ -118,6 +121,18 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "lds_vocoder_launches": (C.c_int64, [vp]),
         "lds_vocoder_last_flops": (C.c_double, [vp]),
         "lds_vocoder_workspace_bytes": (C.c_int64, [vp]),
+        "lds_units_last_error": (C.c_char_p, []),
+        "lds_units_create": (i32, [vp, i32, C.POINTER(vp)]),
+        "lds_units_destroy": (None, [vp]),
+        "lds_units_load_weight": (i32, [vp, C.c_char_p, vp, i64p, i32, i32]),
+        "lds_units_finalize": (i32, [vp]),
+        "lds_units_encode": (i32, [vp, vp, i32, i32, vp, vp, vp]),
+        "lds_units_out_frames": (i32, [i32]),
+        "lds_units_launches": (C.c_int64, [vp]),
+        "lds_units_last_flops": (C.c_double, [vp]),
+        "lds_units_workspace_bytes": (C.c_int64, [vp]),
+        "lds_units_log_mel": (i32, [vp, i32, i32, vp, i32, vp, vp, vp]),
+        "lds_units_gather_rows": (i32, [vp, vp, i64, i64, i64, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)           # AttributeError if the symbol is not exported

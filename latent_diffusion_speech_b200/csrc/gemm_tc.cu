@@ -383,6 +383,9 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, uint32_t trow,
       if (p.epilogue == EPI_SILU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+      } else if (p.epilogue == EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
       }
       if (region == 2) {                  // V^T: straight from the registers
         if (!skip_store && e.lane < e.nvalid) store_vt32(p, e.grow0 + e.lane, col, v);
@@ -483,6 +486,9 @@ __device__ __forceinline__ void epilogue_tma(const TcParams& p, const CUtensorMa
     if (p.epilogue == EPI_SILU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+    } else if (p.epilogue == EPI_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
     }
     float4* row = reinterpret_cast<float4*>(smem_gen + (buf - smem_gen_addr) + lane * 128);
 #pragma unroll

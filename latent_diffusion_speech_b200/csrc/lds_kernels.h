@@ -57,7 +57,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-enum Epilogue : int { EPI_NONE = 0, EPI_SILU = 1, EPI_GEGLU = 2 };
+enum Epilogue : int { EPI_NONE = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_GELU = 3 };   // EPI_GELU: exact-erf GELU (tensor-core path only)
 
 // C[M,N] = epi( A (*) W^T + bias ) + R.
 //  A: source rows [*, a_ld]; logical K = taps * cin.  taps==1: plain GEMM row m <- source row m.

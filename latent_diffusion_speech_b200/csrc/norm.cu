@@ -781,9 +781,59 @@ cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, 
   return launch_gnc_flags<3>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
 }
 
+// Wide rows (512 < C <= 2048; the Whisper encoder's 1280): one warp per row, the row held in registers (up to 16 float4 per lane),
+// two-pass statistics (mean, then centred sum of squares) like the narrow kernels, gamma / beta read through the read-only path.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, int rows, int C,
+                                                             float* __restrict__ y, __nv_bfloat16* __restrict__ yb, int parts) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int V = C >> 2;
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * C);
+  float4 v[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (lane + 32 * i < V) v[i] = __ldg(src + lane + 32 * i);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (lane + 32 * i < V) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  sum = warp_sum(sum);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (lane + 32 * i < V) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  sq = warp_sum(sq);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < V) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q), be = __ldg(reinterpret_cast<const float4*>(beta) + q);
+      const float4 o = make_float4((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y,
+                                   (v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
+      if (yb) store_planes4(yb + (size_t)row * (parts * C), q * 4, C, parts, o.x, o.y, o.z, o.w);
+      else reinterpret_cast<float4*>(y + (size_t)row * C)[q] = o;
+    }
+  }
+}
+
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int C, float* y,
                              __nv_bfloat16* yb, int parts, cudaStream_t s) {
-  if (C % 4 || C > 512) return cudaErrorInvalidValue;
+  if (C % 4 || C > 2048) return cudaErrorInvalidValue;
+  if (C > 512) {
+    const dim3 g((rows + 7) / 8), b(256);
+    if (C <= 1024) return launch_pdl(layernorm_wide_kernel<8>, g, b, 0, s, 1, x, gamma, beta, eps, rows, C, y, yb, parts);
+    if (C <= 1536) return launch_pdl(layernorm_wide_kernel<12>, g, b, 0, s, 1, x, gamma, beta, eps, rows, C, y, yb, parts);
+    return launch_pdl(layernorm_wide_kernel<16>, g, b, 0, s, 1, x, gamma, beta, eps, rows, C, y, yb, parts);
+  }
   if (yb && (parts < 1 || parts > 3)) return cudaErrorInvalidValue;
   if (C == 256 || C == 384 || C == 512) {        // the denoiser's widths: specialised kernel
     const int pk = yb ? parts : 0;
