@@ -567,7 +567,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const bool split = p.parts == 2;               // split-f16: planes h1, h2 of both operands, three products per K block
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp runs the producer loop in lock step (uniform operands); one elected lane issues each TMA load (tc_ptx.cuh)
       int sa = 0, sw = 0;                        // next slot of each ring
       uint32_t pha = 0, phw = 0;
       const int w_row = (int)crank * (p.BN >> 1);
@@ -578,20 +578,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int blk_b[4], blk_t[4];
       auto load_a = [&](int col, int row, int b) {
         mbar_wait(a_empty(sa), pha ^ 1u);
-        if (leader) mbar_expect_tx(a_full(sa), 2 * A_SLOT_BYTES);
+        if (leader) mbar_expect_tx_elect(a_full(sa), 2 * A_SLOT_BYTES);
         const uint32_t dst = a_ring + sa * A_SLOT_BYTES, bar = mapa_u32(a_full(sa), 0);
         if (p.blk_tiling) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) tma_load_3d_pair(dst + q * (A_SLOT_BYTES / 4), &mapA, bar, col, blk_t[q] + row, blk_b[q]);
+          for (int q = 0; q < 4; ++q) tma_load_3d_pair_elect(dst + q * (A_SLOT_BYTES / 4), &mapA, bar, col, blk_t[q] + row, blk_b[q]);
         } else {
-          tma_load_3d_pair(dst, &mapA, bar, col, row, b);
+          tma_load_3d_pair_elect(dst, &mapA, bar, col, row, b);
         }
         if (++sa == p.na) { sa = 0; pha ^= 1u; }
       };
       auto load_w = [&](int col, int n0) {
         mbar_wait(w_empty(sw), phw ^ 1u);
-        if (leader) mbar_expect_tx(w_full(sw), 2 * p.w_slot_bytes);
-        tma_load_2d_pair(w_ring + sw * p.w_slot_bytes, &mapW, mapa_u32(w_full(sw), 0), col, n0 + w_row);
+        if (leader) mbar_expect_tx_elect(w_full(sw), 2 * p.w_slot_bytes);
+        tma_load_2d_pair_elect(w_ring + sw * p.w_slot_bytes, &mapW, mapa_u32(w_full(sw), 0), col, n0 + w_row);
         if (++sw == p.nw) { sw = 0; phw ^= 1u; }
       };
       for (int item = cid; item < p.total_items; item += ncl) {
