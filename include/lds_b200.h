@@ -206,6 +206,12 @@ LDS_API int lds_op_split_cast(const float* in, void* out_bf16, int64_t rows, int
 LDS_API int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, int parts, const void* w_bf16, int N, int taps,
                    const float* bias, const float* R, int r_ld, int r_div, void* C, int c_ld, int out_kind,
                    int epilogue, void* stream);
+/* The dilated form of lds_op_gemm_tc: a stride-1 'same' convolution along `rows` with an odd number of taps <= 11 and dilation `dil`
+ * (tap t reads row r + (t - (taps-1)/2) * dil, zero outside the utterance) — the ResBlock convolutions of the HiFi-VAEGAN generator
+ * (encoder/hifi_vaegan/modules/models.py:166-184).  epilogue 0 none, 1 SiLU, 3 exact-erf GELU, 4 leaky_relu(act_slope). */
+LDS_API int lds_op_conv1d_tc(const void* A_planes, int batches, int rows, int cin, int parts, const void* w_planes, int N, int taps,
+                     int dil, const float* bias, const float* R, int r_ld, void* C, int c_ld, int out_kind, int epilogue,
+                     float act_slope, void* stream);
 /* Fused QKV projection + tcgen05 flash attention (attention_processor.py:1012-1034) on operand planes:
  *   x planes [B*T][parts*C] -> q/k/v^T scratch (layouts in lds_kernels.h) -> out planes [B*T][parts*C].  parts 1 (bf16) or 2 (split-f16:
  *   Q, K, V^T and the probabilities P are each two fp16 planes, every product is evaluated as three plane products).

@@ -27,7 +27,7 @@ EXPORTS = [
     "lds_num_steps", "lds_workspace_bytes", "lds_kernel_launches", "lds_set_profiling", "lds_profile_num_classes",
     "lds_profile_class_name", "lds_profile_class_ms", "lds_profile_class_launches", "lds_profile_class_flops",
     "lds_profile_class_bytes", "lds_op_gemm", "lds_op_attention", "lds_op_groupnorm", "lds_op_groupnorm_fused", "lds_op_groupnorm_cluster", "lds_op_layernorm",
-    "lds_op_split_cast", "lds_op_gemm_tc", "lds_op_qkv_attention_tc",
+    "lds_op_split_cast", "lds_op_gemm_tc", "lds_op_conv1d_tc", "lds_op_qkv_attention_tc",
     "lds_op_x0_pred", "lds_op_dpm_update", "lds_op_unipc_predict", "lds_op_unipc_correct", "lds_op_ddpm_step", "lds_op_ddim_step",
     "lds_op_pndm_update", "lds_op_q_sample", "lds_op_cast_gather", "lds_op_transpose", "lds_op_div_copy",
     "lds_vocoder_last_error", "lds_vocoder_create", "lds_vocoder_destroy", "lds_vocoder_load_weight", "lds_vocoder_finalize",
@@ -99,6 +99,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "lds_op_layernorm": (i32, [vp, vp, vp, C.c_float, i32, i32, vp, vp]),
         "lds_op_split_cast": (i32, [vp, vp, C.c_int64, i32, i32, vp]),
         "lds_op_gemm_tc": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp]),
+        "lds_op_conv1d_tc": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, i32, f32, vp]),
         "lds_op_qkv_attention_tc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "lds_op_x0_pred": (i32, [vp, vp, f32, f32, vp, i64, vp]),
         "lds_op_dpm_update": (i32, [vp, vp, vp, f32, f32, f32, f32, i32, i64, vp]),

@@ -70,7 +70,7 @@ constexpr int MAX_EPI_BUFS = 4;                       // TMA epilogue buffers pe
 struct TcParams {
   int rows, batches, tiles_per_batch, m_tiles, n_tiles, total_items;   // A: [batches][rows][parts*cin]; item = (M-tile group, N tile)
   int blk_tiling, blks_per_batch, total_blks;   // flat tiling of batched convolutions in 32-row blocks (rows % 32 == 0)
-  int cin, taps, pad, parts;
+  int cin, taps, pad, dil, parts;
   int BN, na, nw, w_slot_bytes;         // ring depths (A slots, W slots)
   int nkb, kb_per_tap;                  // K blocks of TBK per plane (all taps) / per tap
   int N;
@@ -79,6 +79,7 @@ struct TcParams {
   void* C; int c_ld; int out_kind;      // 0 fp32, 1 bf16, 2 split bf16 (3 planes of c_ld/3 columns), 3 attention operands
   int epilogue, dbg;
   float out_scale;                      // accumulator scale (split-f16: 1 / (scale_A * scale_W)); applied before bias / activation
+  float act_slope;                      // EPI_LRELU
   int small_off;                        // split-f16: TMEM column offset of the "small" accumulator (h1*w2 + h2*w1) behind the main one; 0 = none
   int n_buf, buf_stride;                // accumulator buffers in TMEM (2: epilogue of tile i overlaps the main loop of tile i+1) and their stride
   int att_parts;                        // planes of the attention operands (out_kind 3)
@@ -386,6 +387,9 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, uint32_t trow,
       } else if (p.epilogue == EPI_GELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+      } else if (p.epilogue == EPI_LRELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.act_slope;
       }
       if (region == 2) {                  // V^T: straight from the registers
         if (!skip_store && e.lane < e.nvalid) store_vt32(p, e.grow0 + e.lane, col, v);
@@ -489,6 +493,9 @@ __device__ __forceinline__ void epilogue_tma(const TcParams& p, const CUtensorMa
     } else if (p.epilogue == EPI_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+    } else if (p.epilogue == EPI_LRELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.act_slope;
     }
     float4* row = reinterpret_cast<float4*>(smem_gen + (buf - smem_gen_addr) + lane * 128);
 #pragma unroll
@@ -610,7 +617,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int n0 = nt * p.BN;
         int tap = 0, cb = 0;
         for (int kb = 0; kb < p.nkb; ++kb) {
-          const int row = t0 - p.pad + tap, acol = cb * TBK, wcol = tap * p.parts * p.cin + cb * TBK;
+          const int row = t0 - p.pad + tap * p.dil, acol = cb * TBK, wcol = tap * p.parts * p.cin + cb * TBK;
           if (split) {                           // need order of the MMA warp: A_h1, W_h2 | A_h2, W_h1
             load_a(acol, row, b);
             load_w(wcol + p.cin, n0);
@@ -937,7 +944,7 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (a.batches <= 0 || a.rows <= 0 || a.N <= 0) return cudaSuccess;
   const bool split = a.a_parts == 2 && a.w_parts == 2 && a.n_pairs == 3;      // split-f16 (fp32-accurate)
   const bool plain = a.a_parts == 1 && a.w_parts == 1 && a.n_pairs == 1;
-  if (a.cin % 64 || a.N % 128 || (a.taps != 1 && a.taps != 3) || (!split && !plain) || (a.out_kind != 3 && a.c_ld % 8) ||
+  if (a.cin % 64 || a.N % 128 || a.taps < 1 || a.taps > 11 || a.taps % 2 == 0 || a.dil < 1 || (!split && !plain) || (a.out_kind != 3 && a.c_ld % 8) ||
       (a.R && a.r_ld % 4) || a.r_div < 1)
     return cudaErrorInvalidValue;
   if (a.out_kind == 3 && (!a.q_out || !a.k_out || !a.vt_out || a.att_T < 1 || a.att_dpad % 32 || a.N != 3 * a.att_H * a.att_dpad ||
@@ -1008,7 +1015,7 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   p.rows = a.rows; p.batches = a.batches; p.tiles_per_batch = (a.rows + TBM - 1) / TBM;
   p.n_tiles = a.N / p.BN; p.total_items = p.n_tiles * ((p.m_tiles + csize - 1) / csize);
-  p.cin = a.cin; p.taps = a.taps; p.pad = a.taps == 3 ? 1 : 0; p.parts = a.a_parts;
+  p.cin = a.cin; p.taps = a.taps; p.dil = a.dil; p.pad = (a.taps - 1) / 2 * a.dil; p.parts = a.a_parts;
   p.kb_per_tap = a.cin / TBK; p.nkb = a.taps * p.kb_per_tap;
   p.N = a.N; p.bias = a.bias; p.R = a.R; p.r_ld = a.r_ld; p.r_div = a.r_div;
   p.C = a.C; p.c_ld = a.c_ld; p.out_kind = a.out_kind; p.epilogue = a.epilogue;
@@ -1017,7 +1024,7 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
 #else
   p.dbg = 0;
 #endif
-  p.out_scale = a.out_scale; p.att_parts = a.att_parts;
+  p.out_scale = a.out_scale; p.act_slope = a.act_slope; p.att_parts = a.att_parts;
   // TMEM: main accumulator (BN columns) [+ small accumulator (BN columns) in split-f16 mode] per buffer; two buffers when they fit
   p.small_off = split ? p.BN : 0;
   p.buf_stride = split ? 2 * p.BN : p.BN;

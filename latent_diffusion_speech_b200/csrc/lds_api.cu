@@ -1380,6 +1380,18 @@ int lds_op_gemm_tc(const void* A_bf16, int batches, int rows, int cin, int parts
   return op_status(lds::launch_gemm_tc(g, (cudaStream_t)stream), "lds_op_gemm_tc");
 }
 
+int lds_op_conv1d_tc(const void* A_planes, int batches, int rows, int cin, int parts, const void* w_planes, int N, int taps, int dil,
+                     const float* bias, const float* R, int r_ld, void* C, int c_ld, int out_kind, int epilogue, float act_slope,
+                     void* stream) {
+  if (!A_planes || !w_planes || !C || (parts != 1 && parts != 2)) return fail(LDS_ERR_INVALID, "lds_op_conv1d_tc: bad argument (parts must be 1 or 2)");
+  lds::TcGemmArgs g;
+  g.A = (const __nv_bfloat16*)A_planes; g.batches = batches; g.rows = rows; g.cin = cin;
+  g.W = (const __nv_bfloat16*)w_planes; g.N = N; g.taps = taps; g.dil = dil;
+  if (parts == 2) { lds::tc_set_split_pairs(g); g.out_scale = 1.f / (lds::PLANE_SCALE * lds::PLANE_SCALE); }
+  g.bias = bias; g.R = R; g.r_ld = r_ld; g.C = C; g.c_ld = c_ld; g.out_kind = out_kind; g.epilogue = epilogue; g.act_slope = act_slope;
+  return op_status(lds::launch_gemm_tc(g, (cudaStream_t)stream), "lds_op_conv1d_tc");
+}
+
 int lds_op_qkv_attention_tc(const void* x_planes, const void* w_qkv, int B, int T, int C, int H, int dpad, int parts,
                             void* q_scratch, void* k_scratch, void* vt_scratch, void* out_planes, void* stream) {
   if (!x_planes || !w_qkv || !q_scratch || !k_scratch || !vt_scratch || !out_planes || (parts != 1 && parts != 2) || H < 1 || C % H)

@@ -57,7 +57,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-enum Epilogue : int { EPI_NONE = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_GELU = 3 };   // EPI_GELU: exact-erf GELU (tensor-core path only)
+enum Epilogue : int { EPI_NONE = 0, EPI_SILU = 1, EPI_GEGLU = 2, EPI_GELU = 3, EPI_LRELU = 4 };   // EPI_GELU (exact-erf) / EPI_LRELU (slope act_slope): tensor-core path only
 
 // C[M,N] = epi( A (*) W^T + bias ) + R.
 //  A: source rows [*, a_ld]; logical K = taps * cin.  taps==1: plain GEMM row m <- source row m.
@@ -88,19 +88,21 @@ cudaError_t launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
 //  Split-f16 (fp32-accurate): parts = 2 (fp16 planes h1, h2 of the scaled operand) and the three products h1*w2, h2*w1 (into a
 //  "small" TMEM accumulator) and h1*w1 (into the main one); the epilogue adds the two and multiplies by out_scale =
 //  1 / (scale_A * scale_W) — three tensor-core products per logical product.
-//  taps==3: k=3, stride-1, pad-1 convolution along `rows` (TMA out-of-bounds fill = zero padding).
+//  taps in {3, 5, 7, 9, 11}: stride-1 'same' convolution along `rows` with dilation `dil` (tap t reads row r + (t - (taps-1)/2) * dil;
+//  TMA out-of-bounds fill = zero padding).
 //  out_kind: 0 fp32 [*, c_ld], 1 bf16 [*, c_ld], 2 three bf16 planes of c_ld/3 columns each,
 //            3 attention operands of a fused QKV projection with N = 3*H*dpad columns ([q | k | v], head dim padded
 //              to dpad): q_out/k_out planes [rows][parts][H*dpad], vt_out planes [B][parts][H][dpad][T_pad] (V transposed,
 //              keys contiguous) — the layouts attention_tc.cu loads with TMA.
 struct TcGemmArgs {
   const __nv_bfloat16* A = nullptr; int batches = 1, rows = 0, cin = 0, a_parts = 1;
-  const __nv_bfloat16* W = nullptr; int N = 0, taps = 1, w_parts = 1;
+  const __nv_bfloat16* W = nullptr; int N = 0, taps = 1, w_parts = 1, dil = 1;
   int n_pairs = 1; int pair_a[6] = {0, 0, 0, 0, 0, 0}; int pair_w[6] = {0, 0, 0, 0, 0, 0};
   const float* bias = nullptr;
   const float* R = nullptr; int r_ld = 0, r_div = 1;
   void* C = nullptr; int c_ld = 0, out_kind = 0, epilogue = EPI_NONE;
   float out_scale = 1.f;                  // applied to the accumulator before bias / activation (split-f16: 1 / (scale_A * scale_W))
+  float act_slope = 0.f;                  // EPI_LRELU: negative-side slope
   __nv_bfloat16 *q_out = nullptr, *k_out = nullptr, *vt_out = nullptr; int att_T = 0, att_H = 0, att_dpad = 0, att_Tpad = 0;
   int att_parts = 1;                      // planes of the attention operands written by out_kind 3 (bf16: 1 or 3)
 };
@@ -121,6 +123,8 @@ inline void tc_set_split_pairs(TcGemmArgs& a) {   // h1*w2, h2*w1, h1*w1
 }
 // fp32 [rows, C] -> bf16 [rows, parts*C]: parts=1 plain rounding; parts=3 hi/mid/lo planes (x == hi+mid+lo to 24 bits)
 cudaError_t launch_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, cudaStream_t s);
+// the same with leaky_relu(x, slope) applied first (the pre-activation of the vocoder's dilated convolutions)
+cudaError_t launch_lrelu_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, float slope, cudaStream_t s);
 // Gathering casts for the two resampling convolutions (channels-last [B, t, C] fp32 -> bf16 planes):
 //  mode 1: nearest upsample to t_out frames, out [B, t_out, parts*C], src = min(floor(u*scale), t_in-1)   (resnet.py:157-160)
 //  mode 2: k=3 / stride-2 / pad-1 im2col, out [B, t_out, parts*3C] with element (p, tap, c) at p*3C + tap*C + c  (resnet.py:200)

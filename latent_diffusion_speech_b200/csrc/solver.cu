@@ -224,7 +224,8 @@ __global__ void spk_gather_kernel(const float* __restrict__ table, const int64_t
 }
 
 // fp32 -> bf16 planes; one thread per 4 consecutive channels
-__global__ void split_cast_kernel(const float4* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows, int C, int parts) {
+template <bool LRELU>
+__global__ void split_cast_kernel(const float4* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows, int C, int parts, float slope) {
   pdl_trigger();
   pdl_wait();
   const int V = C >> 2;
@@ -232,7 +233,11 @@ __global__ void split_cast_kernel(const float4* __restrict__ in, __nv_bfloat16* 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / V;
     const int c = (int)(i - row * V) * 4;
-    const float4 q = in[i];
+    float4 q = in[i];
+    if (LRELU) {
+      q.x = q.x > 0.f ? q.x : q.x * slope; q.y = q.y > 0.f ? q.y : q.y * slope;
+      q.z = q.z > 0.f ? q.z : q.z * slope; q.w = q.w > 0.f ? q.w : q.w * slope;
+    }
     store_planes4(out + row * (int64_t)(parts * C), c, C, parts, q.x, q.y, q.z, q.w);
   }
 }
@@ -341,7 +346,11 @@ cudaError_t launch_div_copy(const float* in, float* out, int64_t n, float diviso
 }
 cudaError_t launch_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, cudaStream_t s) {
   if (C % 4 || parts < 1 || parts > 3) return cudaErrorInvalidValue;
-  return launch_pdl(split_cast_kernel, dim3(grid_for(rows * (C / 4))), dim3(256), 0, s, 1, V4(in), out, rows, C, parts);
+  return launch_pdl(split_cast_kernel<false>, dim3(grid_for(rows * (C / 4))), dim3(256), 0, s, 1, V4(in), out, rows, C, parts, 1.f);
+}
+cudaError_t launch_lrelu_split_cast(const float* in, __nv_bfloat16* out, int64_t rows, int C, int parts, float slope, cudaStream_t s) {
+  if (C % 4 || parts < 1 || parts > 3) return cudaErrorInvalidValue;
+  return launch_pdl(split_cast_kernel<true>, dim3(grid_for(rows * (C / 4))), dim3(256), 0, s, 1, V4(in), out, rows, C, parts, slope);
 }
 cudaError_t launch_cast_gather(const float* in, __nv_bfloat16* out, int B, int t_in, int t_out, int C, int parts, int mode,
                                float scale, cudaStream_t s) {

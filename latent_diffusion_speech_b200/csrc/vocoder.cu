@@ -7,12 +7,16 @@
 //   encoder/hifi_vaegan/modules/models.py:161-221   ResBlock1 / ResBlock2 (dilated k in {3,7,11} convolutions with residuals)
 //   encoder/hifi_vaegan/hifi_vaegan.py:52-65        Hifi_VAEGAN.forward: [B,T,C] -> [B,C,T], remove_weight_norm, Generator
 //
-// Layout: channels-FIRST fp32 [B, C, L] (time contiguous) — the waveform-rate layers have 32-64 channels and up to 512 samples per
-// frame, so time is the long, coalescing axis.  Arithmetic: IEEE fp32 FFMA on the CUDA cores, register-blocked direct
-// convolution (8 output channels x 8 time steps per thread, input slab with its dilated halo and the [ci][tap][co] weight slab
-// staged in shared memory, leaky_relu applied once while staging).  Round-2 scope is a CORRECT, measured implementation; the
-// tensor-core form (the C >= 128 levels are 48 % of the FLOPs and fit gemm_tc's implicit-GEMM with a dilation term in the TMA
-// row coordinate) is the next step.
+// Two forms of the ResBlock convolutions:
+//   * levels whose channel count is a multiple of 128 (256 and 128 channels in the HiFi-GAN V1 layout: 48 % of the FLOPs) run on the
+//     tensor cores: channels-LAST fp32 [B*L, C] state, every dilated k in {3..11} convolution an implicit GEMM of gemm_tc.cu (tap t =
+//     the TMA row coordinate shifted by (t - (k-1)/2) * dilation, zero padding = TMA out-of-bounds fill, split-f16 operand planes:
+//     fp32-accurate at three tcgen05 products per logical product), leaky_relu fused into the operand cast / the first convolution's
+//     epilogue, bias + residual in the second one's;
+//   * the waveform-rate levels (64 / 32 channels, up to 512 samples per frame: time is the long, coalescing axis) and the transposed
+//     convolutions stay channels-FIRST fp32 [B, C, L] on the CUDA cores: IEEE FFMA, register-blocked direct convolution (8 output
+//     channels x 8 time steps per thread, input slab with its dilated halo and the [ci][tap][co] weight slab staged in shared memory,
+//     leaky_relu applied once while staging).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -26,8 +30,13 @@
 #include <vector>
 
 #include "../../include/lds_b200.h"
+#include "lds_kernels.h"
+#include "planes.cuh"
+#include "host_pack.h"
 
 namespace {
+
+using namespace lds;
 
 thread_local std::string g_voc_error;
 int vfail(int code, const char* fmt, ...) {
@@ -183,7 +192,23 @@ __global__ void voc_transpose_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
-struct ConvP { const float* w = nullptr; const float* b = nullptr; int cin = 0, cout = 0, k = 0; };
+struct ConvP { const float* w = nullptr; const float* b = nullptr; const __nv_bfloat16* wh = nullptr; int cin = 0, cout = 0, k = 0; };
+
+// resblock levels that run as implicit GEMMs on the tensor cores (gemm_tc: K blocks of 64 channels, N tiles of 128)
+inline bool tc_level(int ch) { return ch >= 128 && ch % 128 == 0; }
+
+// xs (+)= r over n floats: mode 0 xs = r ; 1 xs = xs + r ; 2 xs = (xs + r) / div     (mean over the resblocks, models.py:243-251)
+__global__ void voc_acc_kernel(float4* __restrict__ xs, const float4* __restrict__ r, int64_t n4, int mode, float div) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = r[i];
+    if (mode) {
+      const float4 o = xs[i];
+      a.x = o.x + a.x; a.y = o.y + a.y; a.z = o.z + a.z; a.w = o.w + a.w;
+      if (mode == 2) { a.x = __fdiv_rn(a.x, div); a.y = __fdiv_rn(a.y, div); a.z = __fdiv_rn(a.z, div); a.w = __fdiv_rn(a.w, div); }
+    }
+    xs[i] = a;
+  }
+}
 
 template <int KS>
 cudaError_t launch_conv_ks(const float* x, const ConvP& c, const float* res, float* y, int B, int L, int dil, int pad, float in_slope,
@@ -223,6 +248,8 @@ struct lds_vocoder {
   std::map<std::string, std::pair<std::vector<float>, std::vector<int64_t>>> raw;
   float* warena = nullptr;
   size_t warena_floats = 0;
+  __nv_bfloat16* wharena = nullptr;          // split-f16 operand planes of the tensor-core levels' resblock filters
+  float wscale = 1.f;
   ConvP conv_pre, conv_post;
   std::vector<ConvP> ups;
   std::vector<std::vector<ConvP>> rb1, rb2;      // per resblock: convs1 / convs2 (ResBlock2: rb1 = convs, rb2 empty)
@@ -277,6 +304,7 @@ void lds_vocoder_destroy(lds_vocoder* v) {
   cudaSetDevice(v->device);
   cudaDeviceSynchronize();
   if (v->warena) cudaFree(v->warena);
+  if (v->wharena) cudaFree(v->wharena);
   if (v->arena) cudaFree(v->arena);
   delete v;
 }
@@ -310,6 +338,18 @@ int lds_vocoder_finalize(lds_vocoder* v) {
     fix.emplace_back(slot, off);
   };
   int rc = LDS_OK;
+  // tensor-core levels: one power-of-two scale for their resblock filters (planes.cuh; lds_api.cu does the same for the denoiser)
+  PlanePacker pkh;
+  std::vector<std::pair<const __nv_bfloat16**, size_t>> fixh;
+  {
+    float wmax = 0.f;
+    for (const auto& kv : v->raw)
+      if (kv.first.rfind("resblocks.", 0) == 0 && kv.second.second.size() == 3)
+        for (float x : kv.second.first) wmax = std::max(wmax, std::fabs(x));
+    float sc = 4096.f;
+    while (sc > 1.f && wmax * sc >= 16384.f) sc *= 0.5f;
+    v->wscale = pkh.scale = sc;
+  }
   // Conv1d weight [cout, cin, k] -> [cin][k][cout];  ConvTranspose1d weight [cin, cout, k] -> [cin][k][cout]
   auto conv = [&](ConvP& p, const std::string& key, int cin, int cout, int k, bool transposed) -> bool {
     auto itw = v->raw.find(key + ".weight"), itb = v->raw.find(key + ".bias");
@@ -328,6 +368,13 @@ int lds_vocoder_finalize(lds_vocoder* v) {
     put(&p.w, t.data(), t.size());
     put(&p.b, itb->second.first.data(), (size_t)cout);
     p.cin = cin; p.cout = cout; p.k = k;
+    if (!transposed && key.rfind("resblocks.", 0) == 0 && tc_level(cin) && cin == cout) {   // [cout][tap][plane][cin] for gemm_tc
+      std::vector<float> tt((size_t)cout * k * cin);
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int kk = 0; kk < k; ++kk) tt[((size_t)co * k + kk) * cin + ci] = src[((size_t)co * cin + ci) * k + kk];
+      fixh.emplace_back(&p.wh, pkh.add(tt.data(), (size_t)cout * k, cin, 2));
+    }
     return true;
   };
   const int nrb = c.n_ups * c.n_kernels;
@@ -362,6 +409,12 @@ int lds_vocoder_finalize(lds_vocoder* v) {
   if (cudaMemcpy(v->warena, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
     return vfail(LDS_ERR_CUDA, "upload of the vocoder weights failed");
   for (auto& f : fix) *f.first = v->warena + f.second;
+  if (!pkh.host.empty()) {
+    if (cudaMalloc(&v->wharena, pkh.host.size() * sizeof(uint16_t)) != cudaSuccess ||
+        cudaMemcpy(v->wharena, pkh.host.data(), pkh.host.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+      return vfail(LDS_ERR_CUDA, "upload of the vocoder's tensor-core filters failed");
+    for (auto& f : fixh) *f.first = v->wharena + f.second;
+  }
   v->raw.clear();
   v->finalized = true;
   return LDS_OK;
@@ -382,13 +435,17 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
   const lds_vocoder_config& c = v->cfg;
   // workspace: z^T and conv_pre output, then per level: level input x, xs, and three scratch tensors of the level's size
   size_t need = (size_t)B * c.inter_channels * T + (size_t)B * c.upsample_initial_channel * T;
-  size_t lvl_max = 0;
+  size_t lvl_max = 0, tc_max = 0;
   {
     int ch = c.upsample_initial_channel;
     int64_t L = T;
-    for (int i = 0; i < c.n_ups; ++i) { ch /= 2; L *= c.upsample_rates[i]; lvl_max = std::max(lvl_max, (size_t)B * ch * (size_t)L); }
+    for (int i = 0; i < c.n_ups; ++i) {
+      ch /= 2; L *= c.upsample_rates[i];
+      lvl_max = std::max(lvl_max, (size_t)B * ch * (size_t)L);
+      if (tc_level(ch)) tc_max = std::max(tc_max, (size_t)B * ch * (size_t)L);
+    }
   }
-  need += 6 * (lvl_max + 64) + 1024;
+  need += 6 * (lvl_max + 64) + 4 * (tc_max + 64) + 1024;   // tensor-core levels: two channels-last fp32 tensors + two split-f16 plane buffers
   if (need > v->arena_cap) {           // grow-only; growing synchronises (work in flight may still use the old arena)
     if (cudaDeviceSynchronize() != cudaSuccess) return vfail(LDS_ERR_CUDA, "synchronize before workspace growth failed");
     if (v->arena) { cudaFree(v->arena); v->arena = nullptr; v->arena_cap = 0; }
@@ -401,6 +458,10 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
   float* pre = take((size_t)B * c.upsample_initial_channel * T);
   float* lv[6];
   for (int i = 0; i < 6; ++i) lv[i] = take(lvl_max);
+  float* x_cl = take(tc_max);
+  float* xs_cl = take(tc_max);
+  __nv_bfloat16* a_p = reinterpret_cast<__nv_bfloat16*>(take(tc_max));      // 2 planes x 2 bytes = one float per element
+  __nv_bfloat16* t_p = reinterpret_cast<__nv_bfloat16*>(take(tc_max));
   double flops = 0;
   auto ck = [&](cudaError_t e, const char* what) -> int {
     ++v->launches;
@@ -430,6 +491,51 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
     }
     ch /= 2;
     L = Lo;
+    if (tc_level(ch) && v->rb1[(size_t)i * c.n_kernels][0].wh) {
+      // ---- tensor-core level: channels-last state, dilated convolutions as implicit GEMMs (gemm_tc.cu) ----
+      const int64_t rows = (int64_t)B * L;
+      auto conv_tc = [&](const __nv_bfloat16* A, const ConvP& w, int dil, int epi, const float* R, float* out_f32, __nv_bfloat16* out_planes) {
+        TcGemmArgs g;
+        g.A = A; g.batches = B; g.rows = (int)L; g.cin = w.cin; g.taps = w.k; g.dil = dil; g.W = w.wh; g.N = w.cout; g.bias = w.b;
+        tc_set_split_pairs(g);
+        g.out_scale = 1.f / (PLANE_SCALE * v->wscale);
+        g.epilogue = epi; g.act_slope = 0.1f;
+        if (out_planes) { g.C = out_planes; g.c_ld = 2 * w.cout; g.out_kind = 2; }
+        else { g.C = out_f32; g.c_ld = w.cout; g.out_kind = 0; g.R = R; g.r_ld = w.cout; }
+        return launch_gemm_tc(g, s);
+      };
+      VTRY(ck(launch_transpose_bct_to_btc(xin, x_cl, B, ch, (int)L, 1.f, s), "transpose to channels-last"));
+      for (int j = 0; j < c.n_kernels; ++j) {
+        const int n = i * c.n_kernels + j;
+        const float* cur = x_cl;
+        const int nconv = (int)v->rb1[n].size();
+        for (int q = 0; q < nconv; ++q) {
+          const int d = c.resblock_dilations[j][q];
+          const bool last = q == nconv - 1;
+          float* dst = last ? (j == 0 ? xs_cl : lv[4]) : (cur == lv[2] ? lv[3] : lv[2]);
+          VTRY(ck(launch_lrelu_split_cast(cur, a_p, rows, ch, 2, 0.1f, s), "lrelu_split_cast"));
+          if (c.resblock_kind == 1) {     // xt = c2(lrelu(c1(lrelu(x)))); x = xt + x   (models.py:186-193)
+            VTRY(ck(conv_tc(a_p, v->rb1[n][q], d, EPI_LRELU, nullptr, nullptr, t_p), "resblock conv1 (tc)"));
+            VTRY(ck(conv_tc(t_p, v->rb2[n][q], 1, EPI_NONE, cur, dst, nullptr), "resblock conv2 (tc)"));
+            flops += 2.0 * 2.0 * B * L * ch * ch * c.resblock_kernel_sizes[j];
+          } else {                        // xt = c(lrelu(x)); x = xt + x   (models.py:214-217)
+            VTRY(ck(conv_tc(a_p, v->rb1[n][q], d, EPI_NONE, cur, dst, nullptr), "resblock conv (tc)"));
+            flops += 2.0 * B * L * ch * ch * c.resblock_kernel_sizes[j];
+          }
+          cur = dst;
+        }
+        if (j > 0) {                      // xs += r_j ; the last one also divides by num_kernels (models.py:243-251)
+          const int64_t n4 = rows * ch / 4;
+          voc_acc_kernel<<<(unsigned)std::min<int64_t>((n4 + 255) / 256, 2368), 256, 0, s>>>(
+              reinterpret_cast<float4*>(xs_cl), reinterpret_cast<const float4*>(lv[4]), n4, j == c.n_kernels - 1 ? 2 : 1, (float)c.n_kernels);
+          VTRY(ck(cudaGetLastError(), "resblock mean"));
+        }
+      }
+      VTRY(ck(launch_transpose_btc_to_bct(xs_cl, lv[1], B, ch, (int)L, 1.f, s), "transpose to channels-first"));
+      std::swap(lv[1], lv[5]);
+      x = lv[5];
+      continue;
+    }
     for (int j = 0; j < c.n_kernels; ++j) {
       const int n = i * c.n_kernels + j;
       // xs = r_0; xs += r_j; x = xs / num_kernels   (models.py:243-251; a single resblock: x = r_0 / 1 = r_0)

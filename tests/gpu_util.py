@@ -151,6 +151,19 @@ def op_gemm_tc(a_bf16, batches, rows, cin, parts, w_bf16, N, taps=1, bias=None, 
     return out
 
 
+def op_conv1d_tc(a_planes, batches, rows, cin, parts, w_planes, N, taps, dil, bias=None, R=None, out_kind=0, epilogue=0, act_slope=0.0):
+    if out_kind == 0:
+        out = torch.empty(batches * rows, N, device=a_planes.device, dtype=torch.float32)
+        c_ld = N
+    else:                      # 16-bit planes (bf16: 1 plane, split-f16: 2)
+        out = torch.empty(batches * rows, parts * N, device=a_planes.device, dtype=torch.bfloat16)
+        c_ld = parts * N
+    check(lib().lds_op_conv1d_tc(ptr(a_planes), batches, rows, cin, parts, ptr(w_planes), N, taps, dil, ptr(bias), ptr(R),
+                                 0 if R is None else R.shape[-1], ptr(out), c_ld, out_kind, epilogue, act_slope, stream()),
+          "lds_op_conv1d_tc")
+    return out
+
+
 def op_qkv_attention_tc(x, wq, wk, wv, B, T, heads, parts):
     """x fp32 [B*T, C]; returns attention output as fp32 (planes summed) [B*T, C]."""
     Cc = x.shape[1]

@@ -1,6 +1,7 @@
 """GPU: the CUDA vocoder (csrc/vocoder.cu through the C ABI) against the goldens of the executed reference Generator and the
-fp64 oracle.  fp32 FFMA vs the reference's fp32 convolutions differ only in summation order: |wav| <= 1 (tanh), tolerance
-max-abs 2e-6 and relative L2 1e-5 against fp64."""
+fp64 oracle.  The 256- / 128-channel levels run their dilated convolutions as split-f16 tensor-core GEMMs (fp32-accurate: 22-bit
+operands, fp32 accumulation in TMEM), the narrow levels as fp32 FFMA: |wav| <= 1 (tanh), tolerance max-abs 2e-6 and relative L2 1e-5
+against fp64 — the tolerance of the all-FFMA form; measured 3-5e-8 / 2.9e-7 on |wav| ~ 0.04 (the reference's own fp32: 2e-8 / 1.7e-7)."""
 import pytest
 import torch
 
@@ -63,3 +64,24 @@ def test_vocoder_interface_mirrors_reference_wrapper():
         voc.infer(V.synthetic_latents(1, 4))           # CPU tensor: no fallback
     with pytest.raises(ValueError):
         Vocoder("nsf-hifigan", None, device="cuda")
+
+
+@pytest.mark.parametrize("taps,dil,cin,N,rows,batches,epi", [(3, 1, 128, 128, 200, 2, 0), (7, 3, 256, 256, 333, 2, 4), (11, 5, 128, 128, 160, 3, 0),
+                                                          (11, 1, 256, 256, 97, 1, 4), (5, 2, 128, 256, 128, 2, 0)])
+def test_dilated_conv1d_tc_vs_fp64(taps, dil, cin, N, rows, batches, epi):
+    """lds_op_conv1d_tc (the generator's dilated ResBlock convolutions as implicit GEMMs, models.py:166-184) against F.conv1d in fp64:
+    'same' padding dil*(k-1)/2, bias, leaky_relu(0.1) epilogue or fp32 residual; ragged rows, several utterances."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(taps * 100 + dil)
+    x = torch.randn(batches, rows, cin, generator=g)
+    w = torch.randn(N, cin, taps, generator=g) * (cin * taps) ** -0.5
+    bias = torch.randn(N, generator=g)
+    R = torch.randn(batches * rows, N, generator=g) if epi == 0 else None
+    ref = F.conv1d(x.double().transpose(1, 2), w.double(), bias.double(), padding=dil * (taps - 1) // 2, dilation=dil).transpose(1, 2).reshape(-1, N)
+    ref = F.leaky_relu(ref, 0.1) if epi == 4 else ref + R.double()
+    a = G.op_split_cast(x.reshape(-1, cin).cuda(), 2)
+    wp = G.pack_w_parts(w.permute(0, 2, 1).reshape(N, taps * cin).contiguous().cuda(), taps, 2)
+    out = G.op_conv1d_tc(a, batches, rows, cin, 2, wp, N, taps, dil, bias=bias.cuda(), R=None if R is None else R.cuda(), epilogue=epi, act_slope=0.1)
+    e = G.errs(out.cpu(), ref)
+    G.report(test="dilated_conv1d_tc", taps=taps, dil=dil, cin=cin, N=N, **e)
+    assert e["rel_l2"] <= 5e-6 and e["max_abs"] <= 4e-5, e      # measured 0.3-2.5e-6 (K = 384 ... 2816: truncating fp32 accumulate in TMEM)
