@@ -944,7 +944,7 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (a.batches <= 0 || a.rows <= 0 || a.N <= 0) return cudaSuccess;
   const bool split = a.a_parts == 2 && a.w_parts == 2 && a.n_pairs == 3;      // split-f16 (fp32-accurate)
   const bool plain = a.a_parts == 1 && a.w_parts == 1 && a.n_pairs == 1;
-  if (a.cin % 64 || a.N % 128 || a.taps < 1 || a.taps > 11 || a.taps % 2 == 0 || a.dil < 1 || (!split && !plain) || (a.out_kind != 3 && a.c_ld % 8) ||
+  if (a.cin % 64 || a.N % 64 || (a.N % 128 && (a.epilogue == EPI_GEGLU || a.out_kind == 3)) || a.taps < 1 || a.taps > 11 || a.taps % 2 == 0 || a.dil < 1 || (!split && !plain) || (a.out_kind != 3 && a.c_ld % 8) ||
       (a.R && a.r_ld % 4) || a.r_div < 1)
     return cudaErrorInvalidValue;
   if (a.out_kind == 3 && (!a.q_out || !a.k_out || !a.vt_out || a.att_T < 1 || a.att_dpad % 32 || a.N != 3 * a.att_H * a.att_dpad ||
@@ -958,7 +958,8 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
   }
   TcParams p;
-  p.BN = a.N % 256 == 0 ? 256 : ((a.N % 192 == 0 && a.epilogue != EPI_GEGLU) ? 192 : 128);   // GEGLU groups are 128 wide
+  p.BN = a.N % 256 == 0 ? 256 : ((a.N % 192 == 0 && a.epilogue != EPI_GEGLU) ? 192 : (a.N % 128 == 0 ? 128 : 64));   // GEGLU groups are 128 wide;
+  // BN = 64 (N = 64 + 128 j: the vocoder's 64-channel level): an N = 64 instruction costs the same 92 cycles as N = 128
   {
     // Small problems (single utterances, the deep levels of small batches) leave most CTA pairs idle: narrower N tiles double
     // the number of items, and an N = 128 instruction costs 92 cycles against 128 for N = 256, so every item is also 28 %

@@ -8,12 +8,12 @@
 //   encoder/hifi_vaegan/hifi_vaegan.py:52-65        Hifi_VAEGAN.forward: [B,T,C] -> [B,C,T], remove_weight_norm, Generator
 //
 // Two forms of the ResBlock convolutions:
-//   * levels whose channel count is a multiple of 128 (256 and 128 channels in the HiFi-GAN V1 layout: 48 % of the FLOPs) run on the
+//   * levels whose channel count is a multiple of 64 (256, 128 and 64 channels in the HiFi-GAN V1 layout: 83 % of the FLOPs) run on the
 //     tensor cores: channels-LAST fp32 [B*L, C] state, every dilated k in {3..11} convolution an implicit GEMM of gemm_tc.cu (tap t =
 //     the TMA row coordinate shifted by (t - (k-1)/2) * dilation, zero padding = TMA out-of-bounds fill, split-f16 operand planes:
 //     fp32-accurate at three tcgen05 products per logical product), leaky_relu fused into the operand cast / the first convolution's
 //     epilogue, bias + residual in the second one's;
-//   * the waveform-rate levels (64 / 32 channels, up to 512 samples per frame: time is the long, coalescing axis) and the transposed
+//   * the last level (32 channels at 512 samples per frame: time is the long, coalescing axis) and the transposed
 //     convolutions stay channels-FIRST fp32 [B, C, L] on the CUDA cores: IEEE FFMA, register-blocked direct convolution (8 output
 //     channels x 8 time steps per thread, input slab with its dilated halo and the [ci][tap][co] weight slab staged in shared memory,
 //     leaky_relu applied once while staging).
@@ -194,8 +194,8 @@ __global__ void voc_transpose_kernel(const float* __restrict__ in, float* __rest
 
 struct ConvP { const float* w = nullptr; const float* b = nullptr; const __nv_bfloat16* wh = nullptr; int cin = 0, cout = 0, k = 0; };
 
-// resblock levels that run as implicit GEMMs on the tensor cores (gemm_tc: K blocks of 64 channels, N tiles of 128)
-inline bool tc_level(int ch) { return ch >= 128 && ch % 128 == 0; }
+// resblock levels that run as implicit GEMMs on the tensor cores (gemm_tc: K blocks of 64 channels, N tiles of 64 ... 256)
+inline bool tc_level(int ch) { return ch >= 64 && ch % 64 == 0; }
 
 // xs (+)= r over n floats: mode 0 xs = r ; 1 xs = xs + r ; 2 xs = (xs + r) / div     (mean over the resblocks, models.py:243-251)
 __global__ void voc_acc_kernel(float4* __restrict__ xs, const float4* __restrict__ r, int64_t n4, int mode, float div) {

@@ -67,7 +67,8 @@ def test_vocoder_interface_mirrors_reference_wrapper():
 
 
 @pytest.mark.parametrize("taps,dil,cin,N,rows,batches,epi", [(3, 1, 128, 128, 200, 2, 0), (7, 3, 256, 256, 333, 2, 4), (11, 5, 128, 128, 160, 3, 0),
-                                                          (11, 1, 256, 256, 97, 1, 4), (5, 2, 128, 256, 128, 2, 0)])
+                                                          (11, 1, 256, 256, 97, 1, 4), (5, 2, 128, 256, 128, 2, 0), (7, 3, 64, 64, 301, 2, 0), (11, 5, 64, 64, 256, 2, 4),
+                                                          (3, 1, 64, 320, 100, 1, 0)])
 def test_dilated_conv1d_tc_vs_fp64(taps, dil, cin, N, rows, batches, epi):
     """lds_op_conv1d_tc (the generator's dilated ResBlock convolutions as implicit GEMMs, models.py:166-184) against F.conv1d in fp64:
     'same' padding dil*(k-1)/2, bias, leaky_relu(0.1) epilogue or fp32 residual; ragged rows, several utterances."""
