@@ -988,7 +988,9 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   // same as two tiles: 115.1-116.0 k frames/s for all four combinations, GPU call 26 of round 2.  Also measured and rejected,
   // profiles/r02_gemm_experiments_call133.md: an L2 prefetch stream of the A operand 4 / 8 K blocks ahead of the ring loads
   // (cp.async.bulk.prefetch.tensor) — 8-90 % SLOWER per shape: the main loop is bound by L2 -> SM throughput, not latency, and
-  // the prefetches compete for it; A ring of 4 instead of 6 slots: +2 %; the staged epilogue instead of TMA for long K: +5 %.)
+  // the prefetches compete for it; A ring of 4 instead of 6 slots: +2 %; the staged epilogue instead of TMA for long K: +5 %.
+  // bf16 mode, GPU call 141: the staged epilogue for the fused QKV projection 228.4 k -> 209.9 k frames/s, for every 16-bit output
+  // 190.4 k: the direct stores stay.)
   p.nbuf = split ? 2 : 3;
   p.na = (split || !p.tma_epi) ? 6 : 4;
 #ifdef LDS_DEBUG_KNOBS
