@@ -7,15 +7,16 @@
 //   encoder/hifi_vaegan/modules/models.py:161-221   ResBlock1 / ResBlock2 (dilated k in {3,7,11} convolutions with residuals)
 //   encoder/hifi_vaegan/hifi_vaegan.py:52-65        Hifi_VAEGAN.forward: [B,T,C] -> [B,C,T], remove_weight_norm, Generator
 //
-// Two forms of the ResBlock convolutions:
+// Three kinds of layers:
 //   * levels whose channel count is a multiple of 64 (256, 128 and 64 channels in the HiFi-GAN V1 layout: 83 % of the FLOPs) run on the
 //     tensor cores: channels-LAST fp32 [B*L, C] state, every dilated k in {3..11} convolution an implicit GEMM of gemm_tc.cu (tap t =
 //     the TMA row coordinate shifted by (t - (k-1)/2) * dilation, zero padding = TMA out-of-bounds fill, split-f16 operand planes:
 //     fp32-accurate at three tcgen05 products per logical product), leaky_relu fused into the operand cast / the first convolution's
 //     epilogue, bias + residual in the second one's;
-//   * the last level (32 channels at 512 samples per frame: time is the long, coalescing axis) and the transposed
-//     convolutions stay channels-FIRST fp32 [B, C, L] on the CUDA cores: IEEE FFMA, register-blocked direct convolution (8 output
-//     channels x 8 time steps per thread, input slab with its dilated halo and the [ci][tap][co] weight slab staged in shared memory,
+//   * the transposed convolutions (kernel 2u, stride u) are one 3-tap implicit GEMM each with N = u * C_out (lds_vocoder_finalize);
+//   * the last level (32 channels at 512 samples per frame: time is the long, coalescing axis), conv_pre and conv_post stay
+//     channels-FIRST fp32 [B, C, L] on the CUDA cores: IEEE FFMA, register-blocked direct convolution (8 output channels x 8 time
+//     steps per thread, input slab with its dilated halo and the [ci][tap][co] weight slab staged in shared memory,
 //     leaky_relu applied once while staging).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -192,10 +193,13 @@ __global__ void voc_transpose_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
-struct ConvP { const float* w = nullptr; const float* b = nullptr; const __nv_bfloat16* wh = nullptr; int cin = 0, cout = 0, k = 0; };
+struct ConvP { const float* w = nullptr; const float* b = nullptr; const __nv_bfloat16* wh = nullptr; const float* b_rep = nullptr; int cin = 0, cout = 0, k = 0; };
 
 // resblock levels that run as implicit GEMMs on the tensor cores (gemm_tc: K blocks of 64 channels, N tiles of 64 ... 256)
 inline bool tc_level(int ch) { return ch >= 64 && ch % 64 == 0; }
+
+// transposed convolutions that run as a 3-tap implicit GEMM (kernel 2u, even stride u; K blocks of 64 channels, N = u * cout tiles of 64)
+inline bool up_tc_ok(int cin, int cout, int k, int u) { return u >= 2 && u % 2 == 0 && k == 2 * u && cin % 64 == 0 && (u * cout) % 64 == 0; }
 
 // xs (+)= r over n floats: mode 0 xs = r ; 1 xs = xs + r ; 2 xs = (xs + r) / div     (mean over the resblocks, models.py:243-251)
 __global__ void voc_acc_kernel(float4* __restrict__ xs, const float4* __restrict__ r, int64_t n4, int mode, float div) {
@@ -344,14 +348,14 @@ int lds_vocoder_finalize(lds_vocoder* v) {
   {
     float wmax = 0.f;
     for (const auto& kv : v->raw)
-      if (kv.first.rfind("resblocks.", 0) == 0 && kv.second.second.size() == 3)
+      if ((kv.first.rfind("resblocks.", 0) == 0 || kv.first.rfind("ups.", 0) == 0) && kv.second.second.size() == 3)
         for (float x : kv.second.first) wmax = std::max(wmax, std::fabs(x));
     float sc = 4096.f;
     while (sc > 1.f && wmax * sc >= 16384.f) sc *= 0.5f;
     v->wscale = pkh.scale = sc;
   }
   // Conv1d weight [cout, cin, k] -> [cin][k][cout];  ConvTranspose1d weight [cin, cout, k] -> [cin][k][cout]
-  auto conv = [&](ConvP& p, const std::string& key, int cin, int cout, int k, bool transposed) -> bool {
+  auto conv = [&](ConvP& p, const std::string& key, int cin, int cout, int k, bool transposed, int up_rate = 0) -> bool {
     auto itw = v->raw.find(key + ".weight"), itb = v->raw.find(key + ".bias");
     if (itw == v->raw.end() || itb == v->raw.end()) { rc = vfail(LDS_ERR_MISSING, "weight '%s.weight' / '.bias' was not loaded", key.c_str()); return false; }
     const std::vector<int64_t> want = transposed ? std::vector<int64_t>{cin, cout, k} : std::vector<int64_t>{cout, cin, k};
@@ -368,6 +372,32 @@ int lds_vocoder_finalize(lds_vocoder* v) {
     put(&p.w, t.data(), t.size());
     put(&p.b, itb->second.first.data(), (size_t)cout);
     p.cin = cin; p.cout = cout; p.k = k;
+    if (transposed && up_tc_ok(cin, cout, k, up_rate)) {
+      // ConvTranspose1d(stride u, kernel 2u, padding u/2) as ONE 3-tap implicit GEMM with N = u * cout: output frame lo = q*u + s of
+      // input frame q is  s <  u - pad:  W[.., s+pad] x[q] + W[.., s+pad+u] x[q-1]
+      //                  s >= u - pad:  W[.., s+pad-u] x[q+1] + W[.., s+pad] x[q]
+      // (lo = li*u - pad + kk  =>  kk = (lo + pad) mod u (+u), li = (lo + pad - kk) / u), so a GEMM row q of width [u][cout] IS the u
+      // output frames of q in channels-last order; taps (x[q-1], x[q], x[q+1]) = gemm_tc's k3 convolution, a third of the blocks zero.
+      const int u = up_rate, pad = u / 2;
+      std::vector<float> tt((size_t)u * cout * 3 * cin, 0.f), bb((size_t)u * cout);
+      for (int sidx = 0; sidx < u; ++sidx)
+        for (int co = 0; co < cout; ++co) {
+          const size_t n = (size_t)sidx * cout + co;
+          bb[n] = itb->second.first[co];
+          for (int ci = 0; ci < cin; ++ci) {
+            const float* wk = src + ((size_t)ci * cout + co) * k;
+            if (sidx < u - pad) {
+              tt[(n * 3 + 1) * cin + ci] = wk[sidx + pad];
+              tt[(n * 3 + 0) * cin + ci] = wk[sidx + pad + u];
+            } else {
+              tt[(n * 3 + 2) * cin + ci] = wk[sidx + pad - u];
+              tt[(n * 3 + 1) * cin + ci] = wk[sidx + pad];
+            }
+          }
+        }
+      fixh.emplace_back(&p.wh, pkh.add(tt.data(), (size_t)u * cout * 3, cin, 2));
+      put(&p.b_rep, bb.data(), bb.size());
+    }
     if (!transposed && key.rfind("resblocks.", 0) == 0 && tc_level(cin) && cin == cout) {   // [cout][tap][plane][cin] for gemm_tc
       std::vector<float> tt((size_t)cout * k * cin);
       for (int co = 0; co < cout; ++co)
@@ -384,7 +414,7 @@ int lds_vocoder_finalize(lds_vocoder* v) {
   bool ok = conv(v->conv_pre, "conv_pre", c.inter_channels, c.upsample_initial_channel, 7, false);
   int ch = c.upsample_initial_channel;
   for (int i = 0; ok && i < c.n_ups; ++i) {
-    ok = conv(v->ups[i], "ups." + std::to_string(i), ch, ch / 2, c.upsample_kernel_sizes[i], true);
+    ok = conv(v->ups[i], "ups." + std::to_string(i), ch, ch / 2, c.upsample_kernel_sizes[i], true, c.upsample_rates[i]);
     ch /= 2;
     for (int j = 0; ok && j < c.n_kernels; ++j) {
       const int n = i * c.n_kernels + j, k = c.resblock_kernel_sizes[j];
@@ -442,10 +472,11 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
     for (int i = 0; i < c.n_ups; ++i) {
       ch /= 2; L *= c.upsample_rates[i];
       lvl_max = std::max(lvl_max, (size_t)B * ch * (size_t)L);
-      if (tc_level(ch)) tc_max = std::max(tc_max, (size_t)B * ch * (size_t)L);
     }
+    // channels-last tensors of the tensor-core path: a level's input / output, or conv_pre's output ahead of the first transposed convolution
+    tc_max = std::max(lvl_max, (size_t)B * c.upsample_initial_channel * (size_t)T);
   }
-  need += 6 * (lvl_max + 64) + 4 * (tc_max + 64) + 1024;   // tensor-core levels: two channels-last fp32 tensors + two split-f16 plane buffers
+  need += 6 * (lvl_max + 64) + 4 * (tc_max + 64) + 1024;   // tensor-core path: two channels-last fp32 tensors + two split-f16 plane buffers
   if (need > v->arena_cap) {           // grow-only; growing synchronises (work in flight may still use the old arena)
     if (cudaDeviceSynchronize() != cudaSuccess) return vfail(LDS_ERR_CUDA, "synchronize before workspace growth failed");
     if (v->arena) { cudaFree(v->arena); v->arena = nullptr; v->arena_cap = 0; }
@@ -475,36 +506,55 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
   }
   VTRY(ck(launch_conv(zt, v->conv_pre, nullptr, pre, B, T, 1, 1.f, 0, 1.f, 0, s), "conv_pre"));
   flops += 2.0 * B * T * c.inter_channels * c.upsample_initial_channel * 7;
-  const float* x = pre;
+  // The state between levels is either channels-first (x_cf: the FFMA kernels) or channels-last (x_cl_cur: the tensor-core kernels);
+  // a transpose is inserted only where the form changes (after conv_pre, and before the first level that stays on the CUDA cores).
+  const float* x_cf = pre;
+  const float* x_cl_cur = nullptr;
   int ch = c.upsample_initial_channel;
   int64_t L = T;
+  auto conv_tc = [&](const __nv_bfloat16* A, int rows_per_utt, int cin, int taps, int dil, const __nv_bfloat16* W, int N, const float* bias, int epi,
+                     const float* R, float* out_f32, __nv_bfloat16* out_planes) {
+    TcGemmArgs g;
+    g.A = A; g.batches = B; g.rows = rows_per_utt; g.cin = cin; g.taps = taps; g.dil = dil; g.W = W; g.N = N; g.bias = bias;
+    tc_set_split_pairs(g);
+    g.out_scale = 1.f / (PLANE_SCALE * v->wscale);
+    g.epilogue = epi; g.act_slope = 0.1f;
+    if (out_planes) { g.C = out_planes; g.c_ld = 2 * N; g.out_kind = 2; }
+    else { g.C = out_f32; g.c_ld = N; g.out_kind = 0; g.R = R; g.r_ld = N; }
+    return launch_gemm_tc(g, s);
+  };
   for (int i = 0; i < c.n_ups; ++i) {
     const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
     const int64_t Lo = (L - 1) * u - 2 * ((k - u + 1) / 2) + k;
-    float* xin = lv[0];          // level input (output of the transposed convolution)
-    float* xs = lv[1];           // running sum / mean of the resblocks
-    {
+    float* xin = lv[0];          // level input, channels-first (output of the FFMA transposed convolution)
+    float* xs = lv[1];           // running sum / mean of the resblocks, channels-first
+    const bool level_tc = tc_level(ch / 2) && v->rb1[(size_t)i * c.n_kernels][0].wh;
+    bool xin_is_cl = false;      // the level input lives in x_cl (channels-last) instead of xin
+    if (v->ups[i].wh) {          // x = ups[i](leaky_relu(x, 0.1)) as a 3-tap implicit GEMM: [B*L, ch] -> [B*L, u*ch/2] == [B*Lo, ch/2]
+      if (!x_cl_cur) {
+        VTRY(ck(launch_transpose_bct_to_btc(x_cf, xs_cl, B, ch, (int)L, 1.f, s), "transpose to channels-last"));
+        x_cl_cur = xs_cl;
+      }
+      VTRY(ck(launch_lrelu_split_cast(x_cl_cur, a_p, (int64_t)B * L, ch, 2, 0.1f, s), "lrelu_split_cast"));
+      VTRY(ck(conv_tc(a_p, (int)L, ch, 3, 1, v->ups[i].wh, u * (ch / 2), v->ups[i].b_rep, EPI_NONE, nullptr, x_cl, nullptr), "conv_transpose (tc)"));
+      flops += 2.0 * B * Lo * ch * (ch / 2) * ((double)k / u);
+      xin_is_cl = true;
+    } else {
+      if (x_cl_cur) {
+        VTRY(ck(launch_transpose_btc_to_bct(x_cl_cur, lv[5], B, ch, (int)L, 1.f, s), "transpose to channels-first"));
+        x_cf = lv[5];
+      }
       dim3 grid((unsigned)((Lo + 127) / 128), (ch / 2 + 15) / 16, B);
-      voc_convtr1d_kernel<<<grid, 128, 0, s>>>(x, v->ups[i].w, v->ups[i].b, xin, ch, ch / 2, (int)L, (int)Lo, k, u, (k - u + 1) / 2, 0.1f);
+      voc_convtr1d_kernel<<<grid, 128, 0, s>>>(x_cf, v->ups[i].w, v->ups[i].b, xin, ch, ch / 2, (int)L, (int)Lo, k, u, (k - u + 1) / 2, 0.1f);
       VTRY(ck(cudaGetLastError(), "conv_transpose"));
       flops += 2.0 * B * Lo * ch * (ch / 2) * ((double)k / u);
     }
     ch /= 2;
     L = Lo;
-    if (tc_level(ch) && v->rb1[(size_t)i * c.n_kernels][0].wh) {
+    if (level_tc) {
       // ---- tensor-core level: channels-last state, dilated convolutions as implicit GEMMs (gemm_tc.cu) ----
       const int64_t rows = (int64_t)B * L;
-      auto conv_tc = [&](const __nv_bfloat16* A, const ConvP& w, int dil, int epi, const float* R, float* out_f32, __nv_bfloat16* out_planes) {
-        TcGemmArgs g;
-        g.A = A; g.batches = B; g.rows = (int)L; g.cin = w.cin; g.taps = w.k; g.dil = dil; g.W = w.wh; g.N = w.cout; g.bias = w.b;
-        tc_set_split_pairs(g);
-        g.out_scale = 1.f / (PLANE_SCALE * v->wscale);
-        g.epilogue = epi; g.act_slope = 0.1f;
-        if (out_planes) { g.C = out_planes; g.c_ld = 2 * w.cout; g.out_kind = 2; }
-        else { g.C = out_f32; g.c_ld = w.cout; g.out_kind = 0; g.R = R; g.r_ld = w.cout; }
-        return launch_gemm_tc(g, s);
-      };
-      VTRY(ck(launch_transpose_bct_to_btc(xin, x_cl, B, ch, (int)L, 1.f, s), "transpose to channels-last"));
+      if (!xin_is_cl) VTRY(ck(launch_transpose_bct_to_btc(xin, x_cl, B, ch, (int)L, 1.f, s), "transpose to channels-last"));
       for (int j = 0; j < c.n_kernels; ++j) {
         const int n = i * c.n_kernels + j;
         const float* cur = x_cl;
@@ -515,11 +565,13 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
           float* dst = last ? (j == 0 ? xs_cl : lv[4]) : (cur == lv[2] ? lv[3] : lv[2]);
           VTRY(ck(launch_lrelu_split_cast(cur, a_p, rows, ch, 2, 0.1f, s), "lrelu_split_cast"));
           if (c.resblock_kind == 1) {     // xt = c2(lrelu(c1(lrelu(x)))); x = xt + x   (models.py:186-193)
-            VTRY(ck(conv_tc(a_p, v->rb1[n][q], d, EPI_LRELU, nullptr, nullptr, t_p), "resblock conv1 (tc)"));
-            VTRY(ck(conv_tc(t_p, v->rb2[n][q], 1, EPI_NONE, cur, dst, nullptr), "resblock conv2 (tc)"));
+            const ConvP &w1 = v->rb1[n][q], &w2 = v->rb2[n][q];
+            VTRY(ck(conv_tc(a_p, (int)L, ch, w1.k, d, w1.wh, ch, w1.b, EPI_LRELU, nullptr, nullptr, t_p), "resblock conv1 (tc)"));
+            VTRY(ck(conv_tc(t_p, (int)L, ch, w2.k, 1, w2.wh, ch, w2.b, EPI_NONE, cur, dst, nullptr), "resblock conv2 (tc)"));
             flops += 2.0 * 2.0 * B * L * ch * ch * c.resblock_kernel_sizes[j];
           } else {                        // xt = c(lrelu(x)); x = xt + x   (models.py:214-217)
-            VTRY(ck(conv_tc(a_p, v->rb1[n][q], d, EPI_NONE, cur, dst, nullptr), "resblock conv (tc)"));
+            const ConvP& w1 = v->rb1[n][q];
+            VTRY(ck(conv_tc(a_p, (int)L, ch, w1.k, d, w1.wh, ch, w1.b, EPI_NONE, cur, dst, nullptr), "resblock conv (tc)"));
             flops += 2.0 * B * L * ch * ch * c.resblock_kernel_sizes[j];
           }
           cur = dst;
@@ -531,11 +583,12 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
           VTRY(ck(cudaGetLastError(), "resblock mean"));
         }
       }
-      VTRY(ck(launch_transpose_btc_to_bct(xs_cl, lv[1], B, ch, (int)L, 1.f, s), "transpose to channels-first"));
-      std::swap(lv[1], lv[5]);
-      x = lv[5];
+      x_cl_cur = xs_cl;                   // stays channels-last for the next transposed convolution
+      x_cf = nullptr;
       continue;
     }
+    // ---- CUDA-core level (channels-first) ----
+    if (xin_is_cl) VTRY(ck(launch_transpose_btc_to_bct(x_cl, xin, B, ch, (int)L, 1.f, s), "transpose to channels-first"));
     for (int j = 0; j < c.n_kernels; ++j) {
       const int n = i * c.n_kernels + j;
       // xs = r_0; xs += r_j; x = xs / num_kernels   (models.py:243-251; a single resblock: x = r_0 / 1 = r_0)
@@ -559,7 +612,13 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
     }
     // next level reads xs; keep it out of the way of the next level's scratch by swapping roles
     std::swap(lv[1], lv[5]);
-    x = lv[5];
+    x_cf = lv[5];
+    x_cl_cur = nullptr;
+  }
+  const float* x = x_cf;
+  if (!x) {                               // the last level ran on the tensor cores: conv_post (FFMA) reads channels-first
+    VTRY(ck(launch_transpose_btc_to_bct(x_cl_cur, lv[0], B, ch, (int)L, 1.f, s), "transpose to channels-first"));
+    x = lv[0];
   }
   VTRY(ck(launch_conv(x, v->conv_post, nullptr, wav_BL, B, (int)L, 1, 0.01f, 0, 1.f, 1, s), "conv_post"));
   flops += 2.0 * B * L * ch * 7;
