@@ -70,7 +70,8 @@ constexpr int MAX_EPI_BUFS = 4;                       // TMA epilogue buffers pe
 struct TcParams {
   int rows, batches, tiles_per_batch, m_tiles, n_tiles, total_items;   // A: [batches][rows][parts*cin]; item = (M-tile group, N tile)
   int blk_tiling, blks_per_batch, total_blks;   // flat tiling of batched convolutions in 32-row blocks (rows % 32 == 0)
-  int cin, taps, pad, dil, parts;
+  int cin, taps, parts;
+  short tap_row[24];                    // row offset of tap t relative to the output row (uniform: (t - (taps-1)/2) * dil)
   int BN, na, nw, w_slot_bytes;         // ring depths (A slots, W slots)
   int nkb, kb_per_tap;                  // K blocks of TBK per plane (all taps) / per tap
   int N;
@@ -617,7 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int n0 = nt * p.BN;
         int tap = 0, cb = 0;
         for (int kb = 0; kb < p.nkb; ++kb) {
-          const int row = t0 - p.pad + tap * p.dil, acol = cb * TBK, wcol = tap * p.parts * p.cin + cb * TBK;
+          const int row = t0 + p.tap_row[tap], acol = cb * TBK, wcol = tap * p.parts * p.cin + cb * TBK;
           if (split) {                           // need order of the MMA warp: A_h1, W_h2 | A_h2, W_h1
             load_a(acol, row, b);
             load_w(wcol + p.cin, n0);
@@ -944,7 +945,7 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (a.batches <= 0 || a.rows <= 0 || a.N <= 0) return cudaSuccess;
   const bool split = a.a_parts == 2 && a.w_parts == 2 && a.n_pairs == 3;      // split-f16 (fp32-accurate)
   const bool plain = a.a_parts == 1 && a.w_parts == 1 && a.n_pairs == 1;
-  if (a.cin % 64 || a.N % 64 || (a.N % 128 && (a.epilogue == EPI_GEGLU || a.out_kind == 3)) || a.taps < 1 || a.taps > 11 || a.taps % 2 == 0 || a.dil < 1 || (!split && !plain) || (a.out_kind != 3 && a.c_ld % 8) ||
+  if (a.cin % 64 || a.N % 64 || (a.N % 128 && (a.epilogue == EPI_GEGLU || a.out_kind == 3)) || a.taps < 1 || (a.tap_rows ? a.taps > 24 : (a.taps > 11 || a.taps % 2 == 0)) || a.dil < 1 || (!split && !plain) || (a.out_kind != 3 && a.c_ld % 8) ||
       (a.R && a.r_ld % 4) || a.r_div < 1)
     return cudaErrorInvalidValue;
   if (a.out_kind == 3 && (!a.q_out || !a.k_out || !a.vt_out || a.att_T < 1 || a.att_dpad % 32 || a.N != 3 * a.att_H * a.att_dpad ||
@@ -1018,7 +1019,8 @@ cudaError_t launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   p.rows = a.rows; p.batches = a.batches; p.tiles_per_batch = (a.rows + TBM - 1) / TBM;
   p.n_tiles = a.N / p.BN; p.total_items = p.n_tiles * ((p.m_tiles + csize - 1) / csize);
-  p.cin = a.cin; p.taps = a.taps; p.dil = a.dil; p.pad = (a.taps - 1) / 2 * a.dil; p.parts = a.a_parts;
+  p.cin = a.cin; p.taps = a.taps; p.parts = a.a_parts;
+  for (int t = 0; t < 24; ++t) p.tap_row[t] = t < a.taps ? (short)(a.tap_rows ? a.tap_rows[t] : (t - (a.taps - 1) / 2) * a.dil) : 0;
   p.kb_per_tap = a.cin / TBK; p.nkb = a.taps * p.kb_per_tap;
   p.N = a.N; p.bias = a.bias; p.R = a.R; p.r_ld = a.r_ld; p.r_div = a.r_div;
   p.C = a.C; p.c_ld = a.c_ld; p.out_kind = a.out_kind; p.epilogue = a.epilogue;

@@ -97,6 +97,8 @@ cudaError_t launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
 struct TcGemmArgs {
   const __nv_bfloat16* A = nullptr; int batches = 1, rows = 0, cin = 0, a_parts = 1;
   const __nv_bfloat16* W = nullptr; int N = 0, taps = 1, w_parts = 1, dil = 1;
+  const int* tap_rows = nullptr;          // optional (host): row offset of every tap, taps <= 24 of any parity — replaces (t - (taps-1)/2) * dil
+                                          // (time-folded convolutions of the vocoder's narrow levels: non-uniform tap spacing)
   int n_pairs = 1; int pair_a[6] = {0, 0, 0, 0, 0, 0}; int pair_w[6] = {0, 0, 0, 0, 0, 0};
   const float* bias = nullptr;
   const float* R = nullptr; int r_ld = 0, r_div = 1;

@@ -8,15 +8,15 @@
 //   encoder/hifi_vaegan/hifi_vaegan.py:52-65        Hifi_VAEGAN.forward: [B,T,C] -> [B,C,T], remove_weight_norm, Generator
 //
 // Three kinds of layers:
-//   * levels whose channel count is a multiple of 64 (256, 128 and 64 channels in the HiFi-GAN V1 layout: 83 % of the FLOPs) run on the
+//   * ResBlock levels whose channel count is a multiple of 64 (256, 128 and 64 channels in the HiFi-GAN V1 layout) run on the
 //     tensor cores: channels-LAST fp32 [B*L, C] state, every dilated k in {3..11} convolution an implicit GEMM of gemm_tc.cu (tap t =
 //     the TMA row coordinate shifted by (t - (k-1)/2) * dilation, zero padding = TMA out-of-bounds fill, split-f16 operand planes:
 //     fp32-accurate at three tcgen05 products per logical product), leaky_relu fused into the operand cast / the first convolution's
 //     epilogue, bias + residual in the second one's;
 //   * the transposed convolutions (kernel 2u, stride u) are one 3-tap implicit GEMM each with N = u * C_out (lds_vocoder_finalize);
-//   * the last level (32 channels at 512 samples per frame: time is the long, coalescing axis), conv_pre and conv_post stay
-//     channels-FIRST fp32 [B, C, L] on the CUDA cores: IEEE FFMA, register-blocked direct convolution (8 output channels x 8 time
-//     steps per thread, input slab with its dilated halo and the [ci][tap][co] weight slab staged in shared memory,
+//   * the 32-channel level is time-folded onto the same kernel (fold_of below): two frames per GEMM row, block-sparse folded taps;
+//   * conv_pre and conv_post (and any layer the GEMM forms do not cover) stay channels-FIRST fp32 [B, C, L] on the CUDA cores: IEEE
+//     FFMA, register-blocked direct convolution (8 output channels x 8 time steps per thread, input slab with its dilated halo and the [ci][tap][co] weight slab staged in shared memory,
 //     leaky_relu applied once while staging).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -193,10 +193,20 @@ __global__ void voc_transpose_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
-struct ConvP { const float* w = nullptr; const float* b = nullptr; const __nv_bfloat16* wh = nullptr; const float* b_rep = nullptr; int cin = 0, cout = 0, k = 0; };
+struct ConvP {
+  const float* w = nullptr; const float* b = nullptr; int cin = 0, cout = 0, k = 0;
+  const __nv_bfloat16* wh = nullptr;      // tensor-core form (gemm_tc operand planes)
+  const float* b_rep = nullptr;           // bias repeated over the N columns of a folded / transposed-convolution GEMM
+  int fold = 1, ntaps = 0, tap_off[24] = {0};   // time-folded form of a narrow level: `fold` frames per GEMM row, coarse tap offsets
+};
 
 // resblock levels that run as implicit GEMMs on the tensor cores (gemm_tc: K blocks of 64 channels, N tiles of 64 ... 256)
-inline bool tc_level(int ch) { return ch >= 64 && ch % 64 == 0; }
+inline bool tc_level(int ch) { return (ch >= 64 && ch % 64 == 0) || ch == 32 || ch == 16; }
+// Narrow levels are TIME-FOLDED onto the 64-wide K blocks: `fold` = 64 / ch consecutive frames form one GEMM row of 64 "channels"
+// (the channels-last tensor [B, L, ch] IS [B, L / fold, 64] in memory), and the dilated convolution becomes a convolution over
+// folded rows with block-sparse 64 x 64 taps at the (non-uniform) folded offsets floor((s + delta) / fold).
+inline int fold_of(int ch) { return ch < 64 ? 64 / ch : 1; }
+inline int floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
 // transposed convolutions that run as a 3-tap implicit GEMM (kernel 2u, even stride u; K blocks of 64 channels, N = u * cout tiles of 64)
 inline bool up_tc_ok(int cin, int cout, int k, int u) { return u >= 2 && u % 2 == 0 && k == 2 * u && cin % 64 == 0 && (u * cout) % 64 == 0; }
@@ -355,7 +365,7 @@ int lds_vocoder_finalize(lds_vocoder* v) {
     v->wscale = pkh.scale = sc;
   }
   // Conv1d weight [cout, cin, k] -> [cin][k][cout];  ConvTranspose1d weight [cin, cout, k] -> [cin][k][cout]
-  auto conv = [&](ConvP& p, const std::string& key, int cin, int cout, int k, bool transposed, int up_rate = 0) -> bool {
+  auto conv = [&](ConvP& p, const std::string& key, int cin, int cout, int k, bool transposed, int up_rate = 0, int dil = 1) -> bool {
     auto itw = v->raw.find(key + ".weight"), itb = v->raw.find(key + ".bias");
     if (itw == v->raw.end() || itb == v->raw.end()) { rc = vfail(LDS_ERR_MISSING, "weight '%s.weight' / '.bias' was not loaded", key.c_str()); return false; }
     const std::vector<int64_t> want = transposed ? std::vector<int64_t>{cin, cout, k} : std::vector<int64_t>{cout, cin, k};
@@ -398,7 +408,37 @@ int lds_vocoder_finalize(lds_vocoder* v) {
       fixh.emplace_back(&p.wh, pkh.add(tt.data(), (size_t)u * cout * 3, cin, 2));
       put(&p.b_rep, bb.data(), bb.size());
     }
-    if (!transposed && key.rfind("resblocks.", 0) == 0 && tc_level(cin) && cin == cout) {   // [cout][tap][plane][cin] for gemm_tc
+    if (!transposed && key.rfind("resblocks.", 0) == 0 && tc_level(cin) && cin == cout && cin < 64) {   // time-folded form
+      const int f = fold_of(cin), cc = (k - 1) / 2;
+      std::vector<int> offs;
+      for (int so = 0; so < f; ++so)
+        for (int tp = 0; tp < k; ++tp) {
+          const int o = floordiv(so + (tp - cc) * dil, f);
+          if (std::find(offs.begin(), offs.end(), o) == offs.end()) offs.push_back(o);
+        }
+      std::sort(offs.begin(), offs.end());
+      if ((int)offs.size() <= 24) {
+        const int nt = (int)offs.size(), W = 64;
+        std::vector<float> tt((size_t)W * nt * W, 0.f), bb((size_t)W);
+        for (int so = 0; so < f; ++so)
+          for (int co = 0; co < cout; ++co) {
+            const size_t n = (size_t)so * cout + co;
+            bb[n] = itb->second.first[co];
+            for (int j = 0; j < nt; ++j)
+              for (int si = 0; si < f; ++si) {
+                const int delta = f * offs[j] + si - so;
+                if (delta % dil) continue;
+                const int tp = delta / dil + cc;
+                if (tp < 0 || tp >= k) continue;
+                for (int ci = 0; ci < cin; ++ci) tt[(n * nt + j) * W + (size_t)si * cin + ci] = src[((size_t)co * cin + ci) * k + tp];
+              }
+          }
+        fixh.emplace_back(&p.wh, pkh.add(tt.data(), (size_t)W * nt, W, 2));
+        put(&p.b_rep, bb.data(), bb.size());
+        p.fold = f; p.ntaps = nt;
+        for (int j = 0; j < nt; ++j) p.tap_off[j] = offs[j];
+      }
+    } else if (!transposed && key.rfind("resblocks.", 0) == 0 && tc_level(cin) && cin == cout) {   // [cout][tap][plane][cin] for gemm_tc
       std::vector<float> tt((size_t)cout * k * cin);
       for (int co = 0; co < cout; ++co)
         for (int ci = 0; ci < cin; ++ci)
@@ -424,10 +464,10 @@ int lds_vocoder_finalize(lds_vocoder* v) {
       if (c.resblock_kind == 1) v->rb2[n].assign(nconv, ConvP());
       for (int q = 0; ok && q < nconv; ++q) {
         if (c.resblock_kind == 1) {
-          ok = conv(v->rb1[n][q], rk + ".convs1." + std::to_string(q), ch, ch, k, false) &&
-               conv(v->rb2[n][q], rk + ".convs2." + std::to_string(q), ch, ch, k, false);
+          ok = conv(v->rb1[n][q], rk + ".convs1." + std::to_string(q), ch, ch, k, false, 0, c.resblock_dilations[j][q]) &&
+               conv(v->rb2[n][q], rk + ".convs2." + std::to_string(q), ch, ch, k, false, 0, 1);
         } else {
-          ok = conv(v->rb1[n][q], rk + ".convs." + std::to_string(q), ch, ch, k, false);
+          ok = conv(v->rb1[n][q], rk + ".convs." + std::to_string(q), ch, ch, k, false, 0, c.resblock_dilations[j][q]);
         }
       }
     }
@@ -513,9 +553,9 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
   int ch = c.upsample_initial_channel;
   int64_t L = T;
   auto conv_tc = [&](const __nv_bfloat16* A, int rows_per_utt, int cin, int taps, int dil, const __nv_bfloat16* W, int N, const float* bias, int epi,
-                     const float* R, float* out_f32, __nv_bfloat16* out_planes) {
+                     const float* R, float* out_f32, __nv_bfloat16* out_planes, const int* tap_rows = nullptr) {
     TcGemmArgs g;
-    g.A = A; g.batches = B; g.rows = rows_per_utt; g.cin = cin; g.taps = taps; g.dil = dil; g.W = W; g.N = N; g.bias = bias;
+    g.A = A; g.batches = B; g.rows = rows_per_utt; g.cin = cin; g.taps = taps; g.dil = dil; g.W = W; g.N = N; g.bias = bias; g.tap_rows = tap_rows;
     tc_set_split_pairs(g);
     g.out_scale = 1.f / (PLANE_SCALE * v->wscale);
     g.epilogue = epi; g.act_slope = 0.1f;
@@ -528,7 +568,11 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
     const int64_t Lo = (L - 1) * u - 2 * ((k - u + 1) / 2) + k;
     float* xin = lv[0];          // level input, channels-first (output of the FFMA transposed convolution)
     float* xs = lv[1];           // running sum / mean of the resblocks, channels-first
-    const bool level_tc = tc_level(ch / 2) && v->rb1[(size_t)i * c.n_kernels][0].wh;
+    bool level_tc = tc_level(ch / 2) && Lo % fold_of(ch / 2) == 0;
+    for (int j = 0; level_tc && j < c.n_kernels; ++j) {            // every convolution of the level has its tensor-core form
+      for (const ConvP& w : v->rb1[(size_t)i * c.n_kernels + j]) level_tc = level_tc && w.wh;
+      for (const ConvP& w : v->rb2[(size_t)i * c.n_kernels + j]) level_tc = level_tc && w.wh;
+    }
     bool xin_is_cl = false;      // the level input lives in x_cl (channels-last) instead of xin
     if (v->ups[i].wh) {          // x = ups[i](leaky_relu(x, 0.1)) as a 3-tap implicit GEMM: [B*L, ch] -> [B*L, u*ch/2] == [B*Lo, ch/2]
       if (!x_cl_cur) {
@@ -553,7 +597,8 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
     L = Lo;
     if (level_tc) {
       // ---- tensor-core level: channels-last state, dilated convolutions as implicit GEMMs (gemm_tc.cu) ----
-      const int64_t rows = (int64_t)B * L;
+      const int f = fold_of(ch), Cw = ch * f, Lw = (int)(L / f);          // GEMM view: [B * Lw, Cw] (Cw = 64 on a folded level)
+      const int64_t rows = (int64_t)B * Lw;
       if (!xin_is_cl) VTRY(ck(launch_transpose_bct_to_btc(xin, x_cl, B, ch, (int)L, 1.f, s), "transpose to channels-last"));
       for (int j = 0; j < c.n_kernels; ++j) {
         const int n = i * c.n_kernels + j;
@@ -563,21 +608,23 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
           const int d = c.resblock_dilations[j][q];
           const bool last = q == nconv - 1;
           float* dst = last ? (j == 0 ? xs_cl : lv[4]) : (cur == lv[2] ? lv[3] : lv[2]);
-          VTRY(ck(launch_lrelu_split_cast(cur, a_p, rows, ch, 2, 0.1f, s), "lrelu_split_cast"));
+          VTRY(ck(launch_lrelu_split_cast(cur, a_p, rows, Cw, 2, 0.1f, s), "lrelu_split_cast"));
+          auto rconv = [&](const __nv_bfloat16* A, const ConvP& w, int dil, int epi, const float* R, float* out_f32, __nv_bfloat16* out_planes) {
+            return f > 1 ? conv_tc(A, Lw, Cw, w.ntaps, 1, w.wh, Cw, w.b_rep, epi, R, out_f32, out_planes, w.tap_off)
+                         : conv_tc(A, Lw, Cw, w.k, dil, w.wh, Cw, w.b, epi, R, out_f32, out_planes);
+          };
           if (c.resblock_kind == 1) {     // xt = c2(lrelu(c1(lrelu(x)))); x = xt + x   (models.py:186-193)
-            const ConvP &w1 = v->rb1[n][q], &w2 = v->rb2[n][q];
-            VTRY(ck(conv_tc(a_p, (int)L, ch, w1.k, d, w1.wh, ch, w1.b, EPI_LRELU, nullptr, nullptr, t_p), "resblock conv1 (tc)"));
-            VTRY(ck(conv_tc(t_p, (int)L, ch, w2.k, 1, w2.wh, ch, w2.b, EPI_NONE, cur, dst, nullptr), "resblock conv2 (tc)"));
+            VTRY(ck(rconv(a_p, v->rb1[n][q], d, EPI_LRELU, nullptr, nullptr, t_p), "resblock conv1 (tc)"));
+            VTRY(ck(rconv(t_p, v->rb2[n][q], 1, EPI_NONE, cur, dst, nullptr), "resblock conv2 (tc)"));
             flops += 2.0 * 2.0 * B * L * ch * ch * c.resblock_kernel_sizes[j];
           } else {                        // xt = c(lrelu(x)); x = xt + x   (models.py:214-217)
-            const ConvP& w1 = v->rb1[n][q];
-            VTRY(ck(conv_tc(a_p, (int)L, ch, w1.k, d, w1.wh, ch, w1.b, EPI_NONE, cur, dst, nullptr), "resblock conv (tc)"));
+            VTRY(ck(rconv(a_p, v->rb1[n][q], d, EPI_NONE, cur, dst, nullptr), "resblock conv (tc)"));
             flops += 2.0 * B * L * ch * ch * c.resblock_kernel_sizes[j];
           }
           cur = dst;
         }
         if (j > 0) {                      // xs += r_j ; the last one also divides by num_kernels (models.py:243-251)
-          const int64_t n4 = rows * ch / 4;
+          const int64_t n4 = rows * Cw / 4;
           voc_acc_kernel<<<(unsigned)std::min<int64_t>((n4 + 255) / 256, 2368), 256, 0, s>>>(
               reinterpret_cast<float4*>(xs_cl), reinterpret_cast<const float4*>(lv[4]), n4, j == c.n_kernels - 1 ? 2 : 1, (float)c.n_kernels);
           VTRY(ck(cudaGetLastError(), "resblock mean"));
