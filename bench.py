@@ -312,7 +312,7 @@ def tf32_peak(dev) -> dict:
 def vocoder_leg(dev, B: int = 16, T: int = 864) -> dict:
     """HiFi-VAEGAN Generator decode of B x T latent frames to 44.1 kHz audio through the library
     (csrc/vocoder.cu: the transposed convolutions and every ResBlock level as split-f16 tensor-core implicit GEMMs — the 32-channel level
-    time-folded onto 64-wide K blocks — conv_pre / conv_post fp32 FFMA) — the step that turns
+    time-folded onto 64-wide K blocks — conv_post fp32 FFMA) — the step that turns
     the headline's mel frames into waveforms; random-init weights of the HiFi-GAN V1 layout (latent_diffusion_speech_b200/vocoder.py
     DEFAULT_H)."""
     import torch
@@ -335,7 +335,7 @@ def vocoder_leg(dev, B: int = 16, T: int = 864) -> dict:
     out = {"workload": f"hifi-vaegan generator decode, B={B} x T={T} frames -> {wav.shape[-1]} samples each, fp32", "ms_per_step": ms,
            "value": B * T / (ms * 1e-3), "unit": "frames/s", "rtf": (ms * 1e-3) / (B * T / FRAME_RATE),
            "tflops": eng.last_flops / (ms * 1e-3) / 1e12, "flops_per_frame": eng.last_flops / (B * T),
-           "arithmetic": "transposed convolutions + all ResBlock levels (32-channel level time-folded): split-f16 tcgen05 implicit GEMMs (fp32-accurate); conv_pre/post: fp32 FFMA",
+           "arithmetic": "transposed convolutions + all ResBlock levels (32-channel level time-folded): split-f16 tcgen05 implicit GEMMs (fp32-accurate), conv_pre too; conv_post: fp32 FFMA",
            "finite": bool(torch.isfinite(wav).all())}
     voc.generator._invalidate()
     del voc, mel, wav

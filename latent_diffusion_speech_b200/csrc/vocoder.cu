@@ -15,7 +15,8 @@
 //     epilogue, bias + residual in the second one's;
 //   * the transposed convolutions (kernel 2u, stride u) are one 3-tap implicit GEMM each with N = u * C_out (lds_vocoder_finalize);
 //   * the 32-channel level is time-folded onto the same kernel (fold_of below): two frames per GEMM row, block-sparse folded taps;
-//   * conv_pre and conv_post (and any layer the GEMM forms do not cover) stay channels-FIRST fp32 [B, C, L] on the CUDA cores: IEEE
+//   * conv_pre (128 -> 512, k7) is a plain 7-tap implicit GEMM on the mel frames, which already are its channels-last operand;
+//   * conv_post (and any layer the GEMM forms do not cover) stays channels-FIRST fp32 [B, C, L] on the CUDA cores: IEEE
 //     FFMA, register-blocked direct convolution (8 output channels x 8 time steps per thread, input slab with its dilated halo and the [ci][tap][co] weight slab staged in shared memory,
 //     leaky_relu applied once while staging).
 #include <cuda_runtime.h>
@@ -358,7 +359,7 @@ int lds_vocoder_finalize(lds_vocoder* v) {
   {
     float wmax = 0.f;
     for (const auto& kv : v->raw)
-      if ((kv.first.rfind("resblocks.", 0) == 0 || kv.first.rfind("ups.", 0) == 0) && kv.second.second.size() == 3)
+      if ((kv.first.rfind("resblocks.", 0) == 0 || kv.first.rfind("ups.", 0) == 0 || kv.first.rfind("conv_pre.", 0) == 0) && kv.second.second.size() == 3)
         for (float x : kv.second.first) wmax = std::max(wmax, std::fabs(x));
     float sc = 4096.f;
     while (sc > 1.f && wmax * sc >= 16384.f) sc *= 0.5f;
@@ -438,7 +439,8 @@ int lds_vocoder_finalize(lds_vocoder* v) {
         p.fold = f; p.ntaps = nt;
         for (int j = 0; j < nt; ++j) p.tap_off[j] = offs[j];
       }
-    } else if (!transposed && key.rfind("resblocks.", 0) == 0 && tc_level(cin) && cin == cout) {   // [cout][tap][plane][cin] for gemm_tc
+    } else if (!transposed && ((key.rfind("resblocks.", 0) == 0 && tc_level(cin) && cin == cout) ||
+                               (key == "conv_pre" && cin % 64 == 0 && cout % 64 == 0 && k % 2 == 1 && k <= 11))) {   // [cout][tap][plane][cin] for gemm_tc
       std::vector<float> tt((size_t)cout * k * cin);
       for (int co = 0; co < cout; ++co)
         for (int ci = 0; ci < cin; ++ci)
@@ -539,12 +541,13 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
     return e == cudaSuccess ? LDS_OK : vfail(LDS_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   };
 #define VTRY(expr) do { int rc__ = (expr); if (rc__ != LDS_OK) return rc__; } while (0)
-  {  // Hifi_VAEGAN.forward: z = mel.transpose(-1, -2)
+  if (!(v->conv_pre.wh && v->ups[0].wh)) {  // Hifi_VAEGAN.forward: z = mel.transpose(-1, -2)
     dim3 grid((c.inter_channels + 31) / 32, (T + 31) / 32, B), block(32, 8);
     voc_transpose_kernel<<<grid, block, 0, s>>>(mel_BTC, zt, T, c.inter_channels);
     VTRY(ck(cudaGetLastError(), "voc_transpose"));
   }
-  VTRY(ck(launch_conv(zt, v->conv_pre, nullptr, pre, B, T, 1, 1.f, 0, 1.f, 0, s), "conv_pre"));
+  const bool pre_tc = v->conv_pre.wh && v->ups[0].wh;     // conv_pre on the tensor cores: the mel [B, T, C] IS its channels-last operand
+  if (!pre_tc) VTRY(ck(launch_conv(zt, v->conv_pre, nullptr, pre, B, T, 1, 1.f, 0, 1.f, 0, s), "conv_pre"));
   flops += 2.0 * B * T * c.inter_channels * c.upsample_initial_channel * 7;
   // The state between levels is either channels-first (x_cf: the FFMA kernels) or channels-last (x_cl_cur: the tensor-core kernels);
   // a transpose is inserted only where the form changes (after conv_pre, and before the first level that stays on the CUDA cores).
@@ -563,6 +566,12 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
     else { g.C = out_f32; g.c_ld = N; g.out_kind = 0; g.R = R; g.r_ld = N; }
     return launch_gemm_tc(g, s);
   };
+  if (pre_tc) {                  // x = conv_pre(z) as a k7 implicit GEMM straight from the mel frames (no transpose either side)
+    VTRY(ck(launch_split_cast(mel_BTC, a_p, (int64_t)B * T, c.inter_channels, 2, s), "split_cast"));
+    VTRY(ck(conv_tc(a_p, T, c.inter_channels, v->conv_pre.k, 1, v->conv_pre.wh, ch, v->conv_pre.b, EPI_NONE, nullptr, xs_cl, nullptr), "conv_pre (tc)"));
+    x_cl_cur = xs_cl;
+    x_cf = nullptr;
+  }
   for (int i = 0; i < c.n_ups; ++i) {
     const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
     const int64_t Lo = (L - 1) * u - 2 * ((k - u + 1) / 2) + k;
