@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False, debug_knobs: bool = False)
     """debug_knobs=True builds liblds_b200_dbg.so with -DLDS_DEBUG_KNOBS (timing experiments that skip stores / epilogues;
     wrong results by construction — never the product library; load it with LDS_B200_LIB=...)."""
     if debug_knobs:
-        return _build(os.path.join(HERE, "liblds_b200_dbg.so"), os.path.join(HERE, "build", "dbg"), ["-DLDS_DEBUG_KNOBS"], verbose)
+        extra = ["-DLDS_DEBUG_KNOBS"] + os.environ.get("LDS_EXTRA_NVCC_FLAGS", "").split()      # experiment builds only
+        return _build(os.path.join(HERE, "liblds_b200_dbg.so"), os.path.join(HERE, "build", "dbg"), extra, verbose)
     if not force and not _stale():
         return LIB_PATH
     return _build(LIB_PATH, os.path.join(HERE, "build"), [], verbose)

@@ -57,7 +57,10 @@
 namespace lds {
 namespace {
 
-constexpr int TBM = 128, TBK = 64, N_EPI_WARPS = 8, TC_THREADS = 64 + 32 * N_EPI_WARPS;
+#ifndef LDS_N_EPI_WARPS
+#define LDS_N_EPI_WARPS 8      // 16 only in experiment builds (debug-knob library; the TMA epilogue's tile rings do not fit then)
+#endif
+constexpr int TBM = 128, TBK = 64, N_EPI_WARPS = LDS_N_EPI_WARPS, TC_THREADS = 64 + 32 * N_EPI_WARPS;
 constexpr int EPI_PARTS = N_EPI_WARPS / 4;          // epilogue warps per TMEM lane quarter: they interleave the 32-column chunks
 constexpr int A_SLOT_BYTES = TBM * TBK * 2;         // 16 KB: 128 rows x 128 B
 constexpr int MAX_SLOTS = 8;                        // per ring
