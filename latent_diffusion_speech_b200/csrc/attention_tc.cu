@@ -4,12 +4,14 @@
 // path.  Operands come from the fused QKV projection whose epilogue (gemm_tc.cu, out_kind 3) writes
 //   Q, K : bf16 planes [B*T][parts][H][dpad]          (head dim padded to 32/64, pad columns are exact zeros)
 //   V^T  : bf16 planes [B][parts][H][dpad][T_pad]      (keys contiguous -> K-major B operand of the P*V product)
-// so that every MMA operand is a K-major, TMA-swizzled tile.  parts = 1: bf16 mode.  parts = 3: fp32-accurate mode,
-// both products are evaluated as the six significant plane products (split-bf16), softmax in fp32 with expf.
+// so that every MMA operand is a K-major, TMA-swizzled tile.  parts = 1: bf16 mode.  parts = 2: fp32-accurate mode (split-f16,
+// planes.cuh): Q, K, V^T and the probabilities P are two fp16 planes of the scaled value each, both products are evaluated as the
+// three plane products x1*y1 + x1*y2 + x2*y1, softmax in fp32.  parts = 3: round 1's three bf16 planes / six products (kept for A/B
+// through lds_op_qkv_attention_tc).
 //
 // Work item = 128 queries of one (utterance, head); persistent CTAs stride over the items; keys stream in tiles of 64.
 // Two passes over the keys:
-//   pass A: S ~ Q_hi K_hi^T (one plane product: the maximum is only needed to ~1 %) -> TMEM, softmax warps reduce the
+//   pass A: S ~ Q_1 K_1^T (first planes only: the maximum is only needed to ~1 %) -> TMEM, softmax warps reduce the
 //           row maximum m (no exponentials)
 //   pass B: S again, P = exp(S*scale - m) (fp32), row sums in registers, P planes -> shared memory (128B-swizzled,
 //           K-major), O += P V accumulated in TMEM across all key tiles with the accumulate flag (m is final, so O
@@ -257,7 +259,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         umma_commit_elect(s_full(sb));
         k_advance();
       };
-      // pass-B tile `jb`: the six (one) plane products of Q K^T
+      // pass-B tile `jb`: the plane products of Q K^T (three in split-f16 mode, issued as two instructions; one in bf16 mode)
       auto issue_qk_b = [&](int jb, bool last) {
         const int sb = NSB == 1 ? 0 : (jb & 1);
         mbar_wait(k_full(ks), kph);

@@ -90,7 +90,7 @@ cudaError_t launch_gemm_f32(const GemmArgs& a, cudaStream_t s);
 //  1 / (scale_A * scale_W) — three tensor-core products per logical product.
 //  taps in {3, 5, 7, 9, 11}: stride-1 'same' convolution along `rows` with dilation `dil` (tap t reads row r + (t - (taps-1)/2) * dil;
 //  TMA out-of-bounds fill = zero padding).
-//  out_kind: 0 fp32 [*, c_ld], 1 bf16 [*, c_ld], 2 three bf16 planes of c_ld/3 columns each,
+//  out_kind: 0 fp32 [*, c_ld], 1 bf16 [*, c_ld], 2 split-f16 planes [h1 | h2] of c_ld/2 columns each,
 //            3 attention operands of a fused QKV projection with N = 3*H*dpad columns ([q | k | v], head dim padded
 //              to dpad): q_out/k_out planes [rows][parts][H*dpad], vt_out planes [B][parts][H][dpad][T_pad] (V transposed,
 //              keys contiguous) — the layouts attention_tc.cu loads with TMA.
