@@ -412,6 +412,30 @@ def units_leg(dev, B: int = 8, L: int = 3000) -> dict:
     return out
 
 
+def train_loss_leg(model, units, spk, dev, steps: int = 3) -> dict:
+    """SURVEY.md §8(f) rank 4, forward half: Unit2Mel.forward(infer=False) — per-utterance q_sample, ONE denoiser evaluation with
+    per-utterance timesteps and the l2 loss (diffusion.py:173-201) — on the headline batch; no backward pass exists in this library."""
+    import torch
+    B, T = units.shape[0], units.shape[1]
+    g = torch.Generator(device=dev).manual_seed(11)
+    gt = torch.rand(B, T, 128, generator=g, device=dev) * 14 - 12
+    noise = torch.randn(B, 1, 128, T, generator=g, device=dev)
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(5))
+    for _ in range(2):
+        loss = model(units, None, spk_id=spk, gt_spec=gt, infer=False, t=t, noise=noise)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = model(units, None, spk_id=spk, gt_spec=gt, infer=False, t=t, noise=noise)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": f"Unit2Mel.forward(infer=False): p_losses forward, B={B} x T={T}, per-utterance timesteps, l2", "ms_per_step": ms,
+            "value": B * T / (ms * 1e-3), "unit": "frames/s", "loss": float(loss), "model_tflops_per_s": B * flops_per_utt_nfe(T) / (ms * 1e-3) / 1e12,
+            "note": "forward only (validation loss, diffusion/solver.py:56-62); backward / optimiser / DP all-reduce are not built"}
+
+
 def strong_leg(dev, world: int, rank: int, steps: int) -> dict:
     """BASELINE configs[2]: global batch 512 x T=864, bf16 mode, UniPC 10 NFE, split 512/N across the ranks (strong scaling) through
     distributed.sharded_infer; inputs and noise are seeded PER UTTERANCE (global index), so the gathered mel is bit-identical at
@@ -610,6 +634,12 @@ def run_ours(args):
 
     # ---- context legs (outside the timed regions above) ----
     workspace_bytes = eng.workspace_bytes
+    train_loss = None
+    if world == 1 and not args.no_train_loss and precision != "fp32_ffma":
+        try:
+            train_loss = train_loss_leg(model, units_d, spk_d, dev)
+        except Exception as ex:
+            train_loss = {"error": repr(ex)[:300]}
     model.invalidate_engine()
     del model, eng, units_d, noise
     torch.cuda.empty_cache()
@@ -667,6 +697,7 @@ def run_ours(args):
             "strong": strong,
             "vocoder": vocoder,
             "units_frontend": units_fe,
+            "train_loss_forward": train_loss,
             "pipeline_rtf": pipeline,
             "kernel_classes": classes,
             "model_tflops_per_s": B * world * nfe * flops_per_utt_nfe(T) / (ms_step * 1e-3) / 1e12,
@@ -691,6 +722,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-vocoder", action="store_true")
     ap.add_argument("--no-units", action="store_true")
+    ap.add_argument("--no-train-loss", action="store_true")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:   # convenience: self-launch one rank per GPU
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

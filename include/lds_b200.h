@@ -149,6 +149,17 @@ LDS_API int lds_sample(lds_handle* h, const float* cond_BTH, const float* x_init
                float* mel_BTM, void* stream);
 LDS_API int lds_num_steps(const lds_handle* h);
 
+/* Training-loss FORWARD (GaussianDiffusion.forward with infer=False -> p_losses, diffusion/diffusion.py:173-201; the validation loss of
+ * diffusion/solver.py:56-62): one denoiser evaluation with PER-UTTERANCE timesteps and the l1 / l2 loss against the injected noise.
+ *   x_noisy[b] = sqrt_acp[b] * (gt_spec[b] * acoustic_scale) + sqrt_1m_acp[b] * noise[b]         (q_sample, :169-171)
+ *   eps        = unet(cat(x_noisy, cond^T), t)        t_sinusoid: host [B, block_out_channels[0]], one row per utterance
+ *   *loss      = mean |noise - eps|  (loss_type 1)   or   mean (noise - eps)^2  (loss_type 2, the reference's default)
+ * sqrt_acp / sqrt_1m_acp: host [B] = sqrt_alphas_cumprod[t_b] / sqrt_one_minus_alphas_cumprod[t_b]; noise [B, out_dims, T]; loss: one device
+ * float; eps_BMT (optional) receives the prediction in the reference layout.  Needs lds_plan(B, T, ...) (any sampler program).  The
+ * reduction is deterministic (fp64 partial sums in a fixed order).  Backward / optimiser steps are not part of this library. */
+LDS_API int lds_train_loss(lds_handle* h, const float* cond_BTH, const float* gt_spec_BTM, const float* noise_BMT, const float* t_sinusoid,
+                   const float* sqrt_acp, const float* sqrt_1m_acp, int loss_type, float* loss, float* eps_BMT, void* stream);
+
 /* Introspection used by bench.py / tests. */
 LDS_API int64_t lds_workspace_bytes(const lds_handle* h);
 LDS_API int64_t lds_kernel_launches(const lds_handle* h);   /* kernels launched by this handle so far */

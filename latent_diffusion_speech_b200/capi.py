@@ -23,7 +23,7 @@ DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 EXPORTS = [
     "lds_version", "lds_last_error", "lds_create", "lds_destroy", "lds_load_weight", "lds_finalize_weights",
     "lds_plan", "lds_cond", "lds_denoise", "lds_sample_begin", "lds_sample_begin_shallow", "lds_sample_steps", "lds_sample_end",
-    "lds_sample",
+    "lds_sample", "lds_train_loss",
     "lds_num_steps", "lds_workspace_bytes", "lds_kernel_launches", "lds_set_profiling", "lds_profile_num_classes",
     "lds_profile_class_name", "lds_profile_class_ms", "lds_profile_class_launches", "lds_profile_class_flops",
     "lds_profile_class_bytes", "lds_op_gemm", "lds_op_attention", "lds_op_groupnorm", "lds_op_groupnorm_fused", "lds_op_groupnorm_cluster", "lds_op_layernorm",
@@ -81,6 +81,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "lds_sample_steps": (i32, [vp, i32, i32, vp, vp]),
         "lds_sample_end": (i32, [vp, vp, vp]),
         "lds_sample": (i32, [vp, vp, vp, vp, vp, vp]),
+        "lds_train_loss": (i32, [vp, vp, vp, vp, fp, fp, fp, i32, vp, vp, vp]),
         "lds_num_steps": (i32, [vp]),
         "lds_workspace_bytes": (C.c_int64, [vp]),
         "lds_kernel_launches": (C.c_int64, [vp]),
@@ -248,6 +249,23 @@ class Engine:
                                              C.c_void_p(eps.data_ptr()), self._stream()), "lds_denoise")
         self._keep = [x, cond]
         return eps
+
+    def train_loss(self, cond_bth: torch.Tensor, gt_spec_btm: torch.Tensor, noise_bmt: torch.Tensor, t_sin: np.ndarray,
+                   sqrt_acp: np.ndarray, sqrt_1m_acp: np.ndarray, loss_type: str = "l2", return_eps: bool = False):
+        """p_losses forward (diffusion.py:173-187): per-utterance q_sample, one denoiser evaluation with per-utterance timesteps,
+        l1 / l2 loss against the noise.  Returns the 0-dim loss tensor (and the prediction [B, M, T] when asked)."""
+        cond, gt, nz = self._dev(cond_bth), self._dev(gt_spec_btm), self._dev(noise_bmt)
+        ts = np.ascontiguousarray(t_sin, dtype=np.float32)
+        sa, sb = np.ascontiguousarray(sqrt_acp, dtype=np.float32), np.ascontiguousarray(sqrt_1m_acp, dtype=np.float32)
+        if ts.shape[0] != self.B or sa.shape[0] != self.B or sb.shape[0] != self.B:
+            raise ValueError("one timestep / coefficient pair per utterance is required")
+        loss = torch.empty((), device=self.device, dtype=torch.float32)
+        eps = torch.empty_like(nz) if return_eps else None
+        check(self.lib, self.lib.lds_train_loss(self.handle, C.c_void_p(cond.data_ptr()), C.c_void_p(gt.data_ptr()), C.c_void_p(nz.data_ptr()),
+                                                _fptr(ts), _fptr(sa), _fptr(sb), {"l1": 1, "l2": 2}[loss_type], C.c_void_p(loss.data_ptr()),
+                                                C.c_void_p(eps.data_ptr()) if eps is not None else None, self._stream()), "lds_train_loss")
+        self._keep = [cond, gt, nz]
+        return (loss, eps) if return_eps else loss
 
     def sample_begin(self, cond_bth: torch.Tensor, x_init_bmt: torch.Tensor) -> None:
         cond, x = self._dev(cond_bth), self._dev(x_init_bmt)

@@ -162,6 +162,9 @@ struct lds_handle {
   __nv_bfloat16 *norm_b = nullptr, *raw_b = nullptr, *tmp2_b = nullptr, *xn_b = nullptr, *att_b = nullptr, *ffh_b = nullptr,
                 *th_b = nullptr, *cast_b = nullptr, *q_b = nullptr, *k_b = nullptr, *vt_b = nullptr;
   const float* cond_bound = nullptr;
+  float* tb_arena = nullptr;                // per-utterance time conditioning + loss partials of the training-loss forward (grow-only)
+  size_t tb_cap = 0;
+  int64_t ss_bstride = 0;                   // floats between the scale-shift rows of consecutive utterances (0: one row per batch)
   int m_cur = 0;                            // index of m0 in mbuf; m1 = (m_cur+2)%3, free = (m_cur+1)%3
   // bookkeeping
   int64_t launches = 0;
@@ -269,7 +272,8 @@ int run_gn(lds_handle* h, cudaStream_t s, const float* x1, int c1, const float* 
   LDS_TRY(launched(h, s, PC_GN_STATS, 0, 4.0 * elems, launch_gn_stats(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, s),
                    "gn_stats"));
   return launched(h, s, PC_GN_APPLY, 0, 8.0 * elems,
-                  launch_gn_apply(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, eps, n.g, n.b, ss, silu, y, nullptr, 1, nullptr, s),
+                  launch_gn_apply(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, eps, n.g, n.b, ss, silu, y, nullptr, 1, nullptr, s,
+                                  h->ss_bstride),
                   "gn_apply");
 }
 
@@ -361,12 +365,14 @@ int run_gn_planes(lds_handle* h, cudaStream_t s, const float* x1, int c1, const 
   // LDS_GN_MODE: 2 (default) cluster single-pass kernel; 1 one-CTA-per-(utterance, group) single pass; 0 stats + apply
   const int gn_mode = knobs().gn_mode;
   if (gn_mode == 2) {
-    const cudaError_t e = launch_gn_cluster(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, eps, n.g, n.b, ss, silu, nullptr, yb, h->parts, rawb, s);
+    const cudaError_t e = launch_gn_cluster(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, eps, n.g, n.b, ss, silu, nullptr, yb, h->parts, rawb, s,
+                                            h->ss_bstride);
     if (e != cudaErrorNotSupported)
       return launched(h, s, PC_GN_APPLY, 0, (4.0 + 2.0 * h->parts * (rawb ? 2 : 1)) * elems, e, "gn_cluster");
   }
   if (gn_mode == 1 && (int64_t)h->B * h->cfg.norm_groups >= 148) {  // single pass when the slab of one (utterance, group) fits shared memory and there is a CTA per SM
-    const cudaError_t e = launch_gn_fused(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, eps, n.g, n.b, ss, silu, nullptr, yb, h->parts, rawb, s);
+    const cudaError_t e = launch_gn_fused(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, eps, n.g, n.b, ss, silu, nullptr, yb, h->parts, rawb, s,
+                                          h->ss_bstride);
     if (e != cudaErrorNotSupported)
       return launched(h, s, PC_GN_APPLY, 0, (4.0 + 2.0 * h->parts * (rawb ? 2 : 1)) * elems, e, "gn_fused");
   }
@@ -374,7 +380,7 @@ int run_gn_planes(lds_handle* h, cudaStream_t s, const float* x1, int c1, const 
                    "gn_stats"));
   return launched(h, s, PC_GN_APPLY, 0, (4.0 + 2.0 * h->parts * (rawb ? 2 : 1)) * elems,
                   launch_gn_apply(x1, c1, x2, c2, h->B, T, h->cfg.norm_groups, h->gn_part, eps, n.g, n.b, ss, silu, nullptr, yb,
-                                  h->parts, rawb, s), "gn_apply");
+                                  h->parts, rawb, s, h->ss_bstride), "gn_apply");
 }
 int run_ln_planes(lds_handle* h, cudaStream_t s, const float* x, const NormW& n, int rows, int C, __nv_bfloat16* yb) {
   return launched(h, s, PC_LAYERNORM, 0, (4.0 + 2.0 * h->parts) * rows * C,
@@ -666,6 +672,7 @@ void lds_destroy(lds_handle* h) {
   cudaDeviceSynchronize();
   if (h->arena) cudaFree(h->arena);
   if (h->temb_arena) cudaFree(h->temb_arena);
+  if (h->tb_arena) cudaFree(h->tb_arena);
   if (h->warena) cudaFree(h->warena);
   if (h->wharena) cudaFree(h->wharena);
   if (h->barena) cudaFree(h->barena);
@@ -1158,6 +1165,54 @@ int lds_denoise(lds_handle* h, const float* x_BMT, const float* cond_BTH, const 
   LDS_TRY(run_unet(h, s, h->io_a, h->temb_single, h->io_b));
   return launched(h, s, PC_LAYOUT, 0, 8.0 * h->B * h->T * c.out_dims,
                   launch_transpose_btc_to_bct(h->io_b, eps_BMT, h->B, c.out_dims, h->T, 1.f, s), "transpose");
+}
+
+int lds_train_loss(lds_handle* h, const float* cond_BTH, const float* gt_spec_BTM, const float* noise_BMT, const float* t_sinusoid,
+                   const float* sqrt_acp, const float* sqrt_1m_acp, int loss_type, float* loss, float* eps_BMT, void* stream) {
+  if (!h || !h->planned) return fail(LDS_ERR_INVALID, "lds_train_loss: call lds_plan first");
+  if (!cond_BTH || !gt_spec_BTM || !noise_BMT || !t_sinusoid || !sqrt_acp || !sqrt_1m_acp || !loss) return fail(LDS_ERR_INVALID, "lds_train_loss: null argument");
+  if (loss_type != 1 && loss_type != 2) return fail(LDS_ERR_INVALID, "lds_train_loss: loss_type must be 1 (l1) or 2 (l2)");
+  if (h->sticky != cudaSuccess) return fail(LDS_ERR_CUDA, "handle is in a failed state: %s", cudaGetErrorString(h->sticky));
+  cudaStream_t s = (cudaStream_t)stream;
+  LDS_CK(h, cudaSetDevice(h->device));
+  const lds_config& c = h->cfg;
+  const int B = h->B, T = h->T, M = c.out_dims, c0 = c.block_out_channels[0], D = h->temb_dim;
+  // per-utterance time conditioning: [B, temb_total] table + the MLP scratch for B rows + the loss partials (grow-only; growing synchronises)
+  auto r64 = [](size_t n) { return (n + 63) / 64 * 64; };
+  const size_t n_part = (size_t)B * ((T + 31) / 32) * ((M + 31) / 32);
+  const size_t o_tab = 0, o_sin = o_tab + r64((size_t)B * h->temb_total), o_e1 = o_sin + r64((size_t)B * c0), o_e2 = o_e1 + r64((size_t)B * D),
+               o_part = o_e2 + r64((size_t)B * D), total = o_part + r64(2 * n_part);
+  if (total > h->tb_cap) {
+    LDS_CK(h, cudaDeviceSynchronize());
+    if (h->tb_arena) { cudaFree(h->tb_arena); h->tb_arena = nullptr; h->tb_cap = 0; }
+    LDS_CK(h, cudaMalloc(&h->tb_arena, total * sizeof(float)));
+    h->tb_cap = total;
+  }
+  float* table = h->tb_arena + o_tab;
+  if (h->prof.enabled) { prof_reset(h); LDS_TRY(prof_mark(h, s)); }
+  {  // timestep MLP + every time_emb_proj for the B timesteps (unet_1d_condition.py:841-848 with t of shape [B])
+    float *sv_sin = h->sin_dev, *sv_e1 = h->e1, *sv_e2 = h->e2;
+    h->sin_dev = h->tb_arena + o_sin; h->e1 = h->tb_arena + o_e1; h->e2 = h->tb_arena + o_e2;
+    const int rc = run_temb(h, s, t_sinusoid, B, table);
+    h->sin_dev = sv_sin; h->e1 = sv_e1; h->e2 = sv_e2;
+    LDS_TRY(rc);
+  }
+  // x_noisy = q_sample(norm_spec(gt_spec), t, noise) with per-utterance coefficients (diffusion.py:169-171,176), channels-last
+  for (int b = 0; b < B; ++b)
+    LDS_TRY(launched(h, s, PC_SOLVER, 0, 16.0 * T * M,
+                     launch_q_sample(h->io_a + (size_t)b * T * M, gt_spec_BTM + (size_t)b * T * M, noise_BMT + (size_t)b * M * T, c.acoustic_scale,
+                                     sqrt_acp[b], sqrt_1m_acp[b], 1, T, M, s), "q_sample"));
+  LDS_TRY(bind_cond(h, s, cond_BTH));
+  h->ss_bstride = h->temb_total;
+  const int rc = run_unet(h, s, h->io_a, table, h->io_b);       // x_recon = denoise_fn(cat(x_noisy, cond), t) (diffusion.py:177-178)
+  h->ss_bstride = 0;
+  LDS_TRY(rc);
+  LDS_TRY(launched(h, s, PC_SOLVER, 0, 8.0 * B * T * M,
+                   launch_diffusion_loss(h->io_b, noise_BMT, B, T, M, loss_type == 1, reinterpret_cast<double*>(h->tb_arena + o_part), loss, s),
+                   "diffusion_loss"));
+  if (eps_BMT)
+    LDS_TRY(launched(h, s, PC_LAYOUT, 0, 8.0 * B * T * M, launch_transpose_btc_to_bct(h->io_b, eps_BMT, B, M, T, 1.f, s), "transpose"));
+  return LDS_OK;
 }
 
 int lds_num_steps(const lds_handle* h) {

@@ -147,16 +147,18 @@ cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, in
                             cudaStream_t s);
 cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups,
                             const float* part, float eps, const float* gamma, const float* beta, const float* ss,
-                            int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s);
+                            int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s, int64_t ss_bstride = 0);
+// (ss_bstride: floats between the scale-shift rows of consecutive utterances — per-utterance timesteps of the training-loss forward;
+//  0 = one row for the whole batch, the sampler's case)
 // single-pass variant (slab of one (utterance, group) in shared memory); cudaErrorNotSupported when it does not fit
 cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
                             const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
-                            int parts, __nv_bfloat16* rawb, cudaStream_t s);
+                            int parts, __nv_bfloat16* rawb, cudaStream_t s, int64_t ss_bstride = 0);
 // cluster variant: the slab is split along time over a thread-block cluster of 1..8 CTAs (partials exchanged through
 // distributed shared memory) — small CTAs, several per SM, and slabs up to 8 x 200 KB stay single-pass
 cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
                               const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
-                              int parts, __nv_bfloat16* rawb, cudaStream_t s);
+                              int parts, __nv_bfloat16* rawb, cudaStream_t s, int64_t ss_bstride = 0);
 //  (yb != nullptr: write bf16 operand planes [B*T, parts*C] instead of fp32 y; rawb: also copy the un-normalised
 //   concat input as planes — the A operand of the 1x1 shortcut convolution)
 
@@ -193,6 +195,10 @@ cudaError_t launch_ddpm_step(float* x, const float* eps, const float* noise_BMT,
 cudaError_t launch_q_sample(float* x, const float* gt_BTM, const float* noise_BMT, float acoustic_scale, float sqrt_acp,
                             float sqrt_1m_acp, int B, int T, int M, cudaStream_t s);
 
+// Training loss (diffusion.py:181-185): mean |noise - eps| (l1) or mean (noise - eps)^2 (l2); eps [B,T,M] channels-last, noise [B,M,T];
+// partial: scratch of B * ceil(T/32) * ceil(M/32) doubles; deterministic two-stage reduction, loss: one device float
+cudaError_t launch_diffusion_loss(const float* eps_BTM, const float* noise_BMT, int B, int T, int M, int l1, double* partial, float* loss,
+                                  cudaStream_t s);
 // DDIM step: x = sqrt_aprev * (x / sqrt_at + coef * eps)                                   (diffusion.py:131)
 cudaError_t launch_ddim_step(float* x, const float* eps, float sqrt_at, float coef, float sqrt_aprev, int64_t n, cudaStream_t s);
 // PLMS step: out = x + d*(k1*x - k2*e'), e' = Adams-Bashforth combination selected by mode (solver.cu) (diffusion.py:134-167)

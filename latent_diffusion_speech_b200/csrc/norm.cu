@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                         float eps, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ ss,
                                                         int silu, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
-                                                        int parts, __nv_bfloat16* __restrict__ rawb) {
+                                                        int parts, __nv_bfloat16* __restrict__ rawb, long long ss_b) {
   __shared__ float s_mean[32], s_rstd[32];
   pdl_trigger();
   pdl_wait();
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
   float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sf = sc;
   if (ss) {
-    sc = __ldg(reinterpret_cast<const float4*>(ss + c));
-    sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+    sc = __ldg(reinterpret_cast<const float4*>(ss + (size_t)b * ss_b + c));
+    sf = __ldg(reinterpret_cast<const float4*>(ss + (size_t)b * ss_b + C + c));
   }
   const int t0 = chunk * slab, t1 = min(t0 + slab, T);
   constexpr int U = 8;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const float* __re
                                                                int T, int groups, float eps, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, const float* __restrict__ ss, int silu,
                                                                float* __restrict__ y, __nv_bfloat16* __restrict__ yb, int parts,
-                                                               __nv_bfloat16* __restrict__ rawb) {
+                                                               __nv_bfloat16* __restrict__ rawb, long long ss_b) {
   extern __shared__ float4 slab[];               // [T][q]
   __shared__ float red[GNF_THREADS / 32];
   __shared__ float s_bcast;
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const float* __re
   const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
   float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sf = sc;
   if (ss) {
-    sc = __ldg(reinterpret_cast<const float4*>(ss + c));
-    sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+    sc = __ldg(reinterpret_cast<const float4*>(ss + (size_t)b * ss_b + c));
+    sf = __ldg(reinterpret_cast<const float4*>(ss + (size_t)b * ss_b + C + c));
   }
   for (int t = r0; t < T; t += R) {
     const float4 xv = slab[t * q + v];
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(GNC_THREADS, 8) gn_cluster_kernel(const float*
                                                                     int T, int groups, int n_items, int tc, float eps,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                     const float* __restrict__ ss, float* __restrict__ y,
-                                                                    __nv_bfloat16* __restrict__ yb, __nv_bfloat16* __restrict__ rawb) {
+                                                                    __nv_bfloat16* __restrict__ yb, __nv_bfloat16* __restrict__ rawb, long long ss_b) {
   extern __shared__ float4 slab[];               // [2][tc][q]: frames [rank*tc, rank*tc + tc) of the group, two items
   __shared__ float red[GNC_THREADS / 32][3];     // per-warp (count, mean, M2)
   __shared__ float s_part[2][3];                 // this CTA's (count, mean, M2), read by its cluster peers; per item parity
@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(GNC_THREADS, 8) gn_cluster_kernel(const float*
       A = __ldg(reinterpret_cast<const float4*>(gamma + c));
       Bc = __ldg(reinterpret_cast<const float4*>(beta + c));
       if (SS) {
-        sc = __ldg(reinterpret_cast<const float4*>(ss + c));
-        sf = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+        sc = __ldg(reinterpret_cast<const float4*>(ss + (size_t)b * ss_b + c));
+        sf = __ldg(reinterpret_cast<const float4*>(ss + (size_t)b * ss_b + C + c));
       }
     }
     const float4* sp0 = slab + buf * buf_f4 + r0 * q + v;
@@ -685,7 +685,7 @@ cudaError_t launch_gn_stats(const float* x1, int c1, const float* x2, int c2, in
 
 cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups,
                             const float* part, float eps, const float* gamma, const float* beta, const float* ss,
-                            int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s) {
+                            int silu, float* y, __nv_bfloat16* yb, int parts, __nv_bfloat16* rawb, cudaStream_t s, int64_t ss_bstride) {
   const int C = c1 + c2;
   if (C % (4 * groups) || c1 % 4 || groups > 32 || C / 4 > 256) return cudaErrorInvalidValue;
   const int V = C / 4;
@@ -697,13 +697,13 @@ cudaError_t launch_gn_apply(const float* x1, int c1, const float* x2, int c2, in
   dim3 grid((T + slab - 1) / slab, B);
   const int chunk_rows = gn_chunk_rows(B, T);
   return launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, s, 1, x1, c1, x2, c2, T, groups, rpar, (T + chunk_rows - 1) / chunk_rows, slab, part, eps, gamma, beta, ss,
-                                           silu, y, yb, parts, rawb);
+                                           silu, y, yb, parts, rawb, (long long)ss_bstride);
 }
 
 // cudaErrorNotSupported when the slab of one (utterance, group) does not fit shared memory: use stats + apply then.
 cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
                             const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
-                            int parts, __nv_bfloat16* rawb, cudaStream_t s) {
+                            int parts, __nv_bfloat16* rawb, cudaStream_t s, int64_t ss_bstride) {
   const int C = c1 + c2;
   if (C % (4 * groups) || c1 % 4 || groups > 32) return cudaErrorInvalidValue;
   const int cg = C / groups, q = cg / 4;
@@ -715,7 +715,7 @@ cudaError_t launch_gn_fused(const float* x1, int c1, const float* x2, int c2, in
     if (e != cudaSuccess) return e;
   }
   return launch_pdl(gn_fused_kernel, dim3(groups, B), dim3(GNF_THREADS), smem, s, 1, x1, c1, x2, c2, T, groups, eps, gamma, beta, ss,
-                    silu, y, yb, parts, rawb);
+                    silu, y, yb, parts, rawb, (long long)ss_bstride);
 }
 
 // Cluster single-pass GroupNorm.  cudaErrorNotSupported when even an eighth of the slab does not fit shared memory.
@@ -723,7 +723,7 @@ namespace {
 template <int PARTS, bool SILU, bool SS, bool RAW>
 cudaError_t launch_gnc(dim3 grid, size_t smem, int cl, cudaStream_t s, const float* x1, int c1, const float* x2, int c2, int T, int groups,
                        int n_items, int tc, float eps, const float* gamma, const float* beta, const float* ss, float* y, __nv_bfloat16* yb,
-                       __nv_bfloat16* rawb) {
+                       __nv_bfloat16* rawb, long long ss_b) {
   static unsigned long long configured = 0;
   if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(gn_cluster_kernel<PARTS, SILU, SS, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -732,7 +732,7 @@ cudaError_t launch_gnc(dim3 grid, size_t smem, int cl, cudaStream_t s, const flo
     if (e != cudaSuccess) return e;
   }
   return launch_pdl(gn_cluster_kernel<PARTS, SILU, SS, RAW>, grid, dim3(GNC_THREADS), smem, s, cl, x1, c1, x2, c2, T, groups, n_items, tc, eps,
-                    gamma, beta, ss, y, yb, rawb);
+                    gamma, beta, ss, y, yb, rawb, ss_b);
 }
 template <int PARTS, typename... A>
 cudaError_t launch_gnc_flags(bool silu, bool has_ss, bool raw, A... a) {
@@ -752,8 +752,9 @@ cudaError_t launch_gnc_flags(bool silu, bool has_ss, bool raw, A... a) {
 }  // namespace
 cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, int B, int T, int groups, float eps,
                               const float* gamma, const float* beta, const float* ss, int silu, float* y, __nv_bfloat16* yb,
-                              int parts, __nv_bfloat16* rawb, cudaStream_t s) {
+                              int parts, __nv_bfloat16* rawb, cudaStream_t s, int64_t ss_bstride) {
   const int C = c1 + c2;
+  const long long ss_b = (long long)ss_bstride;
   if (C % (4 * groups) || c1 % 4 || groups > 32 || B <= 0 || T <= 0) return cudaErrorInvalidValue;
   if (yb ? (parts < 1 || parts > 3) : (y == nullptr)) return cudaErrorInvalidValue;
   const int cg = C / groups, q = cg / 4;
@@ -775,10 +776,10 @@ cudaError_t launch_gn_cluster(const float* x1, int c1, const float* x2, int c2, 
   const int n_clusters = (n_items + rounds - 1) / rounds;
   const dim3 grid(n_clusters * cl);
   const bool raw = yb && rawb;
-  if (!yb) return launch_gnc_flags<0>(silu != 0, ss != nullptr, false, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
-  if (parts == 1) return launch_gnc_flags<1>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
-  if (parts == 2) return launch_gnc_flags<2>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
-  return launch_gnc_flags<3>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb);
+  if (!yb) return launch_gnc_flags<0>(silu != 0, ss != nullptr, false, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb, ss_b);
+  if (parts == 1) return launch_gnc_flags<1>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb, ss_b);
+  if (parts == 2) return launch_gnc_flags<2>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb, ss_b);
+  return launch_gnc_flags<3>(silu != 0, ss != nullptr, raw, grid, smem, cl, s, x1, c1, x2, c2, T, groups, n_items, tc, eps, gamma, beta, ss, y, yb, rawb, ss_b);
 }
 
 // Wide rows (512 < C <= 2048; the Whisper encoder's 1280): one warp per row, the row held in registers (up to 16 float4 per lane),

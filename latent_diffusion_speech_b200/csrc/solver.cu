@@ -201,6 +201,51 @@ __global__ void q_sample_kernel(float* __restrict__ x, const float* __restrict__
   }
 }
 
+// Training-loss forward (diffusion.py:173-187): partial sums of |noise - eps| (l1) or (noise - eps)^2 (l2) over 32 x 32 tiles, eps in the
+// channels-last layout [B,T,M], noise in the reference layout [B,M,T] (read through shared memory like the DDPM step).  One partial
+// per block, reduced in a fixed order: the result does not depend on scheduling.
+__global__ void loss_partial_kernel(const float* __restrict__ eps, const float* __restrict__ noise, int T, int M, int l1,
+                                    double* __restrict__ partial) {
+  __shared__ float tile[32][33];
+  __shared__ double wsum[8];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const float* nz = noise + (size_t)b * M * T;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int m = m0 + j, t = t0 + threadIdx.x;
+    if (m < M && t < T) tile[j][threadIdx.x] = nz[(size_t)m * T + t];
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, m = m0 + threadIdx.x;
+    if (t < T && m < M) {
+      const float d = tile[threadIdx.x][j] - eps[((size_t)b * T + t) * M + m];
+      acc += l1 ? (double)fabsf(d) : (double)d * (double)d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x == 0) wsum[threadIdx.y] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    double v = 0.0;
+    for (int w = 0; w < (int)blockDim.y; ++w) v += wsum[w];
+    partial[(size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = v;
+  }
+}
+__global__ void loss_final_kernel(const double* __restrict__ partial, int n, double inv_count, float* __restrict__ out) {
+  __shared__ double ts[256];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) v += partial[i];
+  ts[threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 256; ++i) tot += ts[i];
+    *out = (float)(tot * inv_count);
+  }
+}
+
 __global__ void div_copy_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t n, float d) {
   LDS_VEC4_LOOP(n) {
     const float4 a = in[i];
@@ -316,6 +361,13 @@ cudaError_t launch_q_sample(float* x, const float* gt_BTM, const float* noise_BM
                             float sqrt_1m_acp, int B, int T, int M, cudaStream_t s) {
   dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
   q_sample_kernel<<<grid, block, 0, s>>>(x, gt_BTM, noise_BMT, acoustic_scale, sqrt_acp, sqrt_1m_acp, T, M);
+  return cudaGetLastError();
+}
+cudaError_t launch_diffusion_loss(const float* eps_BTM, const float* noise_BMT, int B, int T, int M, int l1, double* partial, float* loss,
+                                  cudaStream_t s) {
+  dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
+  loss_partial_kernel<<<grid, block, 0, s>>>(eps_BTM, noise_BMT, T, M, l1, partial);
+  loss_final_kernel<<<1, 256, 0, s>>>(partial, (int)(grid.x * grid.y * grid.z), 1.0 / ((double)B * T * M), loss);
   return cudaGetLastError();
 }
 cudaError_t launch_ddim_step(float* x, const float* eps, float sqrt_at, float coef, float sqrt_aprev, int64_t n, cudaStream_t s) {

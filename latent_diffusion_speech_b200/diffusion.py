@@ -120,15 +120,47 @@ class GaussianDiffusion(nn.Module):
         eng.plan(b, t_frames, kind, t_sin, rows, key=(b, t_frames, method, int(infer_speedup), int(t_total)))
         return kind, t_sin
 
+    @torch.no_grad()
+    def _loss_forward(self, gt_btm, t, cond_bth, noise_b1mt, loss_type="l2", return_eps=False):
+        """The training-loss forward on the library: gt_btm [B,T,M] UN-normalised frames (the library applies norm_spec), t [B] int64,
+        cond_bth [B,T,n_hidden], noise [B,1,M,T]."""
+        if loss_type not in ("l1", "l2"):
+            raise NotImplementedError()
+        if self._engine_provider is None:
+            raise RuntimeError("GaussianDiffusion is not attached to a Unit2Mel engine")
+        b, t_frames, m = gt_btm.shape
+        device = gt_btm.device
+        eng = self._engine_provider(device)
+        self.prepare(eng, b, t_frames, "dpm-solver", max(2, self.k_step // 2), self.k_step)       # any program: the plan owns the workspace
+        tc = t.detach().to("cpu").long()
+        t_sin = st.timestep_sinusoid(tc.float(), self.denoise_fn.block_out_channels[0]).numpy()    # Timesteps on an int64 t (diffusion.py:177)
+        sa = self.sqrt_alphas_cumprod.detach().to("cpu")[tc].numpy()               # extract(..., t, shape), diffusion.py:171
+        sb = self.sqrt_one_minus_alphas_cumprod.detach().to("cpu")[tc].numpy()
+        return eng.train_loss(cond_bth, gt_btm, noise_b1mt.reshape(b, m, t_frames), t_sin, sa, sb, loss_type, return_eps)
+
+    def p_losses(self, x_start, t, cond, noise=None, loss_type="l2", return_eps=False):
+        """diffusion.py:173-187, FORWARD only: x_start [B,1,M,T] (already norm_spec'ed), t [B] int64, cond [B,n_hidden,T] -> 0-dim
+        loss on the library (per-utterance q_sample, one denoiser evaluation with per-utterance timesteps, l1 / l2 against the
+        noise).  No autograd graph is built: this is the validation loss of diffusion/solver.py:56-62, not a training step."""
+        nz = torch.randn_like(x_start) if noise is None else noise.to(x_start.device)      # diffusion.py:174
+        gt_btm = self.denorm_spec(x_start[:, 0]).transpose(1, 2).contiguous()              # exact for acoustic_scale == 1 (the config's value)
+        return self._loss_forward(gt_btm, t, cond.transpose(1, 2).contiguous(), nz, loss_type, return_eps)
+
     def forward(self, condition, gt_spec=None, infer=True, infer_speedup=10, method="dpm-solver", k_step=None,
-                use_tqdm=False, noise=None, step_noise=None):
-        """condition [B,T,n_hidden] -> mel [B,T,out_dims]  (diffusion.py:189-343, infer branch).
+                use_tqdm=False, noise=None, step_noise=None, t=None):
+        """condition [B,T,n_hidden] -> mel [B,T,out_dims]  (diffusion.py:189-343, infer branch); with ``infer=False`` the training
+        loss FORWARD (diffusion.py:193-201 -> p_losses), a 0-dim tensor without autograd graph.
 
         ``noise`` ([B,1,M,T]) / ``step_noise`` (callable j0,j1 -> [j1-j0,B,1,M,T]) optionally replace the
-        ``torch.randn`` draws so that callers can make results independent of batch composition."""
+        ``torch.randn`` draws so that callers can make results independent of batch composition; ``t`` ([B] int64) replaces the
+        ``torch.randint`` draw of the training branch."""
         if not infer:
-            raise NotImplementedError(
-                "training (infer=False) is outside the B200 sampling path; use the reference PyTorch modules")
+            b, device = condition.shape[0], condition.device
+            t_max = self.k_step if k_step is None else k_step
+            tt = torch.randint(0, t_max, (b,), device=device).long() if t is None else t.to(device).long()
+            shape = (b, 1, self.out_dims, condition.shape[1])
+            nz = torch.randn(shape, device=device) if noise is None else noise.to(device)       # randn_like(x_start), diffusion.py:174
+            return self._loss_forward(gt_spec.contiguous(), tt, condition, nz)                 # norm_spec + q_sample + unet + mse in the library
         if self._engine_provider is None:
             raise RuntimeError("GaussianDiffusion is not attached to a Unit2Mel engine")
         b, t_frames, device = condition.shape[0], condition.shape[1], condition.device

@@ -97,11 +97,24 @@ class Unit2Mel(nn.Module):
 
     # ---- reference interface ----------------------------------------------------------------
     def forward(self, units, volume, spk_id=None, aug_shift=None, gt_spec=None, infer=True, infer_speedup=10,
-                method="unipc", use_tqdm=False, k_step=None, noise=None, step_noise=None):
-        """units [B,T,input_channel], spk_id [B,1] int64 -> mel [B,T,out_dims] (unit2mel.py:73-89)."""
+                method="unipc", use_tqdm=False, k_step=None, noise=None, step_noise=None, t=None):
+        """units [B,T,input_channel], spk_id [B,1] int64 -> mel [B,T,out_dims] (unit2mel.py:73-89).  ``infer=False`` returns the training
+        loss of ``p_losses`` (diffusion.py:173-201) as a 0-dim tensor computed FORWARD-only on the library — the validation loss of
+        diffusion/solver.py:56-62; there is no autograd graph, backward and optimiser steps stay with the reference (``t`` / ``noise``
+        optionally replace its ``randint`` / ``randn_like`` draws)."""
         if not infer:
-            raise NotImplementedError(
-                "training (infer=False) is outside the B200 sampling path; use the reference PyTorch modules")
+            if gt_spec is None:
+                raise ValueError("infer=False needs gt_spec")
+            if not (volume is None or self.is_tts):
+                raise NotImplementedError("volume_embed is None in the reference (unit2mel.py:56); pass volume=None")
+            if not units.is_cuda:
+                raise RuntimeError("Unit2Mel runs on a CUDA device only (no CPU fallback): move inputs to cuda")
+            eng = self._get_engine(units.device)
+            with torch.no_grad():
+                b, t_frames, _ = units.shape
+                self.decoder.prepare(eng, b, t_frames, "dpm-solver", max(2, self.decoder.k_step // 2), self.decoder.k_step)
+                cond = eng.cond(units, spk_id if (self.n_spk is not None and self.n_spk > 1) else None)
+                return self.decoder(cond, gt_spec=gt_spec, infer=False, k_step=k_step, noise=noise, t=t)
         if not (volume is None or self.is_tts):
             raise NotImplementedError("volume_embed is None in the reference (unit2mel.py:56); pass volume=None")
         if not units.is_cuda:

@@ -108,6 +108,27 @@ def main():
                                 torch_version=torch.__version__)
             print(name, tuple(eps.shape), float(eps.abs().max()))
 
+        # training-loss forward (Unit2Mel.forward(infer=False), unit2mel.py:73-89 -> diffusion.py:193-201 -> p_losses :173-187): the
+        # reference's own forward with its randint (timesteps) and randn_like (noise) draws replaced by seeded ones
+        for name, B, T, tvals in [("trainloss_b2_t40", 2, 40, [17, 903]), ("trainloss_b3_t37", 3, 37, [0, 999, 412])]:
+            if os.path.exists(os.path.join(GOLDEN_DIR, name + ".npz")) and "--force" not in sys.argv:
+                continue
+            units, spk, noise, _, gt = O.synthetic_inputs(B, T, gt=True)
+            tt = torch.tensor(tvals, dtype=torch.long)
+            orig_randint = torch.randint
+            torch.randint = lambda *a, **k: tt.clone()
+            try:
+                with inject_randn([noise]):
+                    loss = model(units, None, spk_id=spk, gt_spec=gt, infer=False)
+            finally:
+                torch.randint = orig_randint
+            cond = (model.unit_embed(units) + model.spk_embed(spk - 1)).transpose(1, 2)
+            spec = model.decoder.norm_spec(gt).transpose(1, 2)[:, None]
+            loss_l1 = model.decoder.p_losses(spec, tt, cond=cond, noise=noise, loss_type="l1")
+            np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), B=B, T=T, t=np.array(tvals), weight_seed=WEIGHT_SEED,
+                                weights_sha256=csum, loss_l2=float(loss), loss_l1=float(loss_l1), torch_version=torch.__version__)
+            print(name, "l2", float(loss), "l1", float(loss_l1))
+
 
 if __name__ == "__main__":
     main()

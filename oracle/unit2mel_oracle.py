@@ -481,6 +481,31 @@ def unit2mel_infer(sd: Dict[str, Tensor], cfg: dict, units: Tensor, spk_id: Opti
     return x.squeeze(1).transpose(1, 2) / scale
 
 
+def unit2mel_train_loss(sd: Dict[str, Tensor], cfg: dict, units: Tensor, spk_id: Optional[Tensor], gt_spec: Tensor, t: Tensor, noise: Tensor,
+                        loss_type: str = "l2", dtype=None, return_eps: bool = False):
+    """Unit2Mel.forward(infer=False) -> scalar loss (unit2mel.py:73-89 -> diffusion.py:193-201 -> p_losses :173-187) with the
+    ``randint`` timesteps t [B] (int64) and the ``randn_like`` noise [B,1,M,T] injected."""
+    if dtype is not None:
+        sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+        units, noise, gt_spec = units.to(dtype), noise.to(dtype), gt_spec.to(dtype)
+    buf = diffusion_buffers()
+    cond = unit2mel_cond(sd, units, spk_id, cfg.get("n_spk")).transpose(1, 2)      # [B,H,T]
+    x_start = (gt_spec * cfg.get("acoustic_scale", 1.0)).transpose(1, 2)[:, None, :, :]
+    tt = t.to("cpu").long()
+    sa = buf["sqrt_alphas_cumprod"][tt].reshape(-1, 1, 1, 1).to(device=x_start.device, dtype=x_start.dtype)       # extract (diffusion.py:18-21)
+    sb = buf["sqrt_one_minus_alphas_cumprod"][tt].reshape(-1, 1, 1, 1).to(device=x_start.device, dtype=x_start.dtype)
+    x_noisy = sa * x_start + sb * noise                                              # q_sample (diffusion.py:169-171)
+    denoise_input = torch.cat([x_noisy[:, 0, :, :], cond], dim=-2)
+    x_recon = unet_forward(sd, cfg, denoise_input, t.to(x_start.device))[:, None, :, :]
+    if loss_type == "l1":
+        loss = (noise - x_recon).abs().mean()
+    elif loss_type == "l2":
+        loss = F.mse_loss(noise, x_recon)
+    else:
+        raise NotImplementedError()
+    return (loss, x_recon[:, 0]) if return_eps else loss
+
+
 def synthetic_inputs(B: int, T: int, seed: int = 7, in_dims: int = 1280, n_spk: int = 323, out_dims: int = 128,
                      noise_seed: int = 1000, n_step_noises: int = 0, gt: bool = False):
     """SURVEY.md §8(d) synthetic inputs with per-utterance seeded noise (shard-invariant)."""

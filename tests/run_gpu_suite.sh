@@ -15,6 +15,6 @@ timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 1200 python bench.py --steps ${BENCH_STEPS:-3} --warmup 3 ${BENCH_FLAGS} > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench rc=$?" >> gpurun_out/bench.log
-timeout 600 python bench.py --steps 2 --warmup 3 --workload dpm20_b64_t864_bf16 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units > gpurun_out/bench_bf16.log 2>&1
+timeout 600 python bench.py --steps 2 --warmup 3 --workload dpm20_b64_t864_bf16 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units --no-train-loss > gpurun_out/bench_bf16.log 2>&1
 echo "bench_bf16 rc=$?" >> gpurun_out/bench_bf16.log
 tail -5 gpurun_out/kernels.log; tail -5 gpurun_out/parity.log; tail -15 gpurun_out/parity_configs.log; tail -3 gpurun_out/smoke.log; tail -c 1500 gpurun_out/bench.log; tail -c 600 gpurun_out/bench.err; tail -c 800 gpurun_out/bench_bf16.log

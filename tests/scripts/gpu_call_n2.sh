@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus.txt
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err; echo n2 rc=$?; tail -1 gpurun_out/bench_n2.log | cut -c1-300
-timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-vocoder --no-units > gpurun_out/bench_n1.log 2> gpurun_out/bench_n1.err; echo n1 rc=$?; tail -1 gpurun_out/bench_n1.log | cut -c1-200
+timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-vocoder --no-units --no-train-loss > gpurun_out/bench_n1.log 2> gpurun_out/bench_n1.err; echo n1 rc=$?; tail -1 gpurun_out/bench_n1.log | cut -c1-200
 python - <<'PY'
 import json
 for f in ("bench_n1","bench_n2"):

@@ -7,7 +7,7 @@ timeout 1500 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_ou
 timeout 400 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo smoke rc=$?; grep "^smoke" gpurun_out/smoke.log
 T0=$(date +%s); timeout 900 python bench.py > gpurun_out/bench.log 2>gpurun_out/bench.err; echo bench rc=$? wall $(( $(date +%s) - T0 )) s; tail -1 gpurun_out/bench.log | cut -c1-200
 T0=$(date +%s); timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.log 2>&1; echo bench_reference rc=$? wall $(( $(date +%s) - T0 )) s; tail -1 gpurun_out/bench_reference.log | cut -c1-300
-F="--no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units"
+F="--no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units --no-train-loss"
 for w in dpm20_b64_t864_bf16 unipc10_b64_t864_bf16 shallow_dpm20_b32_t2584_fp32 shallow_dpm20_b32_t2584_bf16 dpm20_b1_t432_fp32 ddim20_b64_t864_fp32 pndm20_b64_t864_fp32; do
 timeout 400 python bench.py --workload $w --steps 2 --warmup 3 $F > gpurun_out/bench_$w.log 2>&1; echo $w rc=$?; tail -1 gpurun_out/bench_$w.log | cut -c1-140
 done

@@ -2,10 +2,10 @@
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_solver_kernels.py -q -m gpu -x -p no:cacheprovider 2>&1 | tail -3
 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -p no:cacheprovider 2>&1 | tail -3
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units > gpurun_out/bench.log 2>gpurun_out/bench.err
-python bench.py --steps 2 --warmup 3 --workload dpm20_b64_t864_bf16 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units > gpurun_out/bench_bf16.log 2>&1
-python bench.py --steps 2 --warmup 2 --workload shallow_dpm20_b32_t2584_fp32 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units > gpurun_out/bench_t2584.log 2>&1
-python bench.py --steps 3 --warmup 2 --workload dpm20_b1_t432_fp32 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units > gpurun_out/bench_b1.log 2>&1
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units --no-train-loss > gpurun_out/bench.log 2>gpurun_out/bench.err
+python bench.py --steps 2 --warmup 3 --workload dpm20_b64_t864_bf16 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units --no-train-loss > gpurun_out/bench_bf16.log 2>&1
+python bench.py --steps 2 --warmup 2 --workload shallow_dpm20_b32_t2584_fp32 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units --no-train-loss > gpurun_out/bench_t2584.log 2>&1
+python bench.py --steps 3 --warmup 2 --workload dpm20_b1_t432_fp32 --no-cpu-baseline --no-gpu-eager --no-strong --no-vocoder --no-units --no-train-loss > gpurun_out/bench_b1.log 2>&1
 for f in bench bench_bf16 bench_t2584 bench_b1; do python - <<PY
 import json
 try:

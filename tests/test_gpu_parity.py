@@ -73,7 +73,7 @@ def _fp64_reference(name, state_dict, units, spk, noise, method, speedup, gt, k_
 
 
 @pytest.mark.parametrize("precision", FP32_MODES)
-@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("nfe_", "vocoder_", "units_"))])
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("nfe_", "vocoder_", "units_", "trainloss_"))])
 def test_sampler_vs_reference_golden(name, precision, host_model, state_dict):
     gpu_model = gpu_model_for(host_model, precision)
     g = load_golden(name)

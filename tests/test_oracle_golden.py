@@ -6,7 +6,7 @@ import torch
 from conftest import golden_names, load_golden
 from oracle import unit2mel_oracle as O
 
-CASES = [n for n in golden_names() if not n.startswith(("nfe_", "vocoder_", "units_"))]
+CASES = [n for n in golden_names() if not n.startswith(("nfe_", "vocoder_", "units_", "trainloss_"))]
 FAST = ["dpm8_b1_t24", "unipc10_b2_t37", "ddpm12_b2_t24", "shallow_dpm20_b2_t32", "shallow_ddim10_b2_t37", "shallow_pndm10_b1_t37"]
 
 
