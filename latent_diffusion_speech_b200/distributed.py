@@ -6,6 +6,10 @@ replicated, and there is NO collective inside the step loop.  The only exchange 
 ``all_gather`` of the ``[B/G, T, out_dims]`` mel shards (NCCL over NVLink 5 / NVSwitch on the GPU
 box; the same code runs over ``gloo`` in the CPU tests).  The reference has no inference-time
 parallelism at all (tools/infer_tools.py:14 is single-device).
+
+``sharded_train_loss`` is the data-parallel form of the training-loss FORWARD (``forward(infer=False)``): every rank evaluates the
+squared-error sum of its shard and ONE ``all_reduce`` of two scalars (sum, count) gives the global mean — the loss a data-parallel
+trainer would log (the reference's DDP path, 20_train_diffusion.py, averages gradients; there is no backward pass in this package).
 """
 from __future__ import annotations
 
@@ -70,3 +74,28 @@ def sharded_infer(model, units: torch.Tensor, spk_id: Optional[torch.Tensor], *,
             out_dims = model.decoder.out_dims
         mel = torch.zeros((0, units.shape[1], out_dims), dtype=torch.float32, device=units.device)
     return gather_mels(mel, n, group) if gather else mel
+
+
+def sharded_train_loss(model, units: torch.Tensor, spk_id: Optional[torch.Tensor], gt_spec: torch.Tensor, *,
+                       t: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                       group: Optional[dist.ProcessGroup] = None, **forward_kwargs) -> torch.Tensor:
+    """Global-batch mean of the diffusion loss: ``model(units[lo:hi], ..., gt_spec=gt_spec[lo:hi], infer=False)`` on this rank's slice,
+    weighted by its element count, then one ``all_reduce(SUM)`` of (weighted loss, count).  All inputs are given for the GLOBAL batch
+    (``t`` [B] int64 and ``noise`` [B,1,M,T] make the result independent of the number of ranks); a rank with an empty shard
+    contributes (0, 0).  Returns a 0-dim tensor equal on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = units.shape[0]
+    for name, x in (("spk_id", spk_id), ("gt_spec", gt_spec), ("t", t), ("noise", noise)):
+        if x is not None and x.shape[0] != n:
+            raise ValueError(f"{name} has {x.shape[0]} rows, expected the global batch size {n}")
+    lo, hi = shard_bounds(n, world, rank)
+    acc = torch.zeros(2, dtype=torch.float64, device=units.device)
+    if hi > lo:
+        loss = model(units[lo:hi], None, spk_id=None if spk_id is None else spk_id[lo:hi], gt_spec=gt_spec[lo:hi], infer=False,
+                     t=None if t is None else t[lo:hi], noise=None if noise is None else noise[lo:hi], **forward_kwargs)
+        count = float((hi - lo) * gt_spec.shape[1] * gt_spec.shape[2])
+        acc[0], acc[1] = loss.double() * count, count
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    return (acc[0] / acc[1]).float()

@@ -10,3 +10,4 @@ for f in ("bench_n1","bench_n2"):
     d=json.loads([l for l in open(f"gpurun_out/{f}.log") if l.startswith("{")][-1])
     print(f, "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "strong", round(d["strong"]["value"]), d["strong"]["sha256_utt0"], d["strong"]["sha256_utt_last"])
 PY
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tests/gpu_dp_loss_check.py > gpurun_out/dp_loss_n2.log 2>&1; echo dp_loss rc=$?; grep "dp loss" gpurun_out/dp_loss_n2.log

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from latent_diffusion_speech_b200.distributed import gather_mels, shard_bounds, sharded_infer
+from latent_diffusion_speech_b200.distributed import gather_mels, shard_bounds, sharded_infer, sharded_train_loss
 
 
 def test_shard_bounds_cover_batch():
@@ -71,3 +71,40 @@ def test_sharded_infer_rejects_mismatched_global_inputs():
     units = torch.randn(4, 6, 16)
     with pytest.raises(ValueError):
         sharded_infer(_FakeModel(), units, torch.ones(4, 1, dtype=torch.long), noise=torch.randn(4, 1, 8, 6), gt_spec=torch.randn(3, 6, 8))
+
+
+class _FakeLossModel:
+    """Stands in for Unit2Mel.forward(infer=False): the mean of a per-element function over the local shard."""
+
+    def __call__(self, units, volume, spk_id=None, gt_spec=None, infer=False, t=None, noise=None, **kw):
+        assert not infer and gt_spec.shape[0] == units.shape[0] == t.shape[0] == noise.shape[0]
+        err = noise[:, 0].transpose(1, 2) - gt_spec * t.float()[:, None, None] * 1e-3 + spk_id.float()[:, :, None]
+        return (err * err).mean()
+
+
+def _loss_worker(rank, world, port, n_items, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)
+        units = torch.randn(n_items, 6, 16, generator=g)
+        spk = torch.randint(1, 9, (n_items, 1), generator=g)
+        gt = torch.randn(n_items, 6, 8, generator=g)
+        t = torch.randint(0, 1000, (n_items,), generator=g)
+        noise = torch.randn(n_items, 1, 8, 6, generator=g)
+        got = sharded_train_loss(_FakeLossModel(), units, spk, gt, t=t, noise=noise)
+        want = _FakeLossModel()(units, None, spk_id=spk, gt_spec=gt, t=t, noise=noise)
+        ret[rank] = bool(abs(float(got) - float(want)) <= 1e-6 * abs(float(want)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [4, 5, 1])
+def test_sharded_train_loss_equals_global_mean_world2(n_items):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_loss_worker, args=(2, port, n_items, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
