@@ -86,3 +86,28 @@ def test_dilated_conv1d_tc_vs_fp64(taps, dil, cin, N, rows, batches, epi):
     e = G.errs(out.cpu(), ref)
     G.report(test="dilated_conv1d_tc", taps=taps, dil=dil, cin=cin, N=N, **e)
     assert e["rel_l2"] <= 5e-6 and e["max_abs"] <= 4e-5, e      # measured 0.3-2.5e-6 (K = 384 ... 2816: truncating fp32 accumulate in TMEM)
+
+
+@pytest.mark.parametrize("c0,rates,ksizes", [(256, [4, 3], [8, 7]),        # GEMM conv_pre + up 0, 128-ch level on gemm_tc, FFMA up 1 (odd stride), 64-ch level on gemm_tc (N = 64)
+                                            (192, [4, 3], [8, 7]),        # GEMM conv_pre + up 0, 96-ch and 48-ch levels on the CUDA cores
+                                            (128, [2, 2, 2], [4, 4, 4])]) # 64-, 32- (time-folded) and 16-channel (fold 4) levels, every layer but conv_post a GEMM
+def test_vocoder_mixed_layer_forms_vs_fp64(c0, rates, ksizes):
+    """Generator layouts other than HiFi-GAN V1 exercise every transition between the tensor-core (channels-last) and CUDA-core
+    (channels-first) forms of vocoder.cu, the FFMA fallback of the transposed convolution, and time folding by 2 and by 4."""
+    from latent_diffusion_speech_b200.vocoder import Generator
+    h = dict(V.DEFAULT_H, upsample_initial_channel=c0, upsample_rates=rates, upsample_kernel_sizes=ksizes,
+             resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]])
+    torch.manual_seed(99)
+    gen = Generator(h).eval()
+    sd64 = {k: v.detach().double() for k, v in gen.state_dict().items()}
+    z = V.synthetic_latents(2, 21, h["inter_channels"], seed=3)
+    wav = gen.cuda().decode_frames(z.cuda()).cpu()
+    with torch.no_grad():
+        ref64 = V.vocoder_infer(sd64, h, z.double())
+    e = G.errs(wav, ref64)
+    G.report(test="vocoder_mixed_forms", c0=c0, rates=str(rates), **e)
+    hop = 1
+    for u in rates:
+        hop *= u
+    assert wav.shape == (2, 1, 21 * hop)
+    assert e["max_abs"] <= 2e-6 and e["rel_l2"] <= 1e-5, e
