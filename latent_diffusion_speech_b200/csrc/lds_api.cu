@@ -111,6 +111,7 @@ const Knobs& knobs() {
     v.gn_mode = env_int("LDS_GN_MODE", 2);
     v.pdl = env_int("LDS_PDL", 1) != 0;
     v.tma_epi = env_int("LDS_TMA_EPI", 1) != 0;
+    v.red_add = env_int("LDS_RED_ADD", 1) != 0;
     return v;
   }();
   return k;

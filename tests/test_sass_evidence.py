@@ -18,7 +18,7 @@ def sass_counts():
         pytest.skip("cuobjdump not available")
     out = subprocess.run([exe, "-sass", build()], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout.decode()
     assert "sm_100a" in out, "liblds_b200.so carries no sm_100a code"
-    return collections.Counter(re.findall(r"\b(UTCHMMA(?:\.2CTA)?|UTMALDG|UTMASTG|UTCBAR|LDTM|UCGABAR_ARV|UCGABAR_WAIT|LDGSTS)\b", out))
+    return collections.Counter(re.findall(r"\b(UTCHMMA(?:\.2CTA)?|UTMALDG|UTMASTG|UTMAREDG|UTCBAR|LDTM|UCGABAR_ARV|UCGABAR_WAIT|LDGSTS)\b", out))
 
 
 @pytest.mark.parametrize("mnemonic,what", [
@@ -26,6 +26,7 @@ def sass_counts():
     ("UTCHMMA.2CTA", "tcgen05.mma.cta_group::2 (CTA-pair GEMM tiles)"),
     ("UTMALDG", "TMA tensor loads"),
     ("UTMASTG", "TMA tensor stores (fp32 GEMM epilogue: result tiles leave through cp.async.bulk.tensor)"),
+    ("UTMAREDG", "TMA reduce-add stores (in-place residual GEMMs: C += tile through cp.reduce.async.bulk.tensor)"),
     ("UTCBAR", "tcgen05.commit -> mbarrier"),
     ("LDTM", "tcgen05.ld (TMEM accumulator read-out)"),
     ("UCGABAR_ARV", "barrier.cluster.arrive (cluster GroupNorm)"),
