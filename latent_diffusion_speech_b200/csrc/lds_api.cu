@@ -515,10 +515,9 @@ int run_unet(lds_handle* h, cudaStream_t s, const float* x, const float* temb_ro
     const int T = h->Tl[i];
     for (int j = 0; j < L; ++j) {
       float* sk = h->skips[si++];
-      if (!last) {
-        float* r_out = other_hid(h, cur, nullptr);
-        LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, nullptr, T, temb_row, r_out));
-        LDS_TRY(run_transformer(h, s, h->xfs[xi++], r_out, T, sk));
+      if (!last) {   // the transformer works IN PLACE on the resnet's output: its proj_out residual is then a TMA reduce-add (gemm_tc.cu)
+        LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, nullptr, T, temb_row, sk));
+        LDS_TRY(run_transformer(h, s, h->xfs[xi++], sk, T, sk));
       } else {
         LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, nullptr, T, temb_row, sk));
       }
@@ -536,9 +535,9 @@ int run_unet(lds_handle* h, cudaStream_t s, const float* x, const float* temb_ro
     float* a = h->hid[0];
     float* b = h->hid[1];
     LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, nullptr, T, temb_row, a));
-    LDS_TRY(run_transformer(h, s, h->xfs[xi++], a, T, b));
-    LDS_TRY(run_resnet(h, s, h->resnets[ri++], b, nullptr, T, temb_row, a));
-    cur = a;
+    LDS_TRY(run_transformer(h, s, h->xfs[xi++], a, T, a));
+    LDS_TRY(run_resnet(h, s, h->resnets[ri++], a, nullptr, T, temb_row, b));
+    cur = b;
   }
   for (int i = 0; i < nb; ++i) {
     const int lvl = nb - 1 - i;
@@ -549,11 +548,7 @@ int run_unet(lds_handle* h, cudaStream_t s, const float* x, const float* temb_ro
       float* r_out = other_hid(h, cur, nullptr);
       LDS_TRY(run_resnet(h, s, h->resnets[ri++], cur, skip, T, temb_row, r_out));
       cur = r_out;
-      if (i > 0) {
-        float* x_out = other_hid(h, cur, nullptr);
-        LDS_TRY(run_transformer(h, s, h->xfs[xi++], cur, T, x_out));
-        cur = x_out;
-      }
+      if (i > 0) LDS_TRY(run_transformer(h, s, h->xfs[xi++], cur, T, r_out));      // in place
     }
     if (!last) {
       const int t_up = h->Tl[lvl - 1];
