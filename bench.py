@@ -361,7 +361,7 @@ def units_leg(dev, B: int = 8, L: int = 3000) -> dict:
     T = (L - 1) // 2 + 1
     n_align = int(T * 320 / 16000 * FRAME_RATE)
 
-    def timed(fn, n=2, warm=1):
+    def timed(fn, n=3, warm=2):
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
