@@ -616,7 +616,11 @@ int lds_vocode(lds_vocoder* v, const float* mel_BTC, int B, int T, float* wav_BL
         for (int q = 0; q < nconv; ++q) {
           const int d = c.resblock_dilations[j][q];
           const bool last = q == nconv - 1;
-          float* dst = last ? (j == 0 ? xs_cl : lv[4]) : (cur == lv[2] ? lv[3] : lv[2]);
+          // resblock j keeps its running x in ONE buffer (xs_cl for j = 0, whose result starts the mean; lv[4] otherwise): the first
+          // convolution pair reads the level input x_cl as its residual, every later one updates the buffer in place — its residual is
+          // then a TMA reduce-add in gemm_tc (no residual load)
+          float* dst = j == 0 ? xs_cl : lv[4];
+          (void)last;
           VTRY(ck(launch_lrelu_split_cast(cur, a_p, rows, Cw, 2, 0.1f, s), "lrelu_split_cast"));
           auto rconv = [&](const __nv_bfloat16* A, const ConvP& w, int dil, int epi, const float* R, float* out_f32, __nv_bfloat16* out_planes) {
             return f > 1 ? conv_tc(A, Lw, Cw, w.ntaps, 1, w.wh, Cw, w.b_rep, epi, R, out_f32, out_planes, w.tap_off)
