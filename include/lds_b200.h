@@ -334,6 +334,11 @@ LDS_API int lds_units_log_mel(const float* audio_BL, int B, int L, const float* 
 /* out[b * out_per_batch + i, :] = table[b * in_per_batch + idx[i], :] (rows of C floats, C % 4 == 0; idx: device int64 [out_per_batch]).
  * units_forced_alignment 'nearest' / 'left' (tools/tools.py:193-223; idx = the source frame of every output frame, in_per_batch = input
  * frames) and EuclideanCodebook.dequantize / F.embedding (quantize/kmeans_codebook.py:29-31; n_batches = 1, in_per_batch = 0). */
+/* idx[m] = argmax_v -(|x_m|^2 - 2 x_m.e_v + |e_v|^2), the first index on ties: EuclideanCodebook.quantize / .encode
+ * (quantize/kmeans_codebook.py:15-23,37-46).  x [M, C], embed [V, C] (C % 16 == 0, V % 4 == 0); scratch: round_up(V, 64) + M * V floats
+ * on the device; idx: device int64 [M].  fp32 FFMA products (IEEE): the reference's fp32 matmul can only differ on near-ties. */
+LDS_API int lds_units_quantize(const float* x_MC, const float* embed_VC, int64_t M, int V, int C, float* scratch, int64_t* idx_out,
+                       void* stream);
 LDS_API int lds_units_gather_rows(const float* table, const int64_t* idx, int64_t n_batches, int64_t out_per_batch, int64_t in_per_batch,
                           int C, float* out, void* stream);
 

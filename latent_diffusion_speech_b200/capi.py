@@ -34,7 +34,7 @@ EXPORTS = [
     "lds_vocode", "lds_vocoder_hop", "lds_vocoder_launches", "lds_vocoder_last_flops", "lds_vocoder_workspace_bytes",
     "lds_units_last_error", "lds_units_create", "lds_units_destroy", "lds_units_load_weight", "lds_units_finalize", "lds_units_encode",
     "lds_units_out_frames", "lds_units_launches", "lds_units_last_flops", "lds_units_workspace_bytes", "lds_units_log_mel",
-    "lds_units_gather_rows",
+    "lds_units_gather_rows", "lds_units_quantize",
 ]
 
 
@@ -135,6 +135,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "lds_units_workspace_bytes": (C.c_int64, [vp]),
         "lds_units_log_mel": (i32, [vp, i32, i32, vp, i32, vp, vp, vp]),
         "lds_units_gather_rows": (i32, [vp, vp, i64, i64, i64, i32, vp, vp]),
+        "lds_units_quantize": (i32, [vp, vp, i64, i32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)           # AttributeError if the symbol is not exported

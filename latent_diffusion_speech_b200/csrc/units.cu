@@ -154,6 +154,37 @@ __global__ void gather_rows_kernel(const float4* __restrict__ table, const int64
   }
 }
 
+// EuclideanCodebook.quantize (quantize/kmeans_codebook.py:15-23): argmax_v -(|x|^2 - 2 x.e_v + |e_v|^2) = argmax_v (x.e_v - |e_v|^2 / 2).
+// half_norm[v] = -|e_v|^2 / 2 (the bias of the x E^T GEMM); one warp per codeword
+__global__ void codebook_half_norm_kernel(const float* __restrict__ embed, int V, int C, float* __restrict__ out) {
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (v >= V) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) { const float e = embed[(size_t)v * C + c]; s = fmaf(e, e, s); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[v] = -0.5f * s;
+}
+// first index of the row maximum (torch.max(dim=-1).indices semantics on ties); one warp per row
+__global__ void row_argmax_kernel(const float* __restrict__ score, int64_t M, int V, int64_t* __restrict__ idx) {
+  const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = lane; v < V; v += 32) {
+    const float x = score[m * V + v];
+    if (x > best) { best = x; bi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) idx[m] = bi;
+}
+
 struct BlockW {
   const __nv_bfloat16 *qkv_h = nullptr, *out_h = nullptr, *fc1_h = nullptr, *fc2_h = nullptr;
   const float *qkv_b = nullptr, *out_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
@@ -499,6 +530,26 @@ int lds_units_gather_rows(const float* table, const int64_t* idx, int64_t n_batc
       reinterpret_cast<const float4*>(table), idx, reinterpret_cast<float4*>(out), rows, C / 4, out_per_batch, in_per_batch);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? LDS_OK : ufail(LDS_ERR_CUDA, "lds_units_gather_rows: %s", cudaGetErrorString(e));
+}
+
+
+int lds_units_quantize(const float* x_MC, const float* embed_VC, int64_t M, int V, int C, float* scratch, int64_t* idx_out, void* stream) {
+  if (!x_MC || !embed_VC || !scratch || !idx_out || M < 0 || V < 1 || C < 16 || C % 16 || V % 4)
+    return ufail(LDS_ERR_INVALID, "lds_units_quantize: bad argument (C must be a multiple of 16, V of 4)");
+  if (M == 0) return LDS_OK;
+  if (M > 0x7fffffff) return ufail(LDS_ERR_UNSUPPORTED, "lds_units_quantize: more than 2^31 rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* half_norm = scratch;                         // [V], then the scores [M, V]
+  float* score = scratch + ((size_t)V + 63) / 64 * 64;
+  codebook_half_norm_kernel<<<(V * 32 + 255) / 256, 256, 0, s>>>(embed_VC, V, C, half_norm);
+  GemmArgs g;                                          // score = x E^T - |e|^2 / 2 on the fp32 FFMA kernel (IEEE products: index decisions)
+  g.A = x_MC; g.a_ld = C; g.W = embed_VC; g.C = score; g.c_ld = V; g.bias = half_norm; g.M = (int)M; g.N = V; g.K = C; g.taps = 1; g.cin = C;
+  g.t_out = g.t_in = g.t_conv = (int)M;
+  cudaError_t e = launch_gemm_f32(g, s);
+  if (e != cudaSuccess) return ufail(LDS_ERR_CUDA, "lds_units_quantize: gemm: %s", cudaGetErrorString(e));
+  row_argmax_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, s>>>(score, M, V, idx_out);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? LDS_OK : ufail(LDS_ERR_CUDA, "lds_units_quantize: %s", cudaGetErrorString(e));
 }
 
 }  // extern "C"

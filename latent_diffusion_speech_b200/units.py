@@ -5,13 +5,13 @@
 * ``ModelDimensions`` / ``sinusoids`` / ``AudioEncoder``   encoder/whisper/model.py:10-21,32-38,112-131
 * ``WhisperLargeV3`` / ``Units_Encoder.encode``   tools/tools.py:43-126
 * ``units_forced_alignment``                       tools/tools.py:193-223
-* ``EuclideanCodebook.decode``                     quantize/kmeans_codebook.py:29-31,44-46
+* ``EuclideanCodebook`` (encode / decode)          quantize/kmeans_codebook.py:6-52
 
 ``AudioEncoder`` keeps the reference's constructor, ``state_dict()`` keys / shapes and default random init (so
 ``torch.manual_seed(s); AudioEncoder(...)`` holds bit-identical parameters and a reference checkpoint loads strictly); its
 ``forward`` runs on the CUDA library (csrc/units.cu on the sampler's tcgen05 GEMM / attention / LayerNorm kernels).  There
 is no CPU fallback.  Resampling to 16 kHz (torchaudio ``Resample`` / librosa, tools/tools.py:78-95), the w2v-bert / xlsr
-encoders and ``EuclideanCodebook.quantize`` stay with the reference.
+encoders stay with the reference.
 """
 from __future__ import annotations
 
@@ -406,5 +406,27 @@ class EuclideanCodebook(nn.Module):
     def decode(self, embed_ind):
         return self.dequantize(embed_ind)
 
+    @torch.no_grad()
     def quantize(self, x):
-        raise NotImplementedError("nearest-codeword search stays with the reference (quantize/kmeans_codebook.py:15-23)")
+        """x [M, C] -> nearest codeword index [M] (kmeans_codebook.py:15-23) on the GPU: fp32 FFMA GEMM x E^T - |e|^2/2, row argmax."""
+        if not x.is_cuda:
+            raise RuntimeError("EuclideanCodebook.quantize runs on a CUDA device only (no CPU fallback)")
+        lib = load_library()
+        xx = x.float().contiguous()
+        emb = self.embed.to(device=xx.device, dtype=torch.float32).contiguous()
+        M, Cc = xx.shape
+        V = emb.shape[0]
+        scratch = torch.empty((V + 63) // 64 * 64 + M * V, device=xx.device, dtype=torch.float32)
+        idx = torch.empty(M, device=xx.device, dtype=torch.int64)
+        with torch.cuda.device(xx.device):
+            _ucheck(lib, lib.lds_units_quantize(C.c_void_p(xx.data_ptr()), C.c_void_p(emb.data_ptr()), M, V, Cc, C.c_void_p(scratch.data_ptr()),
+                                                C.c_void_p(idx.data_ptr()), _stream(xx.device)), "lds_units_quantize")
+        return idx
+
+    def encode(self, x):
+        """kmeans_codebook.py:37-46: flatten the leading dims, quantize, restore them."""
+        shape = x.shape
+        return self.quantize(x.reshape(-1, shape[-1])).view(*shape[:-1])
+
+    def forward(self, x):
+        return self.decode(self.encode(x))

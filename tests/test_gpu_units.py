@@ -167,3 +167,26 @@ def test_audio_to_units_wrapper_vs_golden():
     assert e["max_abs"] <= 5e-4, e
     with pytest.raises(NotImplementedError):
         ue.encode(torch.zeros(22050).cuda(), 22050)
+
+
+def test_codebook_quantize_and_roundtrip():
+    """EuclideanCodebook.encode / quantize (quantize/kmeans_codebook.py:15-23,37-46): nearest codeword on the GPU (fp32 FFMA GEMM + row
+    argmax).  Perturbed codewords must come back as themselves; on unstructured inputs the chosen codeword is the fp64 optimum up to
+    near-ties (its distance within 1e-5 relative of the best)."""
+    from latent_diffusion_speech_b200.units import EuclideanCodebook
+    gen = torch.Generator().manual_seed(12)
+    V, Cc = 2048, 1280
+    book = torch.randn(V, Cc, generator=gen)
+    cb = EuclideanCodebook(book.numpy()).cuda()
+    true = torch.randint(0, V, (3, 257), generator=gen)
+    x = book[true] + 0.05 * torch.randn(3, 257, Cc, generator=gen)
+    got = cb.encode(x.cuda()).cpu()
+    assert got.shape == true.shape and torch.equal(got, true)
+    assert torch.equal(cb(x.cuda()).cpu(), book[true])                    # forward = decode(encode(x))
+    y = torch.randn(500, Cc, generator=gen)
+    idx = cb.quantize(y.cuda()).cpu()
+    d = torch.cdist(y.double(), book.double()) ** 2
+    best, chosen = d.min(dim=1).values, d[torch.arange(500), idx]
+    agree = float((idx == d.argmin(dim=1)).float().mean())
+    G.report(test="units_codebook_quantize", agree=agree, worst_rel_excess=float(((chosen - best) / best).max()))
+    assert agree >= 0.99 and float(((chosen - best) / best).max()) <= 1e-5
