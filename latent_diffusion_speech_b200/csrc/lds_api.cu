@@ -112,6 +112,7 @@ const Knobs& knobs() {
     v.pdl = env_int("LDS_PDL", 1) != 0;
     v.tma_epi = env_int("LDS_TMA_EPI", 1) != 0;
     v.red_add = env_int("LDS_RED_ADD", 1) != 0;
+    v.ff2_inplace = env_int("LDS_FF2_INPLACE", 1) != 0;
     return v;
   }();
   return k;
@@ -447,8 +448,14 @@ int run_transformer_tc(lds_handle* h, cudaStream_t s, const XfW& w, const float*
   LDS_TRY(run_gemm_tc(h, s, f1));
   TcGemmArgs f2 = tc_base(h, h->ffh_b, 1, M, 4 * C, 1, w.ff2_h, w.ff2_b, C);
   f2.R = h->th; f2.r_ld = C;
-  tc_out_planes(h, f2, h->th_b, C);        // only proj_out consumes the block output
-  LDS_TRY(run_gemm_tc(h, s, f2));
+  if (knobs().ff2_inplace) {               // th += ff2(h) through the TMA reduce-add epilogue, then one cast pass for proj_out's operand
+    tc_out_f32(f2, h->th, C);
+    LDS_TRY(run_gemm_tc(h, s, f2));
+    LDS_TRY(run_cast(h, s, h->th, M, C, h->th_b));
+  } else {
+    tc_out_planes(h, f2, h->th_b, C);      // only proj_out consumes the block output
+    LDS_TRY(run_gemm_tc(h, s, f2));
+  }
   TcGemmArgs po = tc_base(h, h->th_b, 1, M, C, 1, w.proj_out.wh, w.proj_out.b, C);
   tc_out_f32(po, out, C);
   po.R = x; po.r_ld = C;
