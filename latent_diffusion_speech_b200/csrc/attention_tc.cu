@@ -83,8 +83,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // accumulator column block per B plane; the softmax / epilogue threads add the blocks.
 struct MmaItem { int a_plane, b_plane0, n_planes, blk; };
 
-// DUAL (split mode, d <= 32): two S accumulator blocks instead of three and 256 TMEM columns, so that two CTAs fit on
-// one SM and the softmax of one overlaps the tensor-pipe work of the other.
+// DUAL (split modes): 256 TMEM columns per CTA (and, with three bf16 planes, two S accumulator blocks instead of three), so
+// that two CTAs fit on one SM and the softmax of one overlaps the tensor-pipe work of the other.
 //
 // Ring depths are compile-time: NK / NV stages of the K / V^T rings (shared memory), NSB S buffers (TMEM), NPB P buffers (shared
 // memory).  PA = 2: a pass-A step covers two 64-key tiles (the two hi-plane tiles fill plane slots 0 and 1 of a K stage -> one
@@ -537,10 +537,16 @@ cudaError_t launch_attention_tc(const AttnTcArgs& a, cudaStream_t s) {
   if (a.parts == 2) {
     // split-f16 operands (h1, h2 of q, k, v^T; P split the same way): 2 S blocks (128 columns) + 2 O blocks (2*dpad columns).
     // d <= 32: two CTAs per SM (DUAL): 16 (Q) + 2*8 (K) + 2*8 (V^T) + 32 (P) = 80 KB, TMEM 128 + 64.
-    // d > 32: 112 KB + barriers is 1.3 KB too much for two CTAs per SM -> one CTA per SM with S and P double-buffered:
-    //         32 (Q) + 2*16 (K) + 2*16 (V^T) + 2*32 (P) = 160 KB, TMEM 2*128 (S) + 128 (O)
+    // d > 32: two CTAs per SM as well, with single-stage K and V^T rings — the second CTA's work covers the load
+    //         latency the ring would: 32 (Q) + 16 (K) + 16 (V^T) + 32 (P) = 96 KB, TMEM 128 (S) + 128 (O).  Two stages of
+    //         either ring (112 KB + barriers) is 1.3 KB too much for two CTAs per SM.  Measured against one CTA per SM with
+    //         S and P double-buffered (160 KB, TMEM 2*128 + 128; LDS_ATT_DUAL64=0): op time -6% at T=432, -1% at T=216,
+    //         attention -4.4% on the headline (profiles/r02_attention_dual64_call166.txt)
     if (a.dpad == 32) return launch_attn<32, 64, 2, true, 2, 2, 1, 1>(a, s);
-    if (a.dpad == 64) return launch_attn<64, 64, 2, false, 2, 2, 2, 2>(a, s);
+    if (a.dpad == 64) {
+      if (knobs().att_dual64) return launch_attn<64, 64, 2, true, 1, 1, 1, 1>(a, s);
+      return launch_attn<64, 64, 2, false, 2, 2, 2, 2>(a, s);
+    }
   } else if (a.parts == 3) {
     // three bf16 planes, six plane products (round 1's fp32-accurate form; kept for A/B through lds_op_qkv_attention_tc)
     if (a.dpad == 32) return launch_attn<32, 64, 3, true, 2, 1, 1, 1>(a, s);

@@ -111,6 +111,7 @@ const Knobs& knobs() {
     v.gn_mode = env_int("LDS_GN_MODE", 2);
     v.pdl = env_int("LDS_PDL", 1) != 0;
     v.tma_epi = env_int("LDS_TMA_EPI", 1) != 0;
+    v.att_dual64 = env_int("LDS_ATT_DUAL64", 1) != 0;
     v.red_add = env_int("LDS_RED_ADD", 1) != 0;
     v.ff2_inplace = env_int("LDS_FF2_INPLACE", 1) != 0;
     return v;

@@ -21,6 +21,7 @@ struct Knobs {
   bool pdl = true;      // LDS_PDL       programmatic dependent launch attribute on the hot kernels
   bool tma_epi = true;  // LDS_TMA_EPI   fp32 GEMM outputs through the TMA epilogue (0: per-thread ld.global / st.global epilogue)
   bool ff2_inplace = true;    // LDS_FF2_INPLACE  FF2 as an in-place fp32 reduce-add GEMM + one cast pass (0: 16-bit plane output with a register-path residual)
+  bool att_dual64 = true;     // LDS_ATT_DUAL64   split-f16 attention at head dim 33..64: two CTAs per SM with single-stage K / V^T rings (0: one CTA, double-buffered)
   bool red_add = true;  // LDS_RED_ADD   in-place residual GEMMs store through a TMA reduce-add (0: TMA-load the residual, add, TMA-store)
 };
 const Knobs& knobs();
