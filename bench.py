@@ -361,17 +361,24 @@ def units_leg(dev, B: int = 8, L: int = 3000) -> dict:
     T = (L - 1) // 2 + 1
     n_align = int(T * 320 / 16000 * FRAME_RATE)
 
-    def timed(fn, n=3, warm=2):
+    spread = {}
+
+    def timed(fn, n=3, warm=2, key=None):
+        """Median of n individually timed calls (a 25-60 ms call right after a power-capped leg sees clock dips that a short
+        mean would fold in); min / max of the samples are kept under `key`."""
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        ev[0].record()
+        for i in range(n):
             r = fn()
-        e1.record()
+            ev[i + 1].record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n, r
+        ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
+        if key:
+            spread[key] = {"ms_min": ms[0], "ms_max": ms[-1], "samples": n}
+        return ms[n // 2], r
 
     out = {"workload": f"whisper-large-v3 AudioEncoder (32 x 1280 x 20 heads, random init), B={B} x 30 s audio -> {T} units each -> "
                        f"{n_align} aligned frames", "unit": "units/s (encoder frames, 50 per second of audio)"}
@@ -379,11 +386,12 @@ def units_leg(dev, B: int = 8, L: int = 3000) -> dict:
     out["log_mel_ms"] = ms_mel
     for prec in ("fp32", "bf16"):
         enc.set_precision(prec)
-        ms, units = timed(lambda: enc(mel))
+        ms, units = timed(lambda: enc(mel), n=9, warm=3, key=prec)
         fl = enc._engine.last_flops
         out[prec] = {"ms_per_step": ms, "value": B * T / (ms * 1e-3), "tflops": fl / (ms * 1e-3) / 1e12, "launches_per_step": None,
                      "rtf": (ms * 1e-3) / (B * L * UN.HOP_LENGTH / 16000.0), "finite": bool(torch.isfinite(units).all()),
                      "arithmetic": "split-f16 tcgen05 (fp32-accurate, 3 MMAs per product)" if prec == "fp32" else "bf16 tcgen05"}
+        out[prec].update(spread[prec])
         n0 = enc._engine.kernel_launches
         enc(mel)
         out[prec]["launches_per_step"] = enc._engine.kernel_launches - n0
